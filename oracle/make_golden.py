@@ -1,0 +1,243 @@
+"""Regenerate tests/golden/*.pt by EXECUTING the reference (build container only).
+
+    python -m oracle.make_golden            # writes tests/golden/
+    python -m oracle.make_golden --check    # also asserts the oracle restatement is bit-identical
+
+Every fixture stores the seeded inputs (state, t_span, parameters) together with what the
+unmodified reference (/root/reference, imported through oracle/ref_shim.py) produced on CPU in
+fp32: t_eval, sol (or the rows the tests need), gradients, NFE and the per-attempt step trace
+(t, dt, error_ratio) captured from outside by wrapping the reference's own hooks.
+TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from oracle import erk_oracle as eo  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def mlp(dims, act="tanh", seed=0):
+    torch.manual_seed(seed)
+    acts = {"tanh": nn.Tanh, "softplus": nn.Softplus, "relu": nn.ReLU}
+    layers = []
+    for i in range(len(dims) - 1):
+        layers.append(nn.Linear(dims[i], dims[i + 1]))
+        if i < len(dims) - 2:
+            layers.append(acts[act]())
+    return nn.Sequential(*layers)
+
+
+def moons(n, seed=0):
+    """cfg-1 input: the reference's own ToyDataset moons generator (datasets/static_datasets.py:71-95)."""
+    ref_shim.load()
+    from torchdyn.datasets import ToyDataset
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    X, y = ToyDataset().generate(n, "moons", noise=0.4)
+    return X.float(), y.long()
+
+
+class VDP(nn.Module):
+    """Van der Pol oscillator, same dynamics as the reference test system (numerics/systems.py:32-41)."""
+    def __init__(self, alpha):
+        super().__init__()
+        self.alpha = alpha
+        self.p = nn.Parameter(torch.tensor([1.0]))  # so the adjoint has a parameter to differentiate
+
+    def forward(self, t, x, args={}):
+        x1, x2 = x[..., :1], x[..., 1:2]
+        return torch.cat([x2 * self.p, self.alpha * (1 - x1 ** 2) * x2 - x1], -1)
+
+
+def _trace_lists(tr):
+    return [dict(t0=r["t0"], T=r["T"], dt0=r["dt0"], t=list(r["t"]), dt=list(r["dt"]), ratio=list(r["ratio"]))
+            for r in tr.records]
+
+
+def run_ref_neuralode(net, x, t_span, loss_fn, **kw):
+    ref = ref_shim.load()
+    from torchdyn.core import NeuralODE
+    model = NeuralODE(net, **kw)
+    x = x.clone().requires_grad_(True)
+    with ref_shim.StepTrace() as tr:
+        t_eval, sol = model(x, t_span)
+        nfe_f = float(model.vf.nfe)
+        loss = loss_fn(sol)
+        loss.backward()
+    return dict(t_eval=t_eval.detach(), sol_last=sol[-1].detach(), sol_len=int(sol.shape[0]),
+                loss=loss.detach(), gx=x.grad.detach().clone(),
+                gp=[p.grad.detach().clone() for p in net.parameters()],
+                nfe_fwd=nfe_f, nfe_total=float(model.vf.nfe), traces=_trace_lists(tr))
+
+
+def run_oracle_neuralode(net, x, t_span, loss_fn, **kw):
+    for p in net.parameters():
+        p.grad = None
+    model = eo.OracleNeuralODE(net, **kw)
+    x = x.clone().requires_grad_(True)
+    t_eval, sol = model(x, t_span)
+    nfe_f = model.nfe
+    loss = loss_fn(sol)
+    loss.backward()
+    return dict(t_eval=t_eval.detach(), sol_last=sol[-1].detach(), sol_len=int(sol.shape[0]), loss=loss.detach(),
+                gx=x.grad.detach().clone(), gp=[p.grad.detach().clone() for p in net.parameters()],
+                nfe_fwd=nfe_f, nfe_total=model.nfe, traces=model.traces)
+
+
+def check_same(ref_out, ora_out, name):
+    for k in ("t_eval", "sol_last", "loss", "gx"):
+        assert torch.equal(ref_out[k], ora_out[k]), f"{name}: oracle != reference on {k}: " \
+            f"{(ref_out[k] - ora_out[k]).abs().max()}"
+    for a, b in zip(ref_out["gp"], ora_out["gp"]):
+        assert torch.equal(a, b), f"{name}: param grad mismatch {(a - b).abs().max()}"
+    assert ref_out["nfe_total"] == ora_out["nfe_total"], (name, ref_out["nfe_total"], ora_out["nfe_total"])
+    assert len(ref_out["traces"]) == len(ora_out["traces"]), name
+    for r, o in zip(ref_out["traces"], ora_out["traces"]):
+        assert r["t"] == o.t and r["dt"] == o.dt and r["ratio"] == o.ratio, f"{name}: trace mismatch"
+        assert r["dt0"] == o.dt0
+
+
+def neuralode_cases():
+    cases = {}
+    # cfg 1 (BASELINE.json configs[0]): moons 1024x2, MLP 2-64-2 tanh, dopri5 1e-4, backsolve adjoint, CE loss
+    X, y = moons(1024, 0)
+    ce = nn.CrossEntropyLoss()
+    cases["c1_moons_dopri5_adjoint"] = dict(
+        dims=[2, 64, 2], act="tanh", seed=0, x=X, y=y, t_span=torch.linspace(0, 1, 2), loss="ce",
+        kw=dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="adjoint"))
+    cases["c1_moons_tsit5_interp"] = dict(
+        dims=[2, 64, 2], act="tanh", seed=0, x=X[:256], y=y[:256], t_span=torch.linspace(0, 1, 2), loss="ce",
+        kw=dict(solver="tsit5", atol=1e-4, rtol=1e-4, sensitivity="interpolated_adjoint"))
+    torch.manual_seed(3)
+    cases["mlp3_tsit5_adjoint_tspan5"] = dict(
+        dims=[4, 32, 32, 4], act="softplus", seed=1, x=torch.randn(64, 4), y=None, t_span=torch.linspace(0, 1, 5),
+        loss="sq", kw=dict(solver="tsit5", atol=1e-5, rtol=1e-5, sensitivity="adjoint",
+                           atol_adjoint=1e-5, rtol_adjoint=1e-5))
+    torch.manual_seed(4)
+    cases["mlp_relu_dopri5_interp_tspan4"] = dict(
+        dims=[8, 64, 8], act="relu", seed=2, x=torch.randn(128, 8), y=None, t_span=torch.linspace(0, 2, 4),
+        loss="sq", kw=dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="interpolated_adjoint"))
+    torch.manual_seed(5)
+    # cfg 3 reduced (tsit5 + interpolated adjoint, defaults 1e-3), width 128 instead of 1024, B=128
+    cases["c3r_tsit5_interp"] = dict(
+        dims=[16, 128, 16], act="tanh", seed=3, x=torch.randn(128, 16), y=None, t_span=torch.linspace(0, 1, 2),
+        loss="sqmean", kw=dict(solver="tsit5", sensitivity="interpolated_adjoint"))
+    return cases
+
+
+LOSSES = {
+    "sq": lambda sol, y: sol[-1].pow(2).sum(),
+    "sqmean": lambda sol, y: sol[-1].pow(2).mean(),
+    "ce": lambda sol, y: nn.CrossEntropyLoss()(sol[-1], y),
+}
+
+
+def functional_cases():
+    """odeint(f, x, t_span, solver, ...) on an MLP vector field; full solutions stored."""
+    cases = {}
+    torch.manual_seed(11)
+    x = torch.randn(32, 3)
+    for solver in ("euler", "rk4", "dopri5", "tsit5"):
+        cases[f"fn_{solver}_tspan10"] = dict(dims=[3, 16, 3], act="tanh", seed=7, x=x, t_span=torch.linspace(0, 2, 10),
+                                             kw=dict(solver=solver, atol=1e-5, rtol=1e-5))
+    cases["fn_dopri5_4th_tspan10"] = dict(dims=[3, 16, 3], act="tanh", seed=7, x=x, t_span=torch.linspace(0, 2, 10),
+                                          kw=dict(solver="dopri5", atol=1e-5, rtol=1e-5, interpolator="4th"))
+    cases["fn_dopri5_reversed"] = dict(dims=[3, 16, 3], act="tanh", seed=7, x=x, t_span=torch.linspace(1, 0, 4),
+                                       kw=dict(solver="dopri5", atol=1e-6, rtol=1e-6))
+    cases["fn_tsit5_all_eval"] = dict(dims=[3, 16, 3], act="tanh", seed=7, x=x, t_span=torch.linspace(0, 3, 3),
+                                      kw=dict(solver="tsit5", atol=1e-6, rtol=1e-6, return_all_eval=True))
+    cases["fn_rk4_save_at"] = dict(dims=[3, 16, 3], act="tanh", seed=7, x=x, t_span=torch.linspace(0, 1, 21),
+                                   kw=dict(solver="rk4"), save_last=True)
+    # cfg 2 reduced: rk4 100 steps, MLP 32-256-256-32, B=64, forward only, save last
+    torch.manual_seed(12)
+    cases["c2r_rk4_100"] = dict(dims=[32, 256, 256, 32], act="tanh", seed=8, x=torch.randn(64, 32),
+                                t_span=torch.linspace(0, 1, 101), kw=dict(solver="rk4"), save_last=True)
+    return cases
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_shim.load()
+    from torchdyn.numerics import odeint as ref_odeint
+    torch.set_num_threads(1)  # reduction order of torch CPU kernels is thread-count independent for these sizes, but pin it
+
+    for name, c in neuralode_cases().items():
+        net = mlp(c["dims"], c["act"], c["seed"])
+        loss_fn = (lambda sol, c=c: LOSSES[c["loss"]](sol, c["y"]))
+        out = run_ref_neuralode(net, c["x"], c["t_span"], loss_fn, **c["kw"])
+        if args.check:
+            check_same(out, run_oracle_neuralode(net, c["x"], c["t_span"], loss_fn, **c["kw"]), name)
+        fix = dict(kind="neuralode", dims=c["dims"], act=c["act"], x=c["x"], y=c["y"], t_span=c["t_span"], loss=c["loss"],
+                   kw=c["kw"], params=[p.detach().clone() for p in net.parameters()], ref=out)
+        torch.save(fix, os.path.join(OUT, name + ".pt"))
+        ntr = [len(r["t"]) for r in out["traces"]]
+        print(f"{name}: nfe={out['nfe_total']:.0f} attempts per odeint call={ntr} len(t_eval)={len(out['t_eval'])}")
+
+    for name, c in functional_cases().items():
+        net = mlp(c["dims"], c["act"], c["seed"])
+        kw = dict(c["kw"])
+        if c.get("save_last"):
+            kw["save_at"] = c["t_span"][-1:]
+        f = lambda t, x: net(x)
+        with torch.no_grad(), ref_shim.StepTrace() as tr:
+            t_eval, sol = ref_odeint(f, c["x"], c["t_span"], **kw)
+        if args.check:
+            okw = {k: v for k, v in kw.items()}
+            solver = okw.pop("solver")
+            otr = eo.Trace()
+            with torch.no_grad():
+                t2, s2 = eo.odeint(f, c["x"], c["t_span"], solver, trace=otr, **okw)
+            assert torch.equal(t_eval, t2) and torch.equal(sol, s2), f"{name}: oracle != reference"
+            if tr.records:
+                assert tr.records[0]["t"] == otr.t and tr.records[0]["ratio"] == otr.ratio, name
+        fix = dict(kind="functional", dims=c["dims"], act=c["act"], x=c["x"], t_span=c["t_span"], kw=kw,
+                   params=[p.detach().clone() for p in net.parameters()],
+                   ref=dict(t_eval=t_eval, sol=sol, traces=_trace_lists(tr)))
+        torch.save(fix, os.path.join(OUT, name + ".pt"))
+        print(f"{name}: sol {tuple(sol.shape)} attempts={[len(r['t']) for r in tr.records]}")
+
+    # Van der Pol adjoint (reduced test/test_sensitivity.py:40-76): gradient wrt x0, t_span of 20 points
+    for sens in ("adjoint", "interpolated_adjoint"):
+        for solver in ("dopri5", "tsit5"):
+            name = f"vdp_{solver}_{sens}"
+            torch.manual_seed(21)
+            x = torch.randn(64, 2)
+            f = VDP(0.5)
+            t_span = torch.linspace(0, 1, 20)
+            kw = dict(solver=solver, atol=1e-4, rtol=1e-4, atol_adjoint=1e-4, rtol_adjoint=1e-4, sensitivity=sens)
+            out = run_ref_neuralode(f, x, t_span, lambda sol: sol[-1].sum(), **kw)
+            if args.check:
+                check_same(out, run_oracle_neuralode(f, x, t_span, lambda sol: sol[-1].sum(), **kw), name)
+            torch.save(dict(kind="vdp", alpha=0.5, x=x, t_span=t_span, kw=kw, ref=out), os.path.join(OUT, name + ".pt"))
+            print(f"{name}: nfe={out['nfe_total']:.0f} calls={len(out['traces'])}")
+
+    # spline: self-consistency vector (UNPINNED against torchcde, see oracle/__init__.py)
+    torch.manual_seed(31)
+    xs = torch.randn(5, 9, 3)
+    ts = torch.sort(torch.rand(9))[0]
+    co = eo.natural_cubic_coeffs(xs, ts)
+    sp = eo.NaturalCubicSpline.from_coeffs(co, ts)
+    q = torch.tensor([-0.1, float(ts[0]), float(ts[3]), 0.5 * float(ts[3] + ts[4]), float(ts[-1]), 1.5])
+    torch.save(dict(kind="spline", x=xs, t=ts, coeffs=co, q=q, vals=torch.stack([sp.evaluate(v) for v in q])),
+               os.path.join(OUT, "spline_natural.pt"))
+    print("done ->", OUT)
+
+
+if __name__ == "__main__":
+    main()
