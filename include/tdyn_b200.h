@@ -1,0 +1,120 @@
+/*
+ * tdyn_b200.h -- C ABI of libtdyn_b200.so, the sm_100a kernel library behind the
+ * torchdyn-compatible ODE integration path (torchdyn_b200/).
+ *
+ * The reference (DiffEqML/torchdyn 1.0.6) has NO native boundary: the hot path is Python over
+ * eager ATen ops.  Each entry point below therefore cites the reference *Python* expression(s)
+ * it replaces (paths relative to /root/reference/torchdyn/).  INTEGRATION.md shows the ctypes
+ * binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is available from
+ *     tdyn_last_error() (thread-local).  No exception crosses the ABI.
+ *   - all device buffers are BORROWED for the duration of the stream-ordered call; the library
+ *     allocates nothing.  Pointer *tables* (k[]) and coefficient arrays are HOST arrays and are
+ *     copied into kernel parameters by value.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - kernels run on the CUDA device current on the calling thread (callers in other threads,
+ *     e.g. the autograd engine's device thread, must have it set -- PyTorch does).
+ *   - arithmetic is fp32 with one IEEE rounding per reference ATen op (no FMA contraction), so
+ *     the element-wise results are bit-identical to the reference's; reductions accumulate the
+ *     fp32 squares in fp64 with a fixed summation order (deterministic).
+ */
+#ifndef TDYN_B200_H
+#define TDYN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TDYN_API __attribute__((visibility("default")))
+#else
+#define TDYN_API
+#endif
+
+#define TDYN_ABI_VERSION 3
+#define TDYN_MAX_STAGES 7
+
+/* combination shapes of the reference steppers (numerics/solvers/ode.py) */
+#define TDYN_MODE_CHAIN 0 /* y = x + (dt*a0)*k0 + (dt*a1)*k1 + ...   left to right (ode.py:148,150-153 / :170,172-175) */
+#define TDYN_MODE_INNER 1 /* y = x + dt*(a0*k0 + a1*k1 + ...)        (ode.py:68-71,100-103,149,154); x==NULL -> y = dt*(...) (:155) */
+
+TDYN_API int tdyn_version(void);
+TDYN_API const char* tdyn_last_error(void);
+
+/* bytes of zero-initialised device scratch every reducing entry point needs (partials + ticket). */
+TDYN_API int64_t tdyn_reduce_workspace_bytes(void);
+
+/* K5. One RK stage input.  Replaces the per-stage expressions of Euler/RungeKutta4/DormandPrince45/
+ * Tsitouras45.step (numerics/solvers/ode.py:68-71, :97-104, :145-156, :167-178). */
+TDYN_API int tdyn_rk_combine(float* y, const float* x, const float* const* k, const float* coef, int n_k,
+                    int mode, float dt, int64_t n, void* stream);
+
+/* K6. Step finish: x_new = x + dt*(sum bsol_j k_j)  (ode.py:154), err = dt*(sum berr_j k_j) (:155, written
+ * only when err_out != NULL), scaled error e = err/(atol + rtol*max(|x|,|x_new|)) and sum(e^2) over the first
+ * `norm_n` elements (numerics/odeint.py:365-372, numerics/utils.py:33-34).  *sumsq_out (device, fp64) receives
+ * the sum; error_ratio = sqrt(sumsq/norm_n) is formed by the caller (after the cross-GPU sum when sharded). */
+TDYN_API int tdyn_rk_finish(float* x_new, float* err_out, const float* x, const float* const* k,
+                   const float* bsol, int n_sol, const float* berr, int n_err,
+                   float dt, float atol, float rtol, int64_t n, int64_t norm_n,
+                   double* sumsq_out, void* workspace, void* stream);
+
+/* K9. init_step norms (numerics/utils.py:37-54): with scale = atol + |x0|*rtol writes
+ * out[0] = sum((x0/scale)^2), out[1] = sum((f0/scale)^2), out[2] = sum(((f1-f0)/scale)^2) (f1 may be NULL). */
+TDYN_API int tdyn_init_norms(const float* x0, const float* f0, const float* f1, float atol, float rtol,
+                    int64_t n, double* out3, void* workspace, void* stream);
+
+/* K7. dopri5 4th-order dense output (numerics/odeint.py:380-384, numerics/interpolators.py:29-37,57-63):
+ * x_mid = x0 + dt*sum(bmid_i k_i); fit; evaluate at theta = (t - t0)/(t1 - t0) with theta^2..theta^4 given
+ * as the running fp32 powers th[0..3] = theta, theta^2, theta^3, theta^4. */
+TDYN_API int tdyn_dense_eval(float* out, const float* x0, const float* x1, const float* const* k,
+                    const float* bmid, float dt, const float* th, int64_t n, void* stream);
+
+/* K8. Natural cubic spline through the M saved states sol[M, n] of the interpolated adjoint (torchcde 0.2.x
+ * algorithm; reference call sites numerics/sensitivity.py:126-127 build, :132 evaluate).  `aux` is a device
+ * array of 4*M floats computed by the host from the knot times alone (rows: r=1/h, r^2, Thomas multipliers w,
+ * pivots d'); outputs are the knot derivatives kd[M, n] and the per-piece two_c, three_d [M-1, n] (a = sol).
+ * With 2 knots the spline degenerates to the chord (aux unused, t1_minus_t0 used). */
+TDYN_API int tdyn_spline_build(const float* sol, const float* aux, float* kd, float* two_c, float* three_d, int n_knots,
+                      int64_t n, float t1_minus_t0, void* stream);
+/* x(t) = a + s*(b + s*(two_c/2 + three_d*s/3)) for the piece the host selected (s = t - t_piece). */
+TDYN_API int tdyn_spline_eval(float* out, const float* a, const float* b, const float* two_c, const float* three_d, float s,
+                     int64_t n, void* stream);
+
+/* ---- fused MLP vector fields ------------------------------------------------------------------
+ * f(x) = W_L act(... act(W_1 x + b_1) ...) + b_L, weights in nn.Linear layout ([out,in] row-major). */
+#define TDYN_ACT_TANH 0
+#define TDYN_ACT_SOFTPLUS 1 /* torch.nn.Softplus(beta=1, threshold=20) */
+#define TDYN_ACT_RELU 2
+#define TDYN_MAX_LAYERS 4
+
+typedef struct {
+    int n_layers;                      /* number of Linear layers, 2..4 */
+    int dims[TDYN_MAX_LAYERS + 1];     /* dims[0] = state dim = dims[n_layers] */
+    int act;                           /* TDYN_ACT_* applied between Linear layers */
+    const float* w[TDYN_MAX_LAYERS];   /* device, [dims[l+1], dims[l]] */
+    const float* b[TDYN_MAX_LAYERS];   /* device, [dims[l+1]] */
+} tdyn_mlp_t;
+
+/* K2. Tensor-core (tcgen05, 3xTF32) stage kernel for wide MLPs (all hidden widths multiples of 64, >= 128):
+ *   y = combine(x, k[], coef, mode, dt)   (same semantics as tdyn_rk_combine; n_k == 0 -> y = x)
+ *   k_out = f(y)                          [rows, dims[0]]
+ * and, when x_new != NULL (last stage of a fixed-step method), additionally
+ *   x_new = x + dt*(sum_j bsol_j k_j) with k_out as the last term          (ode.py:104)
+ * Replaces `f(t + c*dt, x + dt*(...))` of ode.py:100-103 for nn.Sequential MLP vector fields.
+ * `wsplit` is a device buffer of tdyn_mlp_tc_prepared_bytes() holding the pre-split weights written by
+ * tdyn_mlp_tc_prepare (once per parameter update). */
+TDYN_API int64_t tdyn_mlp_tc_prepared_bytes(const tdyn_mlp_t* mlp);
+TDYN_API int tdyn_mlp_tc_supported(const tdyn_mlp_t* mlp);
+TDYN_API int tdyn_mlp_tc_prepare(const tdyn_mlp_t* mlp, void* wsplit, void* stream);
+TDYN_API int tdyn_mlp_tc_stage(const tdyn_mlp_t* mlp, const void* wsplit, float* k_out, float* y_out,
+                      const float* x, const float* const* k, const float* coef, int n_k, int mode, float dt,
+                      float* x_new, const float* bsol, int n_sol, int64_t rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDYN_B200_H */

@@ -1,0 +1,70 @@
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+
+
+def build_mlp(dims, act, params=None, device="cpu"):
+    acts = {"tanh": nn.Tanh, "softplus": nn.Softplus, "relu": nn.ReLU}
+    layers = []
+    for i in range(len(dims) - 1):
+        layers.append(nn.Linear(dims[i], dims[i + 1]))
+        if i < len(dims) - 2:
+            layers.append(acts[act]())
+    net = nn.Sequential(*layers)
+    if params is not None:
+        with torch.no_grad():
+            for p, v in zip(net.parameters(), params):
+                p.copy_(v)
+    return net.to(device)
+
+
+class VDP(nn.Module):
+    """Van der Pol oscillator used by the vdp_* fixtures (same as oracle/make_golden.py)."""
+
+    def __init__(self, alpha):
+        super().__init__()
+        self.alpha = alpha
+        self.p = nn.Parameter(torch.tensor([1.0]))
+
+    def forward(self, t, x, args={}):
+        x1, x2 = x[..., :1], x[..., 1:2]
+        return torch.cat([x2 * self.p, self.alpha * (1 - x1 ** 2) * x2 - x1], -1)
+
+
+LOSSES = {
+    "sq": lambda sol, y: sol[-1].pow(2).sum(),
+    "sqmean": lambda sol, y: sol[-1].pow(2).mean(),
+    "ce": lambda sol, y: nn.CrossEntropyLoss()(sol[-1], y),
+}
+
+NEURALODE_CASES = ["c1_moons_dopri5_adjoint", "c1_moons_tsit5_interp", "mlp3_tsit5_adjoint_tspan5",
+                   "mlp_relu_dopri5_interp_tspan4", "c3r_tsit5_interp"]
+FUNCTIONAL_CASES = ["fn_euler_tspan10", "fn_rk4_tspan10", "fn_dopri5_tspan10", "fn_tsit5_tspan10",
+                    "fn_dopri5_4th_tspan10", "fn_dopri5_reversed", "fn_tsit5_all_eval", "fn_rk4_save_at", "c2r_rk4_100"]
+VDP_CASES = ["vdp_dopri5_adjoint", "vdp_tsit5_adjoint", "vdp_dopri5_interpolated_adjoint",
+             "vdp_tsit5_interpolated_adjoint"]

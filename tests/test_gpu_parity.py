@@ -1,0 +1,212 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle / the executed-reference fixtures.
+
+Bars (north_star): element-wise kernels bit-exact against the checker arithmetic; reductions to fp64 round-off;
+end-to-end: identical attempted/accepted step sequence, t and dt to fp32 round-off, final state and gradients
+within rtol 1e-5."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import torchdyn_b200
+from torchdyn_b200 import _kernels
+from torchdyn_b200._lib import MODE_CHAIN, MODE_INNER
+from torchdyn_b200.numerics import odeint
+from torchdyn_b200.numerics.spline import NaturalCubicSpline
+from conftest import FUNCTIONAL_CASES, NEURALODE_CASES, VDP, VDP_CASES, build_mlp, load_golden
+from cpu_kernel_double import CpuKernels
+from oracle import erk_oracle as eo
+from parity_helpers import (assert_close, check_functional_case, check_neuralode_case, run_functional_case,
+                            run_neuralode_case)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def real_backend():
+    _kernels.set_test_backend(None)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def _rand(n, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, generator=g) * scale
+
+
+# ------------------------------------------------------------------------------ kernel unit tests
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 1023, 4096, 100003])
+@pytest.mark.parametrize("mode", [MODE_CHAIN, MODE_INNER])
+@pytest.mark.parametrize("nk", [1, 2, 3, 6, 7])
+def test_rk_combine_bit_exact(n, mode, nk):
+    cpu = CpuKernels()
+    x = _rand(n, 1)
+    ks = [_rand(n, 10 + j) for j in range(nk)]
+    coefs = [0.2, -3.7333333, 3.5555556, 0.0, -0.29080933, 0.65104169, 1.0][:nk]
+    coefs = [float(np.float32(c)) for c in coefs]
+    dt = float(np.float32(0.0371))
+    want = cpu.combine(torch.empty(n), x, ks, coefs, mode, dt)
+    kern = _kernels.get(torch.empty(1, device=DEV))
+    got = kern.combine(torch.empty(n, device=DEV), x.to(DEV), [k.to(DEV) for k in ks], coefs, mode, dt)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_rk_combine_misaligned_and_no_x():
+    cpu = CpuKernels()
+    n = 1001
+    base = _rand(n + 3, 5).to(DEV)
+    kb = [_rand(n + 3, 6 + j).to(DEV) for j in range(3)]
+    x, ks = base[1:1 + n], [k[1:1 + n] for k in kb]            # 4-byte aligned views: scalar path
+    coefs = [0.5, 0.25, -1.5]
+    want = cpu.combine(torch.empty(n), x.cpu(), [k.cpu() for k in ks], coefs, MODE_CHAIN, 0.1)
+    kern = _kernels.get(x)
+    got = kern.combine(torch.empty(n, device=DEV), x.contiguous() if False else x, ks, coefs, MODE_CHAIN, 0.1)
+    assert torch.equal(got.cpu(), want)
+    want2 = cpu.combine(torch.empty(n), None, [k.cpu() for k in ks], coefs, MODE_INNER, 0.1)   # err = dt*(...)
+    got2 = kern.combine(torch.empty(n, device=DEV), None, ks, coefs, MODE_INNER, 0.1)
+    assert torch.equal(got2.cpu(), want2)
+
+
+@pytest.mark.parametrize("n,norm_n", [(7, 7), (4096, 4096), (100003, 100003), (100003, 5000), (2 * 2048 + 322 + 1, 4096)])
+def test_rk_finish_matches_checker(n, norm_n):
+    tab = eo.Tableau("dopri5")
+    bsol = [float(v) for v in tab.bsol[:6]]
+    berr = [float(v) for v in tab.berr]
+    x = _rand(n, 2)
+    ks = [_rand(n, 20 + j) for j in range(7)]
+    dt, atol, rtol = float(np.float32(0.0123)), 1e-4, 1e-4
+    xs = eo._inner(x, torch.tensor(dt), [torch.tensor(b) for b in bsol], ks[:6])
+    err = eo._inner(None, torch.tensor(dt), [torch.tensor(b) for b in berr], ks)
+    es = (err / (atol + rtol * torch.max(x.abs(), xs.abs())))[:norm_n]
+    want_sum = float(es.abs().pow(2).double().sum())
+    kern = _kernels.get(torch.empty(1, device=DEV))
+    x_new, err_out = torch.empty(n, device=DEV), torch.empty(n, device=DEV)
+    kern.finish(x_new, err_out, x.to(DEV), [k.to(DEV) for k in ks], bsol, berr, dt, atol, rtol, norm_n)
+    got_sum = kern.read_reduction(1)[0]
+    assert torch.equal(x_new.cpu(), xs) and torch.equal(err_out.cpu(), err)
+    assert abs(got_sum - want_sum) <= 1e-12 * abs(want_sum)
+    # determinism: same launch twice -> identical bits
+    kern.finish(x_new, None, x.to(DEV), [k.to(DEV) for k in ks], bsol, berr, dt, atol, rtol, norm_n)
+    assert kern.read_reduction(1)[0] == got_sum
+
+
+def test_init_norms_matches_checker():
+    n = 77777
+    x0, f0, f1 = _rand(n, 3), _rand(n, 4), _rand(n, 5)
+    atol, rtol = 1e-5, 1e-3
+    scale = atol + x0.abs() * rtol
+    want = [float((v / scale).abs().pow(2).double().sum()) for v in (x0, f0, f1 - f0)]
+    kern = _kernels.get(torch.empty(1, device=DEV))
+    kern.init_norms(x0.to(DEV), f0.to(DEV), f1.to(DEV), atol, rtol)
+    got = kern.read_reduction(3)
+    for g, w in zip(got, want):
+        assert abs(g - w) <= 1e-12 * abs(w)
+
+
+@pytest.mark.parametrize("n", [5, 4096, 33331])
+def test_dense_eval_bit_exact(n):
+    cpu = CpuKernels()
+    x0, x1 = _rand(n, 6), _rand(n, 7)
+    ks = [_rand(n, 30 + j) for j in range(7)]
+    bmid = [float(v) for v in eo.bmid_4th()]
+    dt = float(np.float32(0.31))
+    th = np.float32(0.37)
+    ths = [float(th), float(np.float32(th * th)), float(np.float32(np.float32(th * th) * th)),
+           float(np.float32(np.float32(np.float32(th * th) * th) * th))]
+    want = cpu.dense_eval(torch.empty(n), x0, x1, ks, bmid, dt, ths)
+    kern = _kernels.get(torch.empty(1, device=DEV))
+    got = kern.dense_eval(torch.empty(n, device=DEV), x0.to(DEV), x1.to(DEV), [k.to(DEV) for k in ks], bmid, dt, ths)
+    assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("m", [2, 3, 9, 40])
+def test_spline_matches_checker(m):
+    torch.manual_seed(31 + m)
+    sol = torch.randn(m, 6, 5)
+    t = torch.sort(torch.rand(m))[0] * 2.0
+    co = eo.natural_cubic_coeffs(sol.reshape(m, -1), t)
+    sp = eo.NaturalCubicSpline.from_coeffs(co, t)
+    mine = NaturalCubicSpline(sol.to(DEV), t)
+    qs = [-0.1, float(t[0]), float(t[m // 2]), 0.5 * float(t[0] + t[1]), float(t[-1]), 2.5, float(t[-1]) - 1e-3]
+    for q in qs:
+        want = sp.evaluate(torch.tensor(q)).reshape(6, 5)
+        got = mine.evaluate(np.float32(q)).cpu()
+        assert torch.equal(got, want), (m, q, float((got - want).abs().max()))
+
+
+# ------------------------------------------------------------------------------ end to end vs the executed reference
+
+@pytest.mark.parametrize("name", FUNCTIONAL_CASES)
+def test_functional_odeint_matches_reference(name):
+    fx = load_golden(name)
+    check_functional_case(fx, *run_functional_case(fx, DEV))
+
+
+@pytest.mark.parametrize("name", NEURALODE_CASES)
+def test_neuralode_adjoints_match_reference(name):
+    fx = load_golden(name)
+    check_neuralode_case(fx, run_neuralode_case(fx, DEV))
+
+
+@pytest.mark.parametrize("name", VDP_CASES)
+def test_vdp_adjoint_matches_reference(name):
+    fx = load_golden(name)
+    f = VDP(fx["alpha"]).to(DEV)
+    check_neuralode_case(fx, run_neuralode_case(dict(fx, dims=None, act=None, params=None), DEV, net=f))
+
+
+def test_generic_path_against_live_oracle_conv_state():
+    """4-D state through the generic kernels (cfg-5 shape, reduced): Conv2d + Tanh vector field, dopri5."""
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 3, 3, padding=1), torch.nn.Tanh())
+    x = torch.randn(8, 3, 12, 12)
+    t_span = torch.linspace(0, 1, 3)
+    tr = eo.Trace()
+    with torch.no_grad():
+        t_ref, s_ref = eo.odeint(lambda t, x: net(x), x, t_span, "dopri5", atol=1e-4, rtol=1e-4, trace=tr)
+        netg = net.to(DEV)
+        t_got, s_got = odeint(lambda t, x: netg(x), x.to(DEV), t_span, "dopri5", atol=1e-4, rtol=1e-4)
+    assert s_got.shape == s_ref.shape
+    assert_close(s_got, s_ref, "conv state", rtol=1e-5, atol_scale=5e-6)
+
+
+# ------------------------------------------------------------------------------ size-independent properties at full size
+
+def test_rk4_linear_ode_full_batch_known_answer():
+    """cfg-2-sized batch (2^20 x 32) through the generic rk4 path on dx/dt = -x: x(1) = x0*exp(-1) (rk4, 100 steps:
+    error ~1e-10, below fp32) -- a closed-form check that scales to the full size."""
+    n = 1 << 20
+    x0 = torch.randn(n, 32, device=DEV)
+    t_span = torch.linspace(0, 1, 101)
+    with torch.no_grad():
+        _, sol = odeint(lambda t, x: -x, x0, t_span, "rk4", save_at=t_span[-1:])
+    assert sol.shape == (1, n, 32)
+    assert torch.allclose(sol[0], x0 * float(np.exp(-1.0)), rtol=2e-6, atol=1e-7)
+
+
+def test_adaptive_linear_ode_sum_rule():
+    """Linearity: for f(x) = A x the solver output is linear in x0 for a FIXED step sequence; with the global
+    controller the batch [x0, 2*x0] must give sol(2*x0) == 2*sol(x0) exactly (power-of-two scaling)."""
+    torch.manual_seed(0)
+    A = torch.randn(6, 6, device=DEV) * 0.3
+    x0 = torch.randn(1000, 6, device=DEV)
+    xx = torch.cat([x0, 2 * x0])
+    with torch.no_grad():
+        _, sol = odeint(lambda t, x: x @ A.T, xx, torch.linspace(0, 1, 4), "tsit5", atol=1e-5, rtol=1e-5)
+    assert torch.equal(sol[-1][1000:], 2 * sol[-1][:1000])
+
+
+def test_no_silent_fallback_native_library_is_loaded():
+    import ctypes
+    from torchdyn_b200 import _lib
+    assert isinstance(_lib.load(), ctypes.CDLL)
+    before = _kernels.launches()
+    with torch.no_grad():
+        odeint(lambda t, x: -x, torch.ones(4, 2, device=DEV), torch.linspace(0, 1, 2), "dopri5")
+    assert _kernels.launches() > before
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        odeint(lambda t, x: -x, torch.ones(4, 2), torch.linspace(0, 1, 2), "dopri5")

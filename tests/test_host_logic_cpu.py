@@ -1,0 +1,163 @@
+"""CPU tests of the PRODUCT's host logic (loops, controller, checkpoints, adjoint plumbing, API contract).
+
+The CUDA kernels are replaced by tests/cpu_kernel_double.py (checker arithmetic) via the package's test hook,
+so what is exercised here is everything ABOVE the C ABI.  The kernels themselves are checked on the GPU
+(tests/test_gpu_parity.py).  Expected values: tests/golden (executed reference)."""
+import io
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import torchdyn_b200
+from torchdyn_b200 import _kernels
+import torchdyn_b200.numerics.sensitivity as sens_mod
+from conftest import FUNCTIONAL_CASES, NEURALODE_CASES, VDP, VDP_CASES, load_golden
+from cpu_kernel_double import CpuKernels, OracleSpline
+from parity_helpers import (check_functional_case, check_neuralode_case, run_functional_case, run_neuralode_case)
+
+
+@pytest.fixture(autouse=True)
+def cpu_double(monkeypatch):
+    torch.set_num_threads(1)
+    k = CpuKernels()
+    _kernels.set_test_backend(lambda x: k)
+    monkeypatch.setattr(sens_mod, "NaturalCubicSpline", OracleSpline)
+    yield k
+    _kernels.set_test_backend(None)
+
+
+@pytest.mark.parametrize("name", FUNCTIONAL_CASES)
+def test_functional_odeint_matches_reference(name):
+    fx = load_golden(name)
+    check_functional_case(fx, *run_functional_case(fx, "cpu"), exact=True)
+
+
+@pytest.mark.parametrize("name", NEURALODE_CASES)
+def test_neuralode_adjoints_match_reference(name):
+    fx = load_golden(name)
+    check_neuralode_case(fx, run_neuralode_case(fx, "cpu"), exact=True)
+
+
+@pytest.mark.parametrize("name", VDP_CASES)
+def test_vdp_adjoint_matches_reference(name):
+    fx = load_golden(name)
+    f = VDP(fx["alpha"])
+    out = run_neuralode_case(dict(fx, dims=None, act=None, params=None), "cpu", net=f)
+    check_neuralode_case(fx, out, exact=True)
+
+
+def test_solver_registry_and_errors():
+    from torchdyn_b200.numerics import SOLVER_DICT, str_to_solver, odeint
+    for name in ("euler", "rk4", "rk-4", "RungeKutta4", "dopri5", "DormandPrince45", "DormandPrince5", "tsit5",
+                 "Tsitouras45", "Tsitouras5"):
+        s = str_to_solver(name)
+        assert s.stepping_class in ("fixed", "adaptive")
+    with pytest.raises(KeyError):
+        str_to_solver("not-a-solver")
+    x = torch.randn(4, 2)
+    with pytest.raises(NotImplementedError):
+        odeint(lambda t, x: x, x, torch.zeros(2, 3), "dopri5")
+    with pytest.warns(UserWarning, match="no effect on fixed-step"):
+        odeint(lambda t, x: -x, x, torch.linspace(0, 1, 3), "rk4", atol=1e-5)
+    with pytest.warns(UserWarning, match="save_at has no effect"):
+        odeint(lambda t, x: -x, x, torch.linspace(0, 1, 3), "dopri5", save_at=torch.tensor([1.0]))
+    assert SOLVER_DICT["dopri5"]().order == 5 and SOLVER_DICT["tsit5"]().order == 5 and SOLVER_DICT["rk4"]().order == 4
+
+
+def test_no_cpu_fallback_without_test_hook():
+    _kernels.set_test_backend(None)
+    from torchdyn_b200.numerics import odeint
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        odeint(lambda t, x: -x, torch.randn(4, 2), torch.linspace(0, 1, 3), "dopri5")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        odeint(lambda t, x: -x, torch.randn(4, 2), torch.linspace(0, 1, 3), "rk4")
+
+
+def test_autograd_through_solver_is_refused_loudly():
+    from torchdyn_b200.numerics import odeint
+    net = nn.Linear(2, 2)
+    with pytest.raises(NotImplementedError, match="sensitivity='adjoint'"):
+        odeint(lambda t, x: net(x), torch.randn(4, 2), torch.linspace(0, 1, 3), "dopri5")
+
+
+def test_reversed_span_returns_negated_times():
+    from torchdyn_b200.numerics import odeint
+    with torch.no_grad():
+        t_eval, sol = odeint(lambda t, x: -x, torch.ones(3, 2), torch.tensor([1.0, 0.0]), "dopri5", atol=1e-6, rtol=1e-6)
+    assert torch.allclose(t_eval, torch.tensor([-1.0, 0.0]))
+    assert torch.allclose(sol[-1], torch.full((3, 2), float(np.e)), rtol=1e-4)
+
+
+def test_user_solver_plugin_dict_state_and_args():
+    """A user subclass overriding `step` runs unchanged (reference test/models/test_ode.py:80-99)."""
+    from torchdyn_b200.numerics import Euler
+
+    class DictEuler(Euler):
+        def step(self, f, x, t, dt, k1=None, args=None):
+            out = {"x": x["x"] + dt * f(t, x["x"]) * args["scale"], "n": x["n"] + 1}
+            return None, out, None
+
+    model = torchdyn_b200.NeuralODE(lambda t, x, args={}: -x, solver=DictEuler(), sensitivity="autograd")
+    x0 = {"x": torch.ones(2, 3), "n": torch.zeros(1)}
+    with torch.no_grad():
+        t_eval, sol = model(x0, torch.linspace(0, 1, 11), args={"scale": 1.0})
+    assert isinstance(sol, dict) and sol["x"].shape == (11, 2, 3) and sol["n"][-1].item() == 10
+    assert torch.allclose(sol["x"][-1], torch.full((2, 3), 0.9 ** 10), rtol=1e-5)
+
+
+def test_user_adaptive_solver_module_runs_its_own_step():
+    from torchdyn_b200.numerics import DormandPrince45, odeint
+
+    class MyDopri(DormandPrince45):
+        calls = 0
+
+        def step(self, f, x, t, dt, k1=None, args=None):
+            MyDopri.calls += 1
+            return super().step(f, x, t, dt, k1=k1, args=args)
+
+    with torch.no_grad():
+        t1, s1 = odeint(lambda t, x: -x, torch.ones(4, 2), torch.linspace(0, 1, 3), MyDopri(), atol=1e-5, rtol=1e-5)
+        t2, s2 = odeint(lambda t, x: -x, torch.ones(4, 2), torch.linspace(0, 1, 3), "dopri5", atol=1e-5, rtol=1e-5)
+    assert MyDopri.calls > 0 and torch.allclose(s1, s2, rtol=1e-6) and torch.equal(t1, t2)
+
+
+def test_neuralode_api_surface():
+    net = nn.Sequential(nn.Linear(2, 8), nn.Tanh(), nn.Linear(8, 2))
+    model = torchdyn_b200.NeuralODE(net, solver="dopri5", sensitivity="adjoint", return_t_eval=False)
+    assert "NFE" in repr(model) and model.sensalg == "adjoint" and model.vf.nfe == 0
+    with torch.no_grad():
+        sol = model(torch.randn(5, 2))
+        assert sol.shape == (2, 5, 2)                      # default t_span = linspace(0, 1, 2), sol only
+        traj = model.trajectory(torch.randn(5, 2), torch.linspace(0, 1, 30))
+    assert traj.shape == (30, 5, 2)
+    assert model.vf.nfe > 0
+    # pickling contract (reference test/test_problem.py:20-32)
+    buf = io.BytesIO()
+    torch.save(model, buf)
+    buf.seek(0)
+    again = torch.load(buf, weights_only=False)
+    with torch.no_grad():
+        assert again(torch.zeros(3, 2)).shape == (2, 3, 2)
+    prob = torchdyn_b200.ODEProblem(net, "tsit5", sensitivity="interpolated_adjoint")
+    assert prob.atol == 1e-4 and prob.atol_adjoint == 1e-6
+    with pytest.raises(KeyError):
+        torchdyn_b200.NeuralODE(net, solver="dopri5", solver_adjoint=nn.Identity())   # must be a NAME (reference quirk)
+
+
+def test_save_at_subset_fixed_step():
+    from torchdyn_b200.numerics import odeint
+    t_span = torch.linspace(0, 1, 11)
+    with torch.no_grad():
+        t_eval, sol = odeint(lambda t, x: -x, torch.ones(2, 2), t_span, "rk4", save_at=t_span[[0, 5, 10]])
+    assert sol.shape == (3, 2, 2) and torch.allclose(sol[-1], torch.full((2, 2), float(np.exp(-1.0))), rtol=1e-5)
+    with pytest.raises(AssertionError):
+        odeint(lambda t, x: -x, torch.ones(2, 2), t_span, "rk4", save_at=torch.tensor([0.123]))
+
+
+def test_nan_error_ratio_raises_instead_of_hanging():
+    from torchdyn_b200.numerics import odeint
+    with torch.no_grad(), pytest.raises(RuntimeError, match="did not terminate"):
+        odeint(lambda t, x: x * float("nan"), torch.ones(2, 2), torch.linspace(0, 1, 2), "dopri5")

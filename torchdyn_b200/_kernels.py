@@ -1,0 +1,216 @@
+"""Thin Python face of the CUDA kernels: turns torch tensors into raw pointers + the current stream.
+
+``get(x)`` returns the per-device ``CudaKernels`` object or raises -- there is deliberately no CPU
+implementation in the product (tests inject a checker-backed double through ``set_test_backend``
+to exercise the host logic without a GPU).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+_launches = 0          # kernels launched by this library in this process (bench.py reports it)
+_tls = threading.local()
+_test_backend = None
+
+
+def launches() -> int:
+    return _launches
+
+
+class KernelTimer:
+    """Optional CUDA-event timing of every launch of this library (bench.py's roofline numbers): events are
+    recorded on the launching stream right around the launch; ``summary()`` synchronises and aggregates."""
+
+    def __init__(self):
+        self.records = []   # (name, start_event, end_event, algorithmic_bytes_or_flops)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, work in self.records:
+            a = agg.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
+            a["launches"] += 1
+            a["ms"] += e0.elapsed_time(e1)
+            a["work"] += work
+        return agg
+
+
+_timer: Optional[KernelTimer] = None
+
+
+def set_timer(timer: Optional[KernelTimer]):
+    global _timer
+    _timer = timer
+
+
+class _Timed:
+    __slots__ = ("name", "work", "e0")
+
+    def __init__(self, name, work):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if _timer is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _timer is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _timer.records.append((self.name, self.e0, e1, self.work))
+        return False
+
+
+def set_test_backend(factory):
+    """TESTS ONLY: ``factory(x) -> backend`` replaces the CUDA backend (None restores it)."""
+    global _test_backend
+    _test_backend = factory
+
+
+def _fp(vals: Sequence[float]):
+    return (C.c_float * len(vals))(*vals)
+
+
+def _pp(tensors: Sequence[Tensor]):
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class CudaKernels:
+    """One instance per (device, thread).  Owns the reduction scratch (device), its fp64 result and a
+    pinned host mirror."""
+
+    is_cuda = True
+
+    def __init__(self, device: torch.device):
+        self.lib = _lib.load()
+        self.device = device
+        nbytes = int(self.lib.tdyn_reduce_workspace_bytes())
+        self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        self.red = torch.zeros(4, dtype=torch.float64, device=device)
+        self.red_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @staticmethod
+    def _chk(t: Tensor, name: str):
+        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+            raise RuntimeError(f"torchdyn_b200: `{name}` must be a contiguous CUDA float32 tensor "
+                               f"(got {t.dtype}, {t.device}, contiguous={t.is_contiguous()})")
+
+    def empty_like(self, x: Tensor) -> Tensor:
+        return torch.empty_like(x, memory_format=torch.contiguous_format)
+
+    def time_tensor(self, value, like: Tensor) -> Tensor:
+        """shape-[1] time tensor on the state's device (what the reference hands to f)."""
+        return torch.full((1,), float(value), dtype=like.dtype, device=like.device)
+
+    # -- kernels ------------------------------------------------------------------------------
+    def combine(self, y: Tensor, x: Optional[Tensor], ks: List[Tensor], coefs: Sequence[float], mode: int, dt: float):
+        global _launches
+        n = y.numel()
+        if n == 0:
+            return y
+        for t in ks:
+            self._chk(t, "k")
+        if x is not None:
+            self._chk(x, "x")
+        with _Timed("rk_combine", 4.0 * n * (len(ks) + 1 + (x is not None))):
+            rc = self.lib.tdyn_rk_combine(y.data_ptr(), _ptr(x), _pp(ks), _fp(coefs), len(ks), mode, float(dt), n,
+                                          self._stream())
+        _lib.check(rc, "tdyn_rk_combine")
+        _launches += 1
+        return y
+
+    def finish(self, x_new: Tensor, err_out: Optional[Tensor], x: Tensor, ks: List[Tensor], bsol: Sequence[float],
+               berr: Sequence[float], dt: float, atol: float, rtol: float, norm_n: int):
+        """Launch K6; the fp64 sum of squared scaled errors lands in ``self.red[0]``."""
+        global _launches
+        self._chk(x, "x")
+        for t in ks:
+            self._chk(t, "k")
+        with _Timed("rk_finish", 4.0 * x.numel() * (max(len(bsol), len(berr)) + 2 + (err_out is not None))):
+            rc = self.lib.tdyn_rk_finish(x_new.data_ptr(), _ptr(err_out), x.data_ptr(), _pp(ks), _fp(bsol), len(bsol),
+                                         _fp(berr), len(berr), float(dt), float(atol), float(rtol), x.numel(), int(norm_n),
+                                         self.red.data_ptr(), self.ws.data_ptr(), self._stream())
+        _lib.check(rc, "tdyn_rk_finish")
+        _launches += 1
+
+    def init_norms(self, x0: Tensor, f0: Tensor, f1: Optional[Tensor], atol: float, rtol: float):
+        """Launch K9; sums land in ``self.red[0:3]``."""
+        global _launches
+        self._chk(x0, "x0"); self._chk(f0, "f0")
+        if f1 is not None:
+            self._chk(f1, "f1")
+        rc = self.lib.tdyn_init_norms(x0.data_ptr(), f0.data_ptr(), _ptr(f1), float(atol), float(rtol), x0.numel(),
+                                      self.red.data_ptr(), self.ws.data_ptr(), self._stream())
+        _lib.check(rc, "tdyn_init_norms")
+        _launches += 1
+
+    def dense_eval(self, out: Tensor, x0: Tensor, x1: Tensor, ks: List[Tensor], bmid: Sequence[float], dt: float,
+                   th: Sequence[float]):
+        global _launches
+        for t in (x0, x1, *ks):
+            self._chk(t, "dense input")
+        rc = self.lib.tdyn_dense_eval(out.data_ptr(), x0.data_ptr(), x1.data_ptr(), _pp(ks), _fp(bmid), float(dt),
+                                      _fp(th), out.numel(), self._stream())
+        _lib.check(rc, "tdyn_dense_eval")
+        _launches += 1
+        return out
+
+    def spline_build(self, sol: Tensor, aux: Optional[Tensor], kd: Tensor, two_c: Tensor, three_d: Tensor, dt01: float):
+        global _launches
+        self._chk(sol, "sol")
+        m = sol.shape[0]
+        rc = self.lib.tdyn_spline_build(sol.data_ptr(), _ptr(aux), kd.data_ptr(), two_c.data_ptr(), three_d.data_ptr(),
+                                        m, sol.numel() // m, float(dt01), self._stream())
+        _lib.check(rc, "tdyn_spline_build")
+        _launches += 1
+
+    def spline_eval(self, out: Tensor, a: Tensor, b: Tensor, two_c: Tensor, three_d: Tensor, s: float):
+        global _launches
+        rc = self.lib.tdyn_spline_eval(out.data_ptr(), a.data_ptr(), b.data_ptr(), two_c.data_ptr(), three_d.data_ptr(),
+                                       float(s), out.numel(), self._stream())
+        _lib.check(rc, "tdyn_spline_eval")
+        _launches += 1
+        return out
+
+    def read_reduction(self, n: int = 1):
+        """Device -> pinned host read of the first ``n`` reduction results (the step's ONE host sync)."""
+        self.red_host[:n].copy_(self.red[:n], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.red_host[:n].tolist()
+
+
+def get(x: Tensor):
+    """Kernel backend for the device of ``x``; raises when the CUDA path cannot run (no fallback)."""
+    if _test_backend is not None:
+        return _test_backend(x)
+    if not isinstance(x, Tensor):
+        raise NotImplementedError(f"{type(x)} is not supported as the state variable")
+    if not x.is_cuda:
+        raise RuntimeError("torchdyn_b200 integrates on B200 GPUs only: the state must be a CUDA tensor "
+                           f"(got device {x.device}); there is no CPU fallback")
+    if x.dtype != torch.float32:
+        raise NotImplementedError(f"torchdyn_b200 kernels compute in float32; got state dtype {x.dtype}")
+    cache = getattr(_tls, "cache", None)
+    if cache is None:
+        cache = _tls.cache = {}
+    key = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    k = cache.get(key)
+    if k is None:
+        k = cache[key] = CudaKernels(torch.device("cuda", key))
+    return k

@@ -1,0 +1,479 @@
+// Generic explicit-RK kernels (vector field stays a torch call between launches).
+//   K5 rk_combine   stage input            (reference: numerics/solvers/ode.py:68-71,97-104,145-156,167-178)
+//   K6 rk_finish    x_new, err, sum(e^2)   (ode.py:154-155, numerics/odeint.py:365-372, numerics/utils.py:33-34)
+//   K9 init_norms   init_step norms        (numerics/utils.py:37-54)
+//   K7 dense_eval   dopri5 dense output    (numerics/odeint.py:380-384, numerics/interpolators.py:29-37,57-63)
+// All HBM-bound: 128-bit coalesced loads, one pass, grid = multiple of 148 SMs, no re-reads.
+#include <stdarg.h>
+#include "tdyn_common.cuh"
+
+namespace tdyn {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+constexpr int kThreads = 256;
+
+static inline int grid_for(int64_t work_items) {
+    int64_t b = (work_items + kThreads - 1) / kThreads;
+    if (b < 1) b = 1;
+    if (b > kMaxReduceBlocks) b = kMaxReduceBlocks;
+    return (int)b;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__device__ __forceinline__ float4 ld4(const float* p, int64_t i4) {
+    return __ldg(reinterpret_cast<const float4*>(p) + i4);
+}
+__device__ __forceinline__ float& comp(float4& v, int c) { return reinterpret_cast<float*>(&v)[c]; }
+
+// ------------------------------------------------------------------------------------------ K5
+template <int NK, int MODE>
+__global__ void __launch_bounds__(kThreads) rk_combine_kernel(float* __restrict__ y, const float* __restrict__ x,
+                                                              KPtrs k, Coefs a, float dt, int64_t n, int vec) {
+    Coefs da;
+#pragma unroll
+    for (int j = 0; j < NK; ++j) da.c[j] = mul_rn(dt, a.c[j]);
+    const bool has_x = x != nullptr;
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    int64_t done = 0;
+    if (vec) {
+        const int64_t n4 = n >> 2;
+        for (int64_t i = tid; i < n4; i += stride) {
+            float4 xv = has_x ? ld4(x, i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 kq[NK];
+#pragma unroll
+            for (int j = 0; j < NK; ++j) kq[j] = ld4(k.p[j], i);
+            float4 out;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float kv[TDYN_MAX_STAGES];
+#pragma unroll
+                for (int j = 0; j < NK; ++j) kv[j] = comp(kq[j], c);
+                comp(out, c) = combine1<NK, MODE>(comp(xv, c), has_x, kv, a, da, dt);
+            }
+            reinterpret_cast<float4*>(y)[i] = out;
+        }
+        done = n4 << 2;
+    }
+    for (int64_t i = done + tid; i < n; i += stride) {
+        float kv[TDYN_MAX_STAGES];
+#pragma unroll
+        for (int j = 0; j < NK; ++j) kv[j] = __ldg(k.p[j] + i);
+        y[i] = combine1<NK, MODE>(has_x ? __ldg(x + i) : 0.f, has_x, kv, a, da, dt);
+    }
+}
+
+template <int MODE>
+static int launch_combine(int n_k, float* y, const float* x, const KPtrs& k, const Coefs& a, float dt, int64_t n,
+                          int vec, cudaStream_t st) {
+    const int grid = grid_for(vec ? (n >> 2) + 3 : n);
+#define TDYN_CASE(NK)                                                                          \
+    case NK:                                                                                   \
+        rk_combine_kernel<NK, MODE><<<grid, kThreads, 0, st>>>(y, x, k, a, dt, n, vec);        \
+        break;
+    switch (n_k) {
+        TDYN_CASE(1) TDYN_CASE(2) TDYN_CASE(3) TDYN_CASE(4) TDYN_CASE(5) TDYN_CASE(6) TDYN_CASE(7)
+        default:
+            set_error("tdyn_rk_combine: n_k=%d out of range 1..7", n_k);
+            return 2;
+    }
+#undef TDYN_CASE
+    TDYN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// -------------------------------------------------------------------------------- reductions
+// workspace: double partials[3][kMaxReduceBlocks]; unsigned ticket (zero on entry, reset on exit)
+struct ReduceWs {
+    double partials[3][kMaxReduceBlocks];
+    unsigned int ticket;
+    unsigned int pad[15];
+};
+
+template <int NACC>
+__device__ __forceinline__ void block_reduce_finalize(double (&acc)[NACC], ReduceWs* ws, double* out) {
+    __shared__ double sm[NACC][kThreads / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        double v = warp_sum(acc[a]);
+        if (lane == 0) sm[a][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) v += sm[a][w];
+            ws->partials[a][blockIdx.x] = v;
+        }
+        __threadfence();
+        const unsigned int t = atomicAdd(&ws->ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // fixed-order final sum: thread t takes partials t, t+256, ... then a fixed tree.
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        double v = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += kThreads) v += __ldcg(&ws->partials[a][b]);
+        v = warp_sum(v);
+        __syncthreads();
+        if (lane == 0) sm[a][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) v += sm[a][w];
+            out[a] = v;
+        }
+        ws->ticket = 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K6
+struct FinishArgs {
+    KPtrs k;
+    Coefs bsol, berr;
+    int n_sol, n_err;
+    float dt, atol, rtol;
+};
+
+__device__ __forceinline__ float finish1(float x, const float (&kv)[TDYN_MAX_STAGES], const FinishArgs& A,
+                                         float& x_new, float& err) {
+    float s = mul_rn(A.bsol.c[0], kv[0]);
+#pragma unroll
+    for (int j = 1; j < TDYN_MAX_STAGES; ++j)
+        if (j < A.n_sol) s = add_rn(s, mul_rn(A.bsol.c[j], kv[j]));
+    x_new = add_rn(x, mul_rn(A.dt, s));
+    float e = mul_rn(A.berr.c[0], kv[0]);
+#pragma unroll
+    for (int j = 1; j < TDYN_MAX_STAGES; ++j)
+        if (j < A.n_err) e = add_rn(e, mul_rn(A.berr.c[j], kv[j]));
+    err = mul_rn(A.dt, e);
+    const float den = add_rn(A.atol, mul_rn(A.rtol, fmaxf(fabsf(x), fabsf(x_new))));
+    const float r = div_rn(err, den);
+    return mul_rn(r, r);  // |r|.pow(2)
+}
+
+__global__ void __launch_bounds__(kThreads) rk_finish_kernel(float* __restrict__ x_new, float* __restrict__ err_out,
+                                                             const float* __restrict__ x, FinishArgs A, int64_t n,
+                                                             int64_t norm_n, int vec, ReduceWs* ws, double* out) {
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    double acc[1] = {0.0};
+    int64_t done = 0;
+    const int nk = A.n_err > A.n_sol ? A.n_err : A.n_sol;
+    if (vec) {
+        const int64_t n4 = n >> 2;
+        for (int64_t i = tid; i < n4; i += stride) {
+            float4 xv = ld4(x, i);
+            float4 kq[TDYN_MAX_STAGES];
+#pragma unroll
+            for (int j = 0; j < TDYN_MAX_STAGES; ++j)
+                if (j < nk) kq[j] = ld4(A.k.p[j], i);
+            float4 xn, er;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float kv[TDYN_MAX_STAGES];
+#pragma unroll
+                for (int j = 0; j < TDYN_MAX_STAGES; ++j) kv[j] = (j < nk) ? comp(kq[j], c) : 0.f;
+                const float sq = finish1(comp(xv, c), kv, A, comp(xn, c), comp(er, c));
+                if (4 * i + c < norm_n) acc[0] += (double)sq;
+            }
+            reinterpret_cast<float4*>(x_new)[i] = xn;
+            if (err_out) reinterpret_cast<float4*>(err_out)[i] = er;
+        }
+        done = n4 << 2;
+    }
+    for (int64_t i = done + tid; i < n; i += stride) {
+        float kv[TDYN_MAX_STAGES];
+#pragma unroll
+        for (int j = 0; j < TDYN_MAX_STAGES; ++j) kv[j] = (j < nk) ? __ldg(A.k.p[j] + i) : 0.f;
+        float xn, er;
+        const float sq = finish1(__ldg(x + i), kv, A, xn, er);
+        if (i < norm_n) acc[0] += (double)sq;
+        x_new[i] = xn;
+        if (err_out) err_out[i] = er;
+    }
+    block_reduce_finalize<1>(acc, ws, out);
+}
+
+// ------------------------------------------------------------------------------------------ K9
+__global__ void __launch_bounds__(kThreads) init_norms_kernel(const float* __restrict__ x0, const float* __restrict__ f0,
+                                                              const float* __restrict__ f1, float atol, float rtol,
+                                                              int64_t n, ReduceWs* ws, double* out) {
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = tid; i < n; i += stride) {
+        const float xv = __ldg(x0 + i), fv = __ldg(f0 + i);
+        const float scale = add_rn(atol, mul_rn(fabsf(xv), rtol));
+        const float a = div_rn(xv, scale), b = div_rn(fv, scale);
+        acc[0] += (double)mul_rn(a, a);
+        acc[1] += (double)mul_rn(b, b);
+        if (f1) {
+            const float c = div_rn(sub_rn(__ldg(f1 + i), fv), scale);
+            acc[2] += (double)mul_rn(c, c);
+        }
+    }
+    block_reduce_finalize<3>(acc, ws, out);
+}
+
+// ------------------------------------------------------------------------------------------ K7
+struct DenseArgs {
+    KPtrs k;
+    Coefs bmid;
+    float dt, th1, th2, th3, th4;
+};
+
+__device__ __forceinline__ float dense1(float x0, float x1, const float (&kv)[TDYN_MAX_STAGES], const DenseArgs& A) {
+    // x_mid = x + dt * sum([bmid_i * k_i])  -- python sum starts from int 0: 0 + b0*k0 is exact.
+    float s = mul_rn(A.bmid.c[0], kv[0]);
+#pragma unroll
+    for (int j = 1; j < TDYN_MAX_STAGES; ++j) s = add_rn(s, mul_rn(A.bmid.c[j], kv[j]));
+    const float xm = add_rn(x0, mul_rn(A.dt, s));
+    const float f0 = kv[0], f1 = kv[6], dt = A.dt;
+    // interpolators.py:57-63, python operator order kept
+    const float c1 = add_rn(sub_rn(mul_rn(mul_rn(2.f, dt), sub_rn(f1, f0)), mul_rn(8.f, add_rn(x1, x0))), mul_rn(16.f, xm));
+    const float c2 = sub_rn(add_rn(add_rn(mul_rn(dt, sub_rn(mul_rn(5.f, f0), mul_rn(3.f, f1))), mul_rn(18.f, x0)),
+                                   mul_rn(14.f, x1)),
+                            mul_rn(32.f, xm));
+    const float c3 = add_rn(sub_rn(sub_rn(mul_rn(dt, sub_rn(f1, mul_rn(4.f, f0))), mul_rn(11.f, x0)), mul_rn(5.f, x1)),
+                            mul_rn(16.f, xm));
+    const float c4 = mul_rn(dt, f0);
+    // interpolators.py:29-37
+    float r = add_rn(x0, mul_rn(A.th1, c4));
+    r = add_rn(r, mul_rn(A.th2, c3));
+    r = add_rn(r, mul_rn(A.th3, c2));
+    r = add_rn(r, mul_rn(A.th4, c1));
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads) dense_eval_kernel(float* __restrict__ out, const float* __restrict__ x0,
+                                                              const float* __restrict__ x1, DenseArgs A, int64_t n,
+                                                              int vec) {
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    int64_t done = 0;
+    if (vec) {
+        const int64_t n4 = n >> 2;
+        for (int64_t i = tid; i < n4; i += stride) {
+            float4 a = ld4(x0, i), b = ld4(x1, i), o;
+            float4 kq[TDYN_MAX_STAGES];
+#pragma unroll
+            for (int j = 0; j < TDYN_MAX_STAGES; ++j) kq[j] = ld4(A.k.p[j], i);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float kv[TDYN_MAX_STAGES];
+#pragma unroll
+                for (int j = 0; j < TDYN_MAX_STAGES; ++j) kv[j] = comp(kq[j], c);
+                comp(o, c) = dense1(comp(a, c), comp(b, c), kv, A);
+            }
+            reinterpret_cast<float4*>(out)[i] = o;
+        }
+        done = n4 << 2;
+    }
+    for (int64_t i = done + tid; i < n; i += stride) {
+        float kv[TDYN_MAX_STAGES];
+#pragma unroll
+        for (int j = 0; j < TDYN_MAX_STAGES; ++j) kv[j] = __ldg(A.k.p[j] + i);
+        out[i] = dense1(__ldg(x0 + i), __ldg(x1 + i), kv, A);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K8
+// Natural cubic spline through the saved states of the interpolated adjoint.  Reference call sites:
+// numerics/sensitivity.py:126-127 (torchcde.natural_cubic_coeffs) and :132 (CubicSpline.evaluate); the
+// algorithm is torchcde 0.2.x's (tridiagonal solve for knot derivatives, Thomas sweep).  Layout: sol is
+// [M, N] as produced by the forward pass (no permute), one thread per channel, coalesced over channels,
+// sequential over the M knots.  aux = 4 fp32 rows of length M computed by the host from t alone:
+//   aux[0][m] = r_m = 1/(t_{m+1}-t_m), aux[1][m] = r_m^2, aux[2][m] = w_m (Thomas multiplier), aux[3][m] = d'_m.
+__global__ void __launch_bounds__(kThreads) spline_build_kernel(const float* __restrict__ sol, const float* __restrict__ aux,
+                                                                float* __restrict__ kd, float* __restrict__ two_c,
+                                                                float* __restrict__ three_d, int M, int64_t N) {
+    const float* r = aux; const float* r2 = aux + M; const float* w = aux + 2 * M; const float* dp = aux + 3 * M;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < N; i += (int64_t)gridDim.x * kThreads) {
+        // forward sweep: b'_m = rhs_m - w_m * b'_{m-1},  rhs_m = dxs_m + dxs_{m-1},  dxs_m = 3*(x_{m+1}-x_m)*r_m^2
+        float x_lo = __ldg(sol + i), x_hi = __ldg(sol + N + i);
+        float dxs_prev = mul_rn(mul_rn(3.f, sub_rn(x_hi, x_lo)), __ldg(r2));
+        float bprev = dxs_prev;                        // rhs_0
+        kd[i] = bprev;
+        for (int m = 1; m < M; ++m) {
+            float rhs;
+            if (m < M - 1) {
+                x_lo = x_hi; x_hi = __ldg(sol + (int64_t)(m + 1) * N + i);
+                const float dxs = mul_rn(mul_rn(3.f, sub_rn(x_hi, x_lo)), __ldg(r2 + m));
+                rhs = add_rn(dxs, dxs_prev);
+                dxs_prev = dxs;
+            } else {
+                rhs = add_rn(0.f, dxs_prev);
+            }
+            bprev = sub_rn(rhs, mul_rn(__ldg(w + m), bprev));
+            kd[(int64_t)m * N + i] = bprev;
+        }
+        // back substitution + per-piece coefficients
+        float k_hi = div_rn(bprev, __ldg(dp + M - 1));
+        kd[(int64_t)(M - 1) * N + i] = k_hi;
+        x_hi = __ldg(sol + (int64_t)(M - 1) * N + i);
+        for (int m = M - 2; m >= 0; --m) {
+            const float rm = __ldg(r + m);
+            const float k_lo = div_rn(sub_rn(kd[(int64_t)m * N + i], mul_rn(rm, k_hi)), __ldg(dp + m));
+            kd[(int64_t)m * N + i] = k_lo;
+            x_lo = __ldg(sol + (int64_t)m * N + i);
+            const float six_dx = mul_rn(2.f, mul_rn(3.f, sub_rn(x_hi, x_lo)));
+            const float sr = mul_rn(six_dx, rm);
+            two_c[(int64_t)m * N + i] = mul_rn(sub_rn(sub_rn(sr, mul_rn(4.f, k_lo)), mul_rn(2.f, k_hi)), rm);
+            three_d[(int64_t)m * N + i] = mul_rn(add_rn(mul_rn(-six_dx, rm), mul_rn(3.f, add_rn(k_lo, k_hi))), __ldg(r2 + m));
+            k_hi = k_lo; x_hi = x_lo;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) spline_linear_kernel(const float* __restrict__ sol, float inv_dt_den,
+                                                                 float* __restrict__ kd, float* __restrict__ two_c,
+                                                                 float* __restrict__ three_d, int64_t N) {
+    // two knots: a = x0, b = (x1-x0)/(t1-t0), c = d = 0   (inv_dt_den carries (t1-t0))
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < N; i += (int64_t)gridDim.x * kThreads) {
+        kd[i] = div_rn(sub_rn(__ldg(sol + N + i), __ldg(sol + i)), inv_dt_den);
+        kd[N + i] = 0.f; two_c[i] = 0.f; three_d[i] = 0.f;
+    }
+}
+
+// x(t) = a + s*(b + s*(two_c/2 + three_d*s/3)), s = t - t_idx  (piece idx chosen by the host)
+__global__ void __launch_bounds__(kThreads) spline_eval_kernel(float* __restrict__ out, const float* __restrict__ a,
+                                                               const float* __restrict__ b, const float* __restrict__ c2,
+                                                               const float* __restrict__ d3, float s, int64_t N) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < N; i += (int64_t)gridDim.x * kThreads) {
+        float inner = add_rn(mul_rn(0.5f, __ldg(c2 + i)), div_rn(mul_rn(__ldg(d3 + i), s), 3.f));
+        inner = add_rn(__ldg(b + i), mul_rn(inner, s));
+        out[i] = add_rn(__ldg(a + i), mul_rn(inner, s));
+    }
+}
+
+}  // namespace tdyn
+
+using namespace tdyn;
+
+extern "C" {
+
+int tdyn_version(void) { return TDYN_ABI_VERSION; }
+const char* tdyn_last_error(void) { return g_err; }
+int64_t tdyn_reduce_workspace_bytes(void) { return (int64_t)sizeof(ReduceWs); }
+
+int tdyn_rk_combine(float* y, const float* x, const float* const* k, const float* coef, int n_k, int mode, float dt,
+                    int64_t n, void* stream) {
+    TDYN_REQUIRE(y && k && coef, "tdyn_rk_combine: null argument");
+    TDYN_REQUIRE(n_k >= 1 && n_k <= TDYN_MAX_STAGES, "tdyn_rk_combine: n_k=%d out of range 1..7", n_k);
+    TDYN_REQUIRE(mode == TDYN_MODE_CHAIN || mode == TDYN_MODE_INNER, "tdyn_rk_combine: bad mode %d", mode);
+    TDYN_REQUIRE(mode == TDYN_MODE_INNER || x, "tdyn_rk_combine: CHAIN mode needs x");
+    if (n <= 0) return 0;
+    KPtrs kp{};
+    Coefs a{};
+    int vec = aligned16(y) && (x == nullptr || aligned16(x));
+    for (int j = 0; j < n_k; ++j) {
+        TDYN_REQUIRE(k[j], "tdyn_rk_combine: k[%d] is null", j);
+        kp.p[j] = k[j];
+        a.c[j] = coef[j];
+        vec = vec && aligned16(k[j]);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    return mode == TDYN_MODE_CHAIN ? launch_combine<TDYN_MODE_CHAIN>(n_k, y, x, kp, a, dt, n, vec, st)
+                                   : launch_combine<TDYN_MODE_INNER>(n_k, y, x, kp, a, dt, n, vec, st);
+}
+
+int tdyn_rk_finish(float* x_new, float* err_out, const float* x, const float* const* k, const float* bsol, int n_sol,
+                   const float* berr, int n_err, float dt, float atol, float rtol, int64_t n, int64_t norm_n,
+                   double* sumsq_out, void* workspace, void* stream) {
+    TDYN_REQUIRE(x_new && x && k && bsol && berr && sumsq_out && workspace, "tdyn_rk_finish: null argument");
+    TDYN_REQUIRE(n_sol >= 1 && n_sol <= TDYN_MAX_STAGES && n_err >= 1 && n_err <= TDYN_MAX_STAGES,
+                 "tdyn_rk_finish: n_sol=%d n_err=%d out of range", n_sol, n_err);
+    TDYN_REQUIRE(n > 0 && norm_n >= 0 && norm_n <= n, "tdyn_rk_finish: bad sizes n=%lld norm_n=%lld", (long long)n,
+                 (long long)norm_n);
+    FinishArgs A{};
+    int vec = aligned16(x_new) && aligned16(x) && (!err_out || aligned16(err_out));
+    const int nk = n_err > n_sol ? n_err : n_sol;
+    for (int j = 0; j < nk; ++j) {
+        TDYN_REQUIRE(k[j], "tdyn_rk_finish: k[%d] is null", j);
+        A.k.p[j] = k[j];
+        vec = vec && aligned16(k[j]);
+    }
+    for (int j = 0; j < n_sol; ++j) A.bsol.c[j] = bsol[j];
+    for (int j = 0; j < n_err; ++j) A.berr.c[j] = berr[j];
+    A.n_sol = n_sol; A.n_err = n_err; A.dt = dt; A.atol = atol; A.rtol = rtol;
+    const int grid = grid_for(vec ? (n >> 2) + 3 : n);
+    rk_finish_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x_new, err_out, x, A, n, norm_n, vec,
+                                                                 (ReduceWs*)workspace, sumsq_out);
+    TDYN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tdyn_init_norms(const float* x0, const float* f0, const float* f1, float atol, float rtol, int64_t n, double* out3,
+                    void* workspace, void* stream) {
+    TDYN_REQUIRE(x0 && f0 && out3 && workspace, "tdyn_init_norms: null argument");
+    TDYN_REQUIRE(n > 0, "tdyn_init_norms: n must be positive");
+    const int grid = grid_for(n);
+    init_norms_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x0, f0, f1, atol, rtol, n, (ReduceWs*)workspace, out3);
+    TDYN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tdyn_dense_eval(float* out, const float* x0, const float* x1, const float* const* k, const float* bmid, float dt,
+                    const float* th, int64_t n, void* stream) {
+    TDYN_REQUIRE(out && x0 && x1 && k && bmid && th, "tdyn_dense_eval: null argument");
+    if (n <= 0) return 0;
+    DenseArgs A{};
+    int vec = aligned16(out) && aligned16(x0) && aligned16(x1);
+    for (int j = 0; j < TDYN_MAX_STAGES; ++j) {
+        TDYN_REQUIRE(k[j], "tdyn_dense_eval: k[%d] is null", j);
+        A.k.p[j] = k[j];
+        A.bmid.c[j] = bmid[j];
+        vec = vec && aligned16(k[j]);
+    }
+    A.dt = dt; A.th1 = th[0]; A.th2 = th[1]; A.th3 = th[2]; A.th4 = th[3];
+    const int grid = grid_for(vec ? (n >> 2) + 3 : n);
+    dense_eval_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(out, x0, x1, A, n, vec);
+    TDYN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tdyn_spline_build(const float* sol, const float* aux, float* kd, float* two_c, float* three_d, int n_knots,
+                      int64_t n, float t1_minus_t0, void* stream) {
+    TDYN_REQUIRE(sol && kd && two_c && three_d, "tdyn_spline_build: null argument");
+    TDYN_REQUIRE(n_knots >= 2 && n > 0, "tdyn_spline_build: need >= 2 knots and n > 0 (got %d, %lld)", n_knots, (long long)n);
+    const int grid = grid_for(n);
+    if (n_knots == 2) {
+        spline_linear_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(sol, t1_minus_t0, kd, two_c, three_d, n);
+    } else {
+        TDYN_REQUIRE(aux, "tdyn_spline_build: aux is null");
+        spline_build_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(sol, aux, kd, two_c, three_d, n_knots, n);
+    }
+    TDYN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tdyn_spline_eval(float* out, const float* a, const float* b, const float* two_c, const float* three_d, float s,
+                     int64_t n, void* stream) {
+    TDYN_REQUIRE(out && a && b && two_c && three_d, "tdyn_spline_eval: null argument");
+    if (n <= 0) return 0;
+    spline_eval_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(out, a, b, two_c, three_d, s, n);
+    TDYN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
