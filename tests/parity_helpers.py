@@ -27,7 +27,7 @@ def assert_close(a, b, what, rtol=STATE_RTOL, atol_scale=2e-6):
     assert not bad.any(), f"{what}: max abs diff {float((a - b).abs().max()):.3e} (atol {atol:.2e}, rtol {rtol})"
 
 
-def assert_traces(ref_traces, got_traces, ratio_rtol=2e-3, exact=False):
+def assert_traces(ref_traces, got_traces, ratio_rtol=5e-2, exact=False):
     assert len(ref_traces) == len(got_traces), (len(ref_traces), len(got_traces))
     for r, g in zip(ref_traces, got_traces):
         if exact:
