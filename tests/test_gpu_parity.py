@@ -210,3 +210,72 @@ def test_no_silent_fallback_native_library_is_loaded():
     assert _kernels.launches() > before
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         odeint(lambda t, x: -x, torch.ones(4, 2), torch.linspace(0, 1, 2), "dopri5")
+
+
+# ------------------------------------------------------------------------------ fused tensor-core MLP path (K2)
+
+def _c2_net(seed=8):
+    torch.manual_seed(seed)
+    return build_mlp([32, 256, 256, 32], "tanh")
+
+
+def test_mlp_tc_single_stage_matches_fp64_reference():
+    """One tdyn_mlp_tc_stage launch (prologue combine + MLP + x_new epilogue) against an fp64 evaluation:
+    3xTF32 must keep fp32-level accuracy (max error ~1e-6 relative to the output scale)."""
+    from torchdyn_b200 import fused
+    net = _c2_net()
+    netg = build_mlp([32, 256, 256, 32], "tanh", [p.detach() for p in net.parameters()], DEV)
+    fm = fused.FusedMLP(netg)
+    kern = _kernels.get(torch.empty(1, device=DEV))
+    assert fm.ready(kern), "32-256-256-32 must be supported by the tensor-core kernel"
+    for rows in (128, 1000, 148 * 128 * 2 + 77):
+        g = torch.Generator().manual_seed(rows)
+        x = torch.randn(rows, 32, generator=g)
+        k1 = torch.randn(rows, 32, generator=g)
+        k2 = torch.randn(rows, 32, generator=g)
+        coefs, bsol, dt = [0.25, 0.5], [1 / 6, 1 / 3, 0.5], float(np.float32(0.1))
+        cpu = CpuKernels()
+        y = cpu.combine(torch.empty(rows, 32), x, [k1, k2], coefs, MODE_INNER, dt)
+        with torch.no_grad():
+            want = net.double()(y.double())
+            net.float()
+        k_out, x_new = torch.empty(rows, 32, device=DEV), torch.empty(rows, 32, device=DEV)
+        kern.mlp_tc_stage(fm._desc, fm._img, k_out, x.to(DEV), [k1.to(DEV), k2.to(DEV)], coefs, MODE_INNER, dt, x_new,
+                          bsol, fm.flops_per_row)
+        torch.cuda.synchronize()
+        err = (k_out.cpu().double() - want).abs().max().item()
+        scale = want.abs().max().item()
+        assert err <= 2e-6 * scale, (rows, err, scale)
+        xn_want = cpu.combine(torch.empty(rows, 32), x, [k1, k2, k_out.cpu()], bsol, MODE_INNER, dt)
+        assert torch.equal(x_new.cpu(), xn_want), "x_new epilogue must be bit-exact given k_out"
+
+
+def test_mlp_tc_rk4_matches_reference_fixture():
+    """c2 reduced (fixture c2r_rk4_100: 64 rows, 100 rk4 steps) through the fused path, via NeuralODE."""
+    from torchdyn_b200 import fused
+    fx = load_golden("c2r_rk4_100")
+    net = build_mlp(fx["dims"], fx["act"], fx["params"], DEV)
+    model = torchdyn_b200.NeuralODE(net, solver="rk4")
+    with torch.no_grad():
+        t_eval, sol = model(fx["x"].to(DEV), fx["t_span"], save_at=fx["kw"]["save_at"])
+    assert fused.last_used() is not None, "fused tensor-core path was not taken"
+    assert model.vf.nfe == 400
+    assert_close(sol, fx["ref"]["sol"], "rk4 x100 final state (fused)")
+
+
+def test_mlp_tc_agrees_with_generic_path_full_size():
+    """Full cfg-2 batch for a few steps: fused tensor-core path vs the generic kernels with f = torch (fp32 SGEMM)."""
+    from torchdyn_b200 import fused
+    net = _c2_net(0).to(DEV)
+    model = torchdyn_b200.NeuralODE(net, solver="rk4")
+    x = torch.randn(1 << 20, 32, device=DEV)
+    t_span = torch.linspace(0, 0.05, 6)
+    with torch.no_grad():
+        _, a = model(x, t_span, save_at=t_span[-1:])
+        assert fused.last_used() is not None
+        fused.DISABLED = True
+        try:
+            _, b = model(x, t_span, save_at=t_span[-1:])
+        finally:
+            fused.DISABLED = False
+    assert_close(a, b, "fused vs generic", rtol=1e-5, atol_scale=2e-6)

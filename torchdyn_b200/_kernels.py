@@ -188,6 +188,31 @@ class CudaKernels:
         _launches += 1
         return out
 
+    # -- fused MLP (tensor-core) path -----------------------------------------------------------
+    def mlp_tc_supported(self, desc) -> bool:
+        return bool(self.lib.tdyn_mlp_tc_supported(C.byref(desc)))
+
+    def mlp_tc_prepare(self, desc) -> Tensor:
+        global _launches
+        nbytes = int(self.lib.tdyn_mlp_tc_prepared_bytes(C.byref(desc)))
+        img = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.tdyn_mlp_tc_prepare(C.byref(desc), img.data_ptr(), self._stream()), "tdyn_mlp_tc_prepare")
+        _launches += 1
+        return img
+
+    def mlp_tc_stage(self, desc, img: Tensor, k_out: Tensor, x: Tensor, ks: List[Tensor], coefs: Sequence[float],
+                     mode: int, dt: float, x_new: Optional[Tensor], bsol: Sequence[float], flops_per_row: float):
+        global _launches
+        rows = x.shape[0]
+        kp = _pp(ks) if ks else None
+        cf = _fp(coefs) if len(coefs) else None
+        bs = _fp(bsol) if len(bsol) else None
+        with _Timed("mlp_tc_stage", flops_per_row * rows):
+            rc = self.lib.tdyn_mlp_tc_stage(C.byref(desc), img.data_ptr(), k_out.data_ptr(), None, x.data_ptr(), kp, cf,
+                                            len(coefs), mode, float(dt), _ptr(x_new), bs, len(bsol), rows, self._stream())
+        _lib.check(rc, "tdyn_mlp_tc_stage")
+        _launches += 1
+
     def read_reduction(self, n: int = 1):
         """Device -> pinned host read of the first ``n`` reduction results (the step's ONE host sync)."""
         self.red_host[:n].copy_(self.red[:n], non_blocking=True)

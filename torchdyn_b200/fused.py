@@ -1,6 +1,25 @@
-"""Recognition of fusable MLP vector fields and dispatch to the fused kernels."""
+"""Recognition of fusable MLP vector fields and dispatch to the fused kernels.
+
+A vector field is *fusable* when, after unwrapping torchdyn's call-signature adapters (``DEFunc`` ->
+``DEFuncBase(has_time_arg=False)``, reference core/defunc.py:19-94) or this module's ``MLPField``, it is an
+``nn.Sequential`` of ``Linear`` layers separated by one kind of activation out of Tanh / Softplus(beta=1,
+threshold=20) / ReLU, time-independent, fp32 on CUDA.  The fused kernels evaluate the field inside this library
+(``tdyn_mlp_tc_stage``: tcgen05 3xTF32), so ``f`` is never called; the wrappers' ``nfe`` counters are advanced by
+the same amounts the reference would count (core/defunc.py:31,61).
+"""
 from __future__ import annotations
 
+import weakref
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _kernels, _lib
+from ._lib import ACT_RELU, ACT_SOFTPLUS, ACT_TANH, MODE_CHAIN, MODE_INNER
+
+f32 = np.float32
 DISABLED = False          # bench.py --force-generic / A-B parity runs: keep f a torch call
 _last = None
 
@@ -10,7 +29,164 @@ def last_used():
     return _last
 
 
-def try_fixed(f, x, ts, sv, solver):
+class MLPField(nn.Module):
+    """Functional-API helper: ``odeint(MLPField(net), x, t_span, ...)`` == ``odeint(lambda t, x: net(x), ...)`` but
+    lets the library see (and fuse) the network."""
+
+    def __init__(self, net: nn.Sequential):
+        super().__init__()
+        self.net = net
+        self.nfe = 0.0
+
+    def forward(self, t, x, args={}):
+        self.nfe += 1
+        return self.net(x)
+
+
+def _unwrap(f):
+    """-> (nn.Sequential | None, [objects whose .nfe must advance])"""
+    from .core.defunc import DEFunc, DEFuncBase
+    counters = []
+    cur = f
+    for _ in range(4):
+        if isinstance(cur, MLPField):
+            counters.append(cur)
+            return cur.net, counters
+        if isinstance(cur, DEFunc):
+            if cur.order > 1 or (cur.integral_loss is not None and cur.sensitivity == "autograd"):
+                return None, []
+            counters.append(cur)
+            cur = cur.vf
+            continue
+        if isinstance(cur, DEFuncBase):
+            if cur.has_time_arg:
+                return None, []
+            counters.append(cur)
+            cur = cur.vf
+            continue
+        break
+    return (cur, counters) if isinstance(cur, nn.Sequential) and counters else (None, [])
+
+
+_cache = weakref.WeakKeyDictionary()      # nn.Sequential -> FusedMLP | False (kept off the module: it must stay picklable)
+_ACTS = {nn.Tanh: ACT_TANH, nn.Softplus: ACT_SOFTPLUS, nn.ReLU: ACT_RELU}
+
+
+class FusedMLP:
+    """Descriptor (``tdyn_mlp_t``) + prepared weight images of one fusable network, cached on the module."""
+
+    def __init__(self, net: nn.Sequential):
+        mods = list(net)
+        if len(mods) < 3 or len(mods) % 2 == 0:
+            raise ValueError("not Linear(-act-Linear)+")
+        linears, acts = mods[0::2], mods[1::2]
+        if not all(type(m) is nn.Linear and m.bias is not None for m in linears):
+            raise ValueError("non-Linear layer")
+        kinds = {type(a) for a in acts}
+        if len(kinds) != 1 or next(iter(kinds)) not in _ACTS:
+            raise ValueError("unsupported activation")
+        a0 = acts[0]
+        if isinstance(a0, nn.Softplus) and not all(a.beta == 1 and a.threshold == 20 for a in acts):
+            raise ValueError("Softplus must have beta=1, threshold=20")
+        if len(linears) > _lib.MAX_LAYERS:
+            raise ValueError("too deep")
+        for a, b in zip(linears[:-1], linears[1:]):
+            if a.out_features != b.in_features:
+                raise ValueError("shape chain broken")
+        if linears[0].in_features != linears[-1].out_features:
+            raise ValueError("not an autonomous vector field")
+        self.linears = linears
+        self.act = _ACTS[type(a0)]
+        self.dims = [linears[0].in_features] + [m.out_features for m in linears]
+        self.flops_per_row = 2.0 * sum(a * b for a, b in zip(self.dims[:-1], self.dims[1:]))
+        self._key = None
+        self._desc = None
+        self._img = None
+
+    def _params_key(self):
+        return tuple((p.data_ptr(), p._version) for m in self.linears for p in (m.weight, m.bias))
+
+    def ready(self, kern) -> bool:
+        """(Re)build descriptor + weight image if the parameters changed; False if this net has no fused kernel."""
+        ps = [p for m in self.linears for p in (m.weight, m.bias)]
+        if not all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in ps):
+            return False
+        key = self._params_key()
+        if key == self._key:
+            return self._img is not None
+        d = _lib.MlpDesc()
+        d.n_layers = len(self.linears)
+        for i, v in enumerate(self.dims):
+            d.dims[i] = v
+        d.act = self.act
+        for i, m in enumerate(self.linears):
+            d.w[i] = m.weight.data_ptr()
+            d.b[i] = m.bias.data_ptr()
+        self._key, self._desc, self._img = key, d, None
+        if not kern.mlp_tc_supported(d):
+            return False
+        self._img = kern.mlp_tc_prepare(d)
+        return True
+
+
+def _get_fused(f) -> Optional[tuple]:
+    net, counters = _unwrap(f)
+    if net is None:
+        return None
+    fm = _cache.get(net)
+    if fm is None:
+        try:
+            fm = FusedMLP(net)
+        except ValueError:
+            fm = False
+        _cache[net] = fm
+    return (fm, counters) if fm else None
+
+
+def _isclose_count(t, save_at: np.ndarray) -> int:
+    return int(np.sum(np.abs(f32(t) - save_at) <= (1e-8 + 1e-5 * np.abs(save_at))))
+
+
+def try_fixed(f, x, ts, sv, solver) -> Optional[List[torch.Tensor]]:
+    """Fixed-step solve (euler / rk4) of a fusable MLP field entirely inside this library: one
+    ``tdyn_mlp_tc_stage`` launch per RK stage (stage combination in its prologue, the solution update in the
+    last stage's epilogue).  Returns the list of saved states or None when the generic path must be used."""
     global _last
     _last = None
-    return None
+    if DISABLED or not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
+        return None
+    got = _get_fused(f)
+    if got is None:
+        return None
+    fm, counters = got
+    kern = _kernels.get(x)
+    if not getattr(kern, "is_cuda", False) or x.shape[1] != fm.dims[0] or not fm.ready(kern):
+        return None
+    x = x if x.is_contiguous() else x.contiguous()
+    p = solver.plan()
+    n_stage = len(p.stages) + 1
+    ks = [torch.empty_like(x) for _ in range(n_stage)]
+    t, dt = f32(ts[0]), f32(ts[1] - ts[0])
+    sol = [x] if _isclose_count(t, sv) else []
+    spare, keep_x = None, True      # never recycle the caller's tensor or a saved state
+    with torch.no_grad():
+        for step in range(1, len(ts)):
+            x_new = spare if spare is not None else torch.empty_like(x)
+            for i in range(n_stage):
+                last = i == n_stage - 1
+                coefs = p.stages[i - 1].coefs if i > 0 else ()
+                mode = p.stages[i - 1].mode if i > 0 else MODE_INNER
+                kern.mlp_tc_stage(fm._desc, fm._img, ks[i], x, ks[:len(coefs)], coefs, mode, dt,
+                                  x_new if last else None, p.bsol if last else (), fm.flops_per_row)
+            t = f32(t + dt)
+            saved = bool(_isclose_count(t, sv))
+            if saved:
+                sol.append(x_new)
+            spare = None if keep_x else x
+            x, keep_x = x_new, saved
+            if step < len(ts) - 1:
+                dt = f32(ts[step + 1] - t)
+    for c in counters:
+        c.nfe += n_stage * (len(ts) - 1)
+    _last = "fused tcgen05 3xTF32 MLP stage kernel (tdyn_mlp_tc_stage)"
+    return sol
