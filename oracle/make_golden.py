@@ -29,7 +29,7 @@ from oracle import erk_oracle as eo  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def mlp(dims, act="tanh", seed=0):
+def mlp(dims, act="tanh", seed=0, gain=1.0):
     torch.manual_seed(seed)
     acts = {"tanh": nn.Tanh, "softplus": nn.Softplus, "relu": nn.ReLU}
     layers = []
@@ -37,7 +37,12 @@ def mlp(dims, act="tanh", seed=0):
         layers.append(nn.Linear(dims[i], dims[i + 1]))
         if i < len(dims) - 2:
             layers.append(acts[act]())
-    return nn.Sequential(*layers)
+    net = nn.Sequential(*layers)
+    if gain != 1.0:   # "active controller" fixtures: larger weights -> error estimates far above the fp32 noise floor
+        with torch.no_grad():
+            for p in net.parameters():
+                p.mul_(gain)
+    return net
 
 
 def moons(n, seed=0):
@@ -135,6 +140,16 @@ def neuralode_cases():
     cases["c3r_tsit5_interp"] = dict(
         dims=[16, 128, 16], act="tanh", seed=3, x=torch.randn(128, 16), y=None, t_span=torch.linspace(0, 1, 2),
         loss="sqmean", kw=dict(solver="tsit5", sensitivity="interpolated_adjoint"))
+    # active-controller cases (single interval, scaled weights): error ratios ~0.2-0.9, the step sequence is decided
+    # by the controller rather than by checkpoint clamps or rounding noise
+    torch.manual_seed(6)
+    xa = torch.randn(256, 4) * 2
+    cases["act_dopri5_adjoint"] = dict(
+        dims=[4, 64, 4], act="tanh", seed=5, gain=3.0, x=xa, y=None, t_span=torch.tensor([0.0, 4.0]), loss="sqmean",
+        kw=dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="adjoint", atol_adjoint=1e-4, rtol_adjoint=1e-4))
+    cases["act_tsit5_interp"] = dict(
+        dims=[4, 64, 4], act="tanh", seed=5, gain=4.0, x=xa, y=None, t_span=torch.tensor([0.0, 4.0]), loss="sqmean",
+        kw=dict(solver="tsit5", atol=1e-4, rtol=1e-4, sensitivity="interpolated_adjoint"))
     return cases
 
 
@@ -159,6 +174,12 @@ def functional_cases():
                                        kw=dict(solver="dopri5", atol=1e-6, rtol=1e-6))
     cases["fn_tsit5_all_eval"] = dict(dims=[3, 16, 3], act="tanh", seed=7, x=x, t_span=torch.linspace(0, 3, 3),
                                       kw=dict(solver="tsit5", atol=1e-6, rtol=1e-6, return_all_eval=True))
+    torch.manual_seed(6)
+    xa = torch.randn(256, 4) * 2
+    cases["act_tsit5_fn"] = dict(dims=[4, 64, 4], act="tanh", seed=5, gain=4.0, x=xa, t_span=torch.tensor([0.0, 4.0]),
+                                 kw=dict(solver="tsit5", atol=1e-4, rtol=1e-4, return_all_eval=True))
+    cases["act_dopri5_4th_fn"] = dict(dims=[4, 64, 4], act="tanh", seed=5, gain=4.0, x=xa, t_span=torch.linspace(0, 4, 9),
+                                      kw=dict(solver="dopri5", atol=1e-4, rtol=1e-4, interpolator="4th"))
     cases["fn_rk4_save_at"] = dict(dims=[3, 16, 3], act="tanh", seed=7, x=x, t_span=torch.linspace(0, 1, 21),
                                    kw=dict(solver="rk4"), save_last=True)
     # cfg 2 reduced: rk4 100 steps, MLP 32-256-256-32, B=64, forward only, save last
@@ -178,7 +199,7 @@ def main():
     torch.set_num_threads(1)  # reduction order of torch CPU kernels is thread-count independent for these sizes, but pin it
 
     for name, c in neuralode_cases().items():
-        net = mlp(c["dims"], c["act"], c["seed"])
+        net = mlp(c["dims"], c["act"], c["seed"], c.get("gain", 1.0))
         loss_fn = (lambda sol, c=c: LOSSES[c["loss"]](sol, c["y"]))
         out = run_ref_neuralode(net, c["x"], c["t_span"], loss_fn, **c["kw"])
         if args.check:
@@ -190,7 +211,7 @@ def main():
         print(f"{name}: nfe={out['nfe_total']:.0f} attempts per odeint call={ntr} len(t_eval)={len(out['t_eval'])}")
 
     for name, c in functional_cases().items():
-        net = mlp(c["dims"], c["act"], c["seed"])
+        net = mlp(c["dims"], c["act"], c["seed"], c.get("gain", 1.0))
         kw = dict(c["kw"])
         if c.get("save_last"):
             kw["save_at"] = c["t_span"][-1:]
