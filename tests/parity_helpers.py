@@ -28,6 +28,9 @@ def assert_close(a, b, what, rtol=STATE_RTOL, atol_scale=2e-6):
     assert not bad.any(), f"{what}: max abs diff {float((a - b).abs().max()):.3e} (atol {atol:.2e}, rtol {rtol})"
 
 
+LAST_STRICT_FLAGS = []     # per odeint call of the most recent assert_traces: passed the strict comparison?
+
+
 def _noise_driven(ratios):
     """True when some attempt's successor step size is decided by rounding noise: its error ratio is far below 1
     (the embedded estimate is at the fp32 noise floor) yet not small enough to clip the growth factor at
@@ -53,16 +56,19 @@ def assert_traces(ref_traces, got_traces, exact=False):
     loose one (same end time, step count within +-1).  Returns True if every call passed the strict comparison."""
     assert len(ref_traces) == len(got_traces), (len(ref_traces), len(got_traces))
     all_strict = True
+    LAST_STRICT_FLAGS.clear()
     for r, g in zip(ref_traces, got_traces):
         if exact:
             assert r["dt0"] == g["dt0"] and r["t"] == g["t"] and r["dt"] == g["dt"] and r["ratio"] == g["ratio"]
             continue
         try:
             _compare_call(r, g, T_RTOL_ACTIVE)
+            LAST_STRICT_FLAGS.append(True)
         except AssertionError:
             if not _noise_driven(r["ratio"]):
                 raise
             all_strict = False
+            LAST_STRICT_FLAGS.append(False)
             assert abs(len(r["t"]) - len(g["t"])) <= 1, (len(r["t"]), len(g["t"]))
             np.testing.assert_allclose(g["t"][0], r["t"][0], rtol=1e-6, atol=1e-7)
             np.testing.assert_allclose(g["t"][-1] + g["dt"][-1], r["t"][-1] + r["dt"][-1], rtol=1e-5, atol=1e-6)
@@ -87,7 +93,7 @@ def run_neuralode_case(fx, device, net=None):
     return dict(model=model, net=net, x=x, t_eval=t_eval, sol=sol, loss=loss, traces=traces, nfe_fwd=nfe_f)
 
 
-def check_neuralode_case(fx, out, exact=False):
+def check_neuralode_case(fx, out, exact=False, state_rtol=STATE_RTOL):
     """exact=True (CPU host-logic tests, checker arithmetic below the ABI): bit-identical to the executed reference."""
     ref = fx["ref"]
     strict = assert_traces(ref["traces"], out["traces"], exact=exact)
@@ -97,7 +103,7 @@ def check_neuralode_case(fx, out, exact=False):
         assert all(torch.equal(p.grad, g) for p, g in zip(out["net"].parameters(), ref["gp"]))
     # when a noise-driven call took slightly different steps the solutions agree to the SOLVER tolerance, not to 1e-5
     tol = max(fx["kw"].get("atol", 1e-3), fx["kw"].get("rtol", 1e-3), fx["kw"].get("atol_adjoint", 1e-4))
-    s_rtol, g_rtol, a_scale = (STATE_RTOL, 2e-5, 5e-6) if strict else (20 * tol, 20 * tol, 20 * tol)
+    s_rtol, g_rtol, a_scale = (state_rtol, 2 * state_rtol, 0.5 * state_rtol) if strict else (20 * tol, 20 * tol, 20 * tol)
     if strict:
         assert out["sol"].shape[0] == ref["sol_len"]
         te = out["t_eval"].detach().cpu().numpy()
@@ -105,7 +111,7 @@ def check_neuralode_case(fx, out, exact=False):
         np.testing.assert_allclose(te[[0, -1]], ref["t_eval"].numpy()[[0, -1]], rtol=T_RTOL, atol=1e-7)
         assert out["nfe_fwd"] == ref["nfe_fwd"] and out["model"].vf.nfe == ref["nfe_total"], \
             (out["nfe_fwd"], ref["nfe_fwd"], out["model"].vf.nfe, ref["nfe_total"])
-    assert_close(out["sol"][-1], ref["sol_last"], "final state", rtol=s_rtol, atol_scale=a_scale if not strict else 2e-6)
+    assert_close(out["sol"][-1], ref["sol_last"], "final state", rtol=s_rtol, atol_scale=a_scale if not strict else 0.2 * state_rtol)
     assert_close(out["loss"], ref["loss"], "loss", rtol=s_rtol)
     assert_close(out["x"].grad, ref["gx"], "dL/dx0", rtol=g_rtol, atol_scale=a_scale)
     for i, (p, g) in enumerate(zip(out["net"].parameters(), ref["gp"])):
@@ -130,7 +136,7 @@ def run_functional_case(fx, device, f=None):
     return t_eval, sol, traces
 
 
-def check_functional_case(fx, t_eval, sol, traces, exact=False):
+def check_functional_case(fx, t_eval, sol, traces, exact=False, state_rtol=STATE_RTOL):
     ref = fx["ref"]
     if exact:
         assert torch.equal(t_eval.detach().cpu(), ref["t_eval"]) and torch.equal(sol.cpu(), ref["sol"])
@@ -139,7 +145,7 @@ def check_functional_case(fx, t_eval, sol, traces, exact=False):
     if strict:
         assert sol.shape == ref["sol"].shape, (sol.shape, ref["sol"].shape)
         np.testing.assert_allclose(t_eval.detach().cpu().numpy(), ref["t_eval"].numpy(), rtol=T_RTOL_ACTIVE, atol=1e-7)
-        assert_close(sol, ref["sol"], "solution")
+        assert_close(sol, ref["sol"], "solution", rtol=state_rtol, atol_scale=0.2 * state_rtol)
     else:
         tol = 20 * max(fx["kw"].get("atol", 1e-3), fx["kw"].get("rtol", 1e-3))
         assert_close(sol[-1], ref["sol"][-1], "final state (noise-driven step sizes)", rtol=tol, atol_scale=tol)
