@@ -6,7 +6,7 @@
 //
 // Shape class (BASELINE.json configs[1]): state dim D = 32, two hidden layers of width 256, three Linear layers.
 // One persistent CTA per SM walks 128-row tiles of the batch.  Per tile:
-//   workers (8 warps)  : load x/k rows, combine in the reference's rounding order, split y into TF32 hi/lo and
+//   workers (16 warps) : load x/k rows, combine in the reference's rounding order, split y into TF32 hi/lo and
 //                        store it K-major / 128B-swizzled in shared memory (the UMMA canonical layout);
 //   MMA warp (1 thread): layer 1 as tcgen05.mma kind::tf32  D1[128x256] (TMEM cols 0..255)
 //                        = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (3xTF32: fp32-accurate products, fp32 accumulate);
@@ -27,7 +27,7 @@ namespace tc {
 constexpr int kD = 32;          // state dim
 constexpr int kH = 256;         // hidden width
 constexpr int kTileM = 128;     // rows per tile = TMEM lanes
-constexpr int kWorkers = 256;   // 8 epilogue/prologue warps
+constexpr int kWorkers = 512;   // 16 epilogue/prologue warps (4 per TMEM lane quarter)
 constexpr int kThreads = 64 + kWorkers;
 constexpr int kKB = 32;         // K-block: 32 fp32 = 128 B = one swizzle row
 constexpr uint32_t kATile = kTileM * 128;           // 16 KB: one [128 x 32] operand tile
@@ -42,7 +42,7 @@ constexpr uint32_t kSmemTotal = kSmemBars + 256 + 1024;   // + slack for the man
 constexpr uint32_t kTmemCols = 512;
 
 enum Bar { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, A_FULL0, A_FULL1, A_EMPTY0, A_EMPTY1, A1_FULL, D1_FULL, D2_FULL,
-           D3_FULL, D_FREE, NUM_BARS };
+           D3_FULL, D_FREE, D1_FREE, NUM_BARS };
 
 struct Params {
     const uint8_t* wimg;       // 10 x 64 KB stage images
@@ -93,19 +93,6 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-// 16 consecutive fp32 columns of this warp's 32 TMEM lanes -> 16 registers per thread (thread = lane = row)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // UMMA shared-memory descriptor: K-major operand tile, 128-byte swizzle, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -136,28 +123,38 @@ template <int ACT>
 __device__ __forceinline__ float activate(float z) {
     if (ACT == TDYN_ACT_RELU) return fmaxf(z, 0.f);
     if (ACT == TDYN_ACT_SOFTPLUS) return z > 20.f ? z : log1pf(__expf(z));
-    // tanh with ~2e-7 relative error everywhere: odd polynomial near 0, 1 - 2/(1+e^{2z}) elsewhere (2 MUFU).
-    const float z2 = z * z;
-    float p = fmaf(z2, 2.1869488e-2f, -5.3968254e-2f);       // 62/2835, -17/315
-    p = fmaf(z2, p, 1.3333333e-1f);                          // 2/15
-    p = fmaf(z2, p, -3.3333334e-1f);                         // -1/3
-    const float small = fmaf(z * z2, p, z);
+    // tanh(z) = 1 - 2/(1 + 2^(2z*log2e)): 2 MUFU + 3 FP32 ops, absolute error ~1e-7 (saturates correctly at +-1).
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * 2.8853900817779268f));
-    const float big = 1.f - __fdividef(2.f, 1.f + e);
-    return fabsf(z) < 0.25f ? small : big;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return fmaf(-2.f, r, 1.f);
 }
 
-// 16 activations of one row -> hi/lo TF32 pieces into the [128 x 32] operand tiles at `stage` (hi) / +16 KB (lo)
-__device__ __forceinline__ void store_split16(uint8_t* stage, int row, int half, const float (&a)[16]) {
+// 8 consecutive fp32 columns of this warp's 32 TMEM lanes (thread = lane = row); completion via tmem_wait8
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+// the registers are in/out operands so that no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait8(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :: "memory");
+}
+
+// 8 activations of one row -> hi/lo TF32 pieces into the [128 x 32] operand tiles at `stage` (hi) / +16 KB (lo).
+// hi = rna_tf32(a); lo = a - hi is exact in fp32 and is truncated to TF32 by the tensor core (error 2^-22 |a|).
+__device__ __forceinline__ void store_split8(uint8_t* stage, int row, int sub, const float (&a)[8]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
         float4 hi, lo;
-        hi.x = tf32_rna(a[4 * i + 0]); lo.x = tf32_rna(a[4 * i + 0] - hi.x);
-        hi.y = tf32_rna(a[4 * i + 1]); lo.y = tf32_rna(a[4 * i + 1] - hi.y);
-        hi.z = tf32_rna(a[4 * i + 2]); lo.z = tf32_rna(a[4 * i + 2] - hi.z);
-        hi.w = tf32_rna(a[4 * i + 3]); lo.w = tf32_rna(a[4 * i + 3] - hi.w);
-        const uint32_t off = swz((uint32_t)row, (uint32_t)(half * 4 + i));
+        hi.x = tf32_rna(a[4 * i + 0]); lo.x = a[4 * i + 0] - hi.x;
+        hi.y = tf32_rna(a[4 * i + 1]); lo.y = a[4 * i + 1] - hi.y;
+        hi.z = tf32_rna(a[4 * i + 2]); lo.z = a[4 * i + 2] - hi.z;
+        hi.w = tf32_rna(a[4 * i + 3]); lo.w = a[4 * i + 3] - hi.w;
+        const uint32_t off = swz((uint32_t)row, (uint32_t)(sub * 2 + i));
         *reinterpret_cast<float4*>(stage + off) = hi;
         *reinterpret_cast<float4*>(stage + kATile + off) = lo;
     }
@@ -177,6 +174,65 @@ __device__ __forceinline__ void issue_kblock(uint32_t d_tmem, uint32_t a_hi, uin
     }
 }
 
+struct WorkerCtx {
+    int row, sub;
+    uint32_t lane_addr;
+};
+
+// stage input of one tile: y = combine(x, k, coef) for 8 elements of this thread's row -> A1 (hi/lo, swizzled)
+__device__ __forceinline__ void prologue(const Params& P, uint8_t* smem, const WorkerCtx& w, int64_t tile) {
+    const int64_t grow = tile * kTileM + w.row;
+    const bool valid = grow < P.rows;
+    const size_t goff = (size_t)grow * kD + w.sub * 8;
+    float xv[8], y[8];
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(P.x + goff) + i);
+            xv[4 * i] = q.x; xv[4 * i + 1] = q.y; xv[4 * i + 2] = q.z; xv[4 * i + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xv[i] = 0.f;
+    }
+    if (P.n_k == 0 || !valid) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = xv[i];
+    } else if (P.mode == TDYN_MODE_CHAIN) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = xv[i];
+        for (int j = 0; j < P.n_k; ++j) {
+            const float da = mul_rn(P.dt, P.coef.c[j]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(P.k.p[j] + goff) + i);
+                y[4 * i] = add_rn(y[4 * i], mul_rn(da, q.x));
+                y[4 * i + 1] = add_rn(y[4 * i + 1], mul_rn(da, q.y));
+                y[4 * i + 2] = add_rn(y[4 * i + 2], mul_rn(da, q.z));
+                y[4 * i + 3] = add_rn(y[4 * i + 3], mul_rn(da, q.w));
+            }
+        }
+    } else {
+        float s[8];
+        for (int j = 0; j < P.n_k; ++j) {
+            const float a = P.coef.c[j];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(P.k.p[j] + goff) + i);
+                const float m0 = mul_rn(a, q.x), m1 = mul_rn(a, q.y), m2 = mul_rn(a, q.z), m3 = mul_rn(a, q.w);
+                s[4 * i] = j == 0 ? m0 : add_rn(s[4 * i], m0);
+                s[4 * i + 1] = j == 0 ? m1 : add_rn(s[4 * i + 1], m1);
+                s[4 * i + 2] = j == 0 ? m2 : add_rn(s[4 * i + 2], m2);
+                s[4 * i + 3] = j == 0 ? m3 : add_rn(s[4 * i + 3], m3);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = add_rn(xv[i], mul_rn(P.dt, s[i]));
+    }
+    store_split8(smem + kSmemA1, w.row, w.sub, y);
+    fence_proxy_async();
+}
+
 template <int ACT>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params P) {
     extern __shared__ uint8_t smem_raw[];
@@ -191,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NUM_BARS; ++i) {
             uint32_t cnt = 1;
-            if (i == A_FULL0 || i == A_FULL1 || i == A1_FULL || i == D_FREE) cnt = kWorkers;
+            if (i == A_FULL0 || i == A_FULL1 || i == A1_FULL || i == D_FREE || i == D1_FREE) cnt = kWorkers;
             mbar_init(bar(i), cnt);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -205,21 +261,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
     const int my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // TMEM map: D1 = cols [0,256); D2 = cols [256,512); D3 = cols [256,288) (D2's first chunk, drained before L3 starts)
+    constexpr uint32_t kColD1 = 0, kColD2 = 256, kColD3 = 256;
 
     if (warp == 0) {
-        // ================= weight producer =================
+        // ================= weight producer: W1(0) | per tile: W2[0..7], W1(next tile), W3 =================
         if (lane == 0) {
             uint32_t it = 0;
+            auto load = [&](int s) {
+                const uint32_t slot = it & 1, use = it >> 1;
+                mbar_wait(bar(W_EMPTY0 + slot), (use & 1) ^ 1);
+                mbar_expect_tx(bar(W_FULL0 + slot), kWStage);
+                const uint32_t dst = sbase + kSmemWRing + slot * kWStage;
+                const uint8_t* src = P.wimg + (size_t)s * kWStage;
+                bulk_g2s(dst, src, kWStage / 2, bar(W_FULL0 + slot));
+                bulk_g2s(dst + kWStage / 2, src + kWStage / 2, kWStage / 2, bar(W_FULL0 + slot));
+                ++it;
+            };
+            if (my_tiles > 0) load(0);
             for (int t = 0; t < my_tiles; ++t) {
-                for (int s = 0; s < kWStagesPerTile; ++s, ++it) {
-                    const uint32_t slot = it & 1, use = it >> 1;
-                    mbar_wait(bar(W_EMPTY0 + slot), (use & 1) ^ 1);
-                    mbar_expect_tx(bar(W_FULL0 + slot), kWStage);
-                    const uint32_t dst = sbase + kSmemWRing + slot * kWStage;
-                    const uint8_t* src = P.wimg + (size_t)s * kWStage;
-                    bulk_g2s(dst, src, kWStage / 2, bar(W_FULL0 + slot));
-                    bulk_g2s(dst + kWStage / 2, src + kWStage / 2, kWStage / 2, bar(W_FULL0 + slot));
-                }
+                for (int s = 1; s <= 8; ++s) load(s);
+                if (t + 1 < my_tiles) load(0);
+                load(9);
             }
         }
     } else if (warp == 1) {
@@ -227,22 +290,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
         if (lane == 0) {
             uint32_t wit = 0, ait = 0;
             const uint32_t a1 = sbase + kSmemA1;
+            auto layer1 = [&](int t) {          // [128 x 32] x [256 x 32]^T -> D1
+                mbar_wait(bar(A1_FULL), t & 1);
+                const uint32_t slot = wit & 1, use = wit >> 1;
+                mbar_wait(bar(W_FULL0 + slot), use & 1);
+                tc_fence_after();
+                const uint32_t w = sbase + kSmemWRing + slot * kWStage;
+                issue_kblock(tmem + kColD1, a1, a1 + kATile, w, w + kWStage / 2, umma_idesc(kH), true);
+                tc_commit(bar(W_EMPTY0 + slot));
+                tc_commit(bar(D1_FULL));
+                ++wit;
+            };
+            if (my_tiles > 0) layer1(0);
             for (int t = 0; t < my_tiles; ++t) {
-                const uint32_t tpar = t & 1;
-                if (t > 0) mbar_wait(bar(D_FREE), (t - 1) & 1);       // previous tile's TMEM fully read
-                // ---- layer 1: [128 x 32] x [256 x 32]^T -> D1 (cols 0..255)
-                mbar_wait(bar(A1_FULL), tpar);
-                {
-                    const uint32_t slot = wit & 1, use = wit >> 1;
-                    mbar_wait(bar(W_FULL0 + slot), use & 1);
-                    tc_fence_after();
-                    const uint32_t w = sbase + kSmemWRing + slot * kWStage;
-                    issue_kblock(tmem + 0, a1, a1 + kATile, w, w + kWStage / 2, umma_idesc(kH), true);
-                    tc_commit(bar(W_EMPTY0 + slot));
-                    tc_commit(bar(D1_FULL));
-                    ++wit;
-                }
-                // ---- layer 2: 8 K-blocks -> D2 (cols 256..511)
+                // ---- layer 2: 8 K-blocks -> D2; the previous tile's D3 lives in D2's first columns
+                if (t > 0) mbar_wait(bar(D_FREE), (t - 1) & 1);
                 for (int j = 0; j < kH / kKB; ++j, ++wit, ++ait) {
                     const uint32_t ws = wit & 1, wu = wit >> 1, as = ait & 1, au = ait >> 1;
                     mbar_wait(bar(A_FULL0 + as), au & 1);
@@ -250,12 +312,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                     tc_fence_after();
                     const uint32_t a = sbase + kSmemARing + as * kAStage;
                     const uint32_t w = sbase + kSmemWRing + ws * kWStage;
-                    issue_kblock(tmem + 256, a, a + kATile, w, w + kWStage / 2, umma_idesc(kH), j == 0);
+                    issue_kblock(tmem + kColD2, a, a + kATile, w, w + kWStage / 2, umma_idesc(kH), j == 0);
                     tc_commit(bar(W_EMPTY0 + ws));
                     tc_commit(bar(A_EMPTY0 + as));
                 }
                 tc_commit(bar(D2_FULL));
-                // ---- layer 3: 8 K-blocks, N = 32 -> D3 (cols 0..31); W3 stage = 8 x [hi 4 KB | lo 4 KB]
+                // ---- next tile's layer 1 runs on the tensor pipe while the workers convert D2
+                if (t + 1 < my_tiles) {
+                    mbar_wait(bar(D1_FREE), t & 1);
+                    layer1(t + 1);
+                }
+                // ---- layer 3: 8 K-blocks, N = 32 -> D3; W3 stage = 8 x [hi 4 KB | lo 4 KB]
                 {
                     const uint32_t ws = wit & 1, wu = wit >> 1;
                     mbar_wait(bar(W_FULL0 + ws), wu & 1);
@@ -266,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                         tc_fence_after();
                         const uint32_t a = sbase + kSmemARing + as * kAStage;
                         const uint32_t wj = w + (uint32_t)j * 8192u;
-                        issue_kblock(tmem + 0, a, a + kATile, wj, wj + 4096u, umma_idesc(kD), j == 0);
+                        issue_kblock(tmem + kColD3, a, a + kATile, wj, wj + 4096u, umma_idesc(kD), j == 0);
                         tc_commit(bar(A_EMPTY0 + as));
                     }
                     tc_commit(bar(W_EMPTY0 + ws));
@@ -277,118 +344,86 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
         }
     } else {
         // ================= workers: prologue / activation epilogues / output =================
-        const int wk = warp - 2;                       // 0..7
+        WorkerCtx w;
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
-        const int half = wk >> 2;                      // which 16 of every 32 columns
-        const int row = quarter * 32 + lane;           // row inside the tile == TMEM lane
-        const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+        w.sub = (warp - 2) >> 2;                       // which 8 of every 32 columns (0..3)
+        w.row = quarter * 32 + lane;                   // row inside the tile == TMEM lane
+        w.lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
         uint32_t ait = 0;
+        if (my_tiles > 0) {
+            prologue(P, smem, w, (int64_t)blockIdx.x);
+            mbar_arrive(bar(A1_FULL));
+        }
         for (int t = 0; t < my_tiles; ++t) {
             const uint32_t tpar = t & 1;
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
-            const int64_t grow = tile * kTileM + row;
-            const bool valid = grow < P.rows;
-            const size_t goff = (size_t)grow * kD + half * 16;
-            // ---- prologue: y = combine(x, k, coef) for 16 elements of this row; A1 was released by the previous L1
-            float xv[16], y[16];
-            if (valid) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 q = __ldg(reinterpret_cast<const float4*>(P.x + goff) + i);
-                    xv[4 * i] = q.x; xv[4 * i + 1] = q.y; xv[4 * i + 2] = q.z; xv[4 * i + 3] = q.w;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) xv[i] = 0.f;
-            }
-            if (P.n_k == 0 || !valid) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) y[i] = xv[i];
-            } else if (P.mode == TDYN_MODE_CHAIN) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) y[i] = xv[i];
-                for (int j = 0; j < P.n_k; ++j) {
-                    const float da = mul_rn(P.dt, P.coef.c[j]);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 q = __ldg(reinterpret_cast<const float4*>(P.k.p[j] + goff) + i);
-                        y[4 * i] = add_rn(y[4 * i], mul_rn(da, q.x));
-                        y[4 * i + 1] = add_rn(y[4 * i + 1], mul_rn(da, q.y));
-                        y[4 * i + 2] = add_rn(y[4 * i + 2], mul_rn(da, q.z));
-                        y[4 * i + 3] = add_rn(y[4 * i + 3], mul_rn(da, q.w));
-                    }
-                }
-            } else {
-                float s[16];
-                for (int j = 0; j < P.n_k; ++j) {
-                    const float a = P.coef.c[j];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 q = __ldg(reinterpret_cast<const float4*>(P.k.p[j] + goff) + i);
-                        const float m0 = mul_rn(a, q.x), m1 = mul_rn(a, q.y), m2 = mul_rn(a, q.z), m3 = mul_rn(a, q.w);
-                        s[4 * i] = j == 0 ? m0 : add_rn(s[4 * i], m0);
-                        s[4 * i + 1] = j == 0 ? m1 : add_rn(s[4 * i + 1], m1);
-                        s[4 * i + 2] = j == 0 ? m2 : add_rn(s[4 * i + 2], m2);
-                        s[4 * i + 3] = j == 0 ? m3 : add_rn(s[4 * i + 3], m3);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) y[i] = add_rn(xv[i], mul_rn(P.dt, s[i]));
-            }
-            store_split16(smem + kSmemA1, row, half, y);
-            fence_proxy_async();
-            mbar_arrive(bar(A1_FULL));
-
             // ---- two activation epilogues: D1 -> layer-2 operand, D2 -> layer-3 operand
 #pragma unroll 1
             for (int layer = 0; layer < 2; ++layer) {
                 mbar_wait(bar(layer == 0 ? D1_FULL : D2_FULL), tpar);
                 tc_fence_after();
-                const float* bias = layer == 0 ? P.b1 : P.b2;
-                const uint32_t dcol = layer == 0 ? 0u : 256u;
-#pragma unroll 1
-                for (int j = 0; j < kH / kKB; ++j, ++ait) {
-                    const uint32_t as = ait & 1, au = ait >> 1;
-                    float v[16];
-                    tmem_ld16(lane_addr + dcol + (uint32_t)(j * kKB + half * 16), v);
+                const float* bias = (layer == 0 ? P.b1 : P.b2) + w.sub * 8;
+                const uint32_t src = w.lane_addr + (layer == 0 ? kColD1 : kColD2) + (uint32_t)(w.sub * 8);
+                uint32_t ra[8], rb[8];
+                tmem_ld8(src, ra);
+                tmem_wait8(ra);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + j * kKB + half * 16) + i);
-                        v[4 * i] = activate<ACT>(v[4 * i] + bq.x);
-                        v[4 * i + 1] = activate<ACT>(v[4 * i + 1] + bq.y);
-                        v[4 * i + 2] = activate<ACT>(v[4 * i + 2] + bq.z);
-                        v[4 * i + 3] = activate<ACT>(v[4 * i + 3] + bq.w);
-                    }
+                for (int j = 0; j < kH / kKB; ++j, ++ait) {
+                    uint32_t (&cur)[8] = (j & 1) ? rb : ra;
+                    uint32_t (&nxt)[8] = (j & 1) ? ra : rb;
+                    if (j + 1 < kH / kKB) tmem_ld8(src + (uint32_t)((j + 1) * kKB), nxt);     // prefetch next chunk
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + j * kKB));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + j * kKB) + 1);
+                    float v[8];
+                    v[0] = activate<ACT>(__uint_as_float(cur[0]) + b0.x); v[1] = activate<ACT>(__uint_as_float(cur[1]) + b0.y);
+                    v[2] = activate<ACT>(__uint_as_float(cur[2]) + b0.z); v[3] = activate<ACT>(__uint_as_float(cur[3]) + b0.w);
+                    v[4] = activate<ACT>(__uint_as_float(cur[4]) + b1.x); v[5] = activate<ACT>(__uint_as_float(cur[5]) + b1.y);
+                    v[6] = activate<ACT>(__uint_as_float(cur[6]) + b1.z); v[7] = activate<ACT>(__uint_as_float(cur[7]) + b1.w);
+                    const uint32_t as = ait & 1, au = ait >> 1;
                     mbar_wait(bar(A_EMPTY0 + as), (au & 1) ^ 1);
-                    store_split16(smem + kSmemARing + as * kAStage, row, half, v);
+                    store_split8(smem + kSmemARing + as * kAStage, w.row, w.sub, v);
                     fence_proxy_async();
                     mbar_arrive(bar(A_FULL0 + as));
+                    if (j + 1 < kH / kKB) tmem_wait8(nxt);
+                }
+                if (layer == 0) {
+                    // D1 fully read: the tensor pipe may overwrite it with the next tile's layer 1 ...
+                    tc_fence_before();
+                    mbar_arrive(bar(D1_FREE));
+                    // ... whose stage input we produce now (A1 is free: this tile's layer 1 has completed)
+                    if (t + 1 < my_tiles) {
+                        prologue(P, smem, w, tile + gridDim.x);
+                        mbar_arrive(bar(A1_FULL));
+                    }
                 }
             }
             // ---- output: k_out = D3 + b3 (and x_new for the last stage of a fixed-step method)
             mbar_wait(bar(D3_FULL), tpar);
             tc_fence_after();
-            float o[16];
-            tmem_ld16(lane_addr + (uint32_t)(half * 16), o);
+            uint32_t ro[8];
+            tmem_ld8(w.lane_addr + kColD3 + (uint32_t)(w.sub * 8), ro);
+            tmem_wait8(ro);
             tc_fence_before();
             mbar_arrive(bar(D_FREE));
+            const int64_t grow = tile * kTileM + w.row;
+            if (grow < P.rows) {
+                const size_t goff = (size_t)grow * kD + w.sub * 8;
+                float o[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 bq = __ldg(reinterpret_cast<const float4*>(P.b3 + half * 16) + i);
-                o[4 * i] += bq.x; o[4 * i + 1] += bq.y; o[4 * i + 2] += bq.z; o[4 * i + 3] += bq.w;
-            }
-            if (valid) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 2; ++i) {
+                    const float4 bq = __ldg(reinterpret_cast<const float4*>(P.b3 + w.sub * 8) + i);
+                    o[4 * i] = __uint_as_float(ro[4 * i]) + bq.x; o[4 * i + 1] = __uint_as_float(ro[4 * i + 1]) + bq.y;
+                    o[4 * i + 2] = __uint_as_float(ro[4 * i + 2]) + bq.z; o[4 * i + 3] = __uint_as_float(ro[4 * i + 3]) + bq.w;
                     reinterpret_cast<float4*>(P.k_out + goff)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
                 if (P.x_new) {
                     // x + dt*(b0*k0 + ... + b_last*k_out)
-                    float s[16];
+                    float s[8];
                     for (int j = 0; j < P.n_sol; ++j) {
                         const float b = P.bsol.c[j];
                         const bool last = j == P.n_sol - 1;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
+                        for (int i = 0; i < 2; ++i) {
                             float4 q;
                             if (last) q = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                             else q = __ldg(reinterpret_cast<const float4*>(P.k.p[j] + goff) + i);
@@ -400,10 +435,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 2; ++i) {
+                        const float4 xq = __ldg(reinterpret_cast<const float4*>(P.x + goff) + i);
                         reinterpret_cast<float4*>(P.x_new + goff)[i] =
-                            make_float4(add_rn(xv[4 * i], mul_rn(P.dt, s[4 * i])), add_rn(xv[4 * i + 1], mul_rn(P.dt, s[4 * i + 1])),
-                                        add_rn(xv[4 * i + 2], mul_rn(P.dt, s[4 * i + 2])), add_rn(xv[4 * i + 3], mul_rn(P.dt, s[4 * i + 3])));
+                            make_float4(add_rn(xq.x, mul_rn(P.dt, s[4 * i])), add_rn(xq.y, mul_rn(P.dt, s[4 * i + 1])),
+                                        add_rn(xq.z, mul_rn(P.dt, s[4 * i + 2])), add_rn(xq.w, mul_rn(P.dt, s[4 * i + 3])));
+                    }
                 }
             }
         }
