@@ -35,7 +35,7 @@ extern "C" {
 #define TDYN_API
 #endif
 
-#define TDYN_ABI_VERSION 3
+#define TDYN_ABI_VERSION 4
 #define TDYN_MAX_STAGES 7
 
 /* combination shapes of the reference steppers (numerics/solvers/ode.py) */
@@ -92,12 +92,27 @@ TDYN_API int tdyn_spline_eval(float* out, const float* a, const float* b, const 
 #define TDYN_MAX_LAYERS 4
 
 typedef struct {
-    int n_layers;                      /* number of Linear layers, 2..4 */
+    int n_layers;                      /* number of Linear layers, 1..4 */
     int dims[TDYN_MAX_LAYERS + 1];     /* dims[0] = state dim = dims[n_layers] */
     int act;                           /* TDYN_ACT_* applied between Linear layers */
     const float* w[TDYN_MAX_LAYERS];   /* device, [dims[l+1], dims[l]] */
     const float* b[TDYN_MAX_LAYERS];   /* device, [dims[l+1]] */
 } tdyn_mlp_t;
+
+/* K1/K3 (stage form). FFMA kernels for NARROW MLP vector fields (every width <= 128, <= 4 Linear layers; weights in
+ * shared memory).  `sign` (+1 / -1) multiplies every output: reversed-time solves integrate -f(-t, .)
+ * (numerics/odeint.py:54-58) without an extra negation pass.
+ *   forward : out = sign * f(y)                                             replaces f(t, y) (core/defunc.py:30-35)
+ *   adjoint : dx = sign*f(x); dlam = sign*(-lam^T df/dx); dmu = sign*(-sum_batch lam^T df/dtheta), i.e. the body of
+ *             adjoint_dynamics (numerics/sensitivity.py:57-75 and :130-147): forward + VJP + the batch-reduced
+ *             parameter-gradient contraction in ONE launch; dmu is in vf.parameters() order (weight [out,in]
+ *             row-major, then bias, layer by layer).  `workspace`: tdyn_mlp_ffma_workspace_bytes() zero-initialised
+ *             bytes (per-CTA partials + ticket; deterministic fixed-order cross-CTA sum). */
+TDYN_API int tdyn_mlp_ffma_supported(const tdyn_mlp_t* mlp);
+TDYN_API int64_t tdyn_mlp_ffma_workspace_bytes(const tdyn_mlp_t* mlp);
+TDYN_API int tdyn_mlp_ffma_forward(const tdyn_mlp_t* mlp, const float* y, float* out, int64_t rows, float sign, void* stream);
+TDYN_API int tdyn_mlp_ffma_adjoint(const tdyn_mlp_t* mlp, const float* x, const float* lam, float* dx, float* dlam,
+                                   float* dmu, void* workspace, int64_t rows, float sign, void* stream);
 
 /* K2. Tensor-core (tcgen05, 3xTF32) stage kernel for wide MLPs (all hidden widths multiples of 64, >= 128):
  *   y = combine(x, k[], coef, mode, dt)   (same semantics as tdyn_rk_combine; n_k == 0 -> y = x)

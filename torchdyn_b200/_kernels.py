@@ -213,6 +213,31 @@ class CudaKernels:
         _lib.check(rc, "tdyn_mlp_tc_stage")
         _launches += 1
 
+    def mlp_ffma_supported(self, desc) -> bool:
+        return bool(self.lib.tdyn_mlp_ffma_supported(C.byref(desc)))
+
+    def mlp_ffma_workspace(self, desc) -> Tensor:
+        return torch.zeros(int(self.lib.tdyn_mlp_ffma_workspace_bytes(C.byref(desc))), dtype=torch.uint8, device=self.device)
+
+    def mlp_ffma_forward(self, desc, y: Tensor, out: Tensor, sign: float, flops_per_row: float):
+        global _launches
+        with _Timed("mlp_ffma_forward", flops_per_row * y.shape[0]):
+            rc = self.lib.tdyn_mlp_ffma_forward(C.byref(desc), y.data_ptr(), out.data_ptr(), y.shape[0], float(sign),
+                                                self._stream())
+        _lib.check(rc, "tdyn_mlp_ffma_forward")
+        _launches += 1
+        return out
+
+    def mlp_ffma_adjoint(self, desc, x: Tensor, lam: Tensor, dx: Tensor, dlam: Tensor, dmu: Tensor, ws: Tensor,
+                         rows: int, sign: float, flops_per_row: float):
+        """x, lam, dx, dlam: [rows*D] fp32 (possibly views into the flat adjoint vector); dmu: [P]."""
+        global _launches
+        with _Timed("mlp_ffma_adjoint", 3.0 * flops_per_row * rows):
+            rc = self.lib.tdyn_mlp_ffma_adjoint(C.byref(desc), x.data_ptr(), lam.data_ptr(), dx.data_ptr(), dlam.data_ptr(),
+                                                dmu.data_ptr(), ws.data_ptr(), int(rows), float(sign), self._stream())
+        _lib.check(rc, "tdyn_mlp_ffma_adjoint")
+        _launches += 1
+
     def read_reduction(self, n: int = 1):
         """Device -> pinned host read of the first ``n`` reduction results (the step's ONE host sync)."""
         self.red_host[:n].copy_(self.red[:n], non_blocking=True)

@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdyn_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_STAGES = 7
 MAX_LAYERS = 4
 MODE_CHAIN, MODE_INNER = 0, 1
@@ -49,6 +49,11 @@ SIGNATURES = {
                                     C.c_float, C.c_void_p]),
     "tdyn_spline_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int64,
                                    C.c_void_p]),
+    "tdyn_mlp_ffma_supported": (C.c_int, [C.POINTER(MlpDesc)]),
+    "tdyn_mlp_ffma_workspace_bytes": (C.c_int64, [C.POINTER(MlpDesc)]),
+    "tdyn_mlp_ffma_forward": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
+    "tdyn_mlp_ffma_adjoint": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "tdyn_mlp_tc_prepared_bytes": (C.c_int64, [C.POINTER(MlpDesc)]),
     "tdyn_mlp_tc_supported": (C.c_int, [C.POINTER(MlpDesc)]),
     "tdyn_mlp_tc_prepare": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_void_p]),
