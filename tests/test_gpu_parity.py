@@ -303,3 +303,69 @@ def test_mlp_tc_agrees_with_generic_path_full_size():
         finally:
             fused.DISABLED = False
     assert_close(a, b, "fused vs generic", rtol=1e-5, atol_scale=2e-6)
+
+
+# ------------------------------------------------------------------------------ narrow-MLP FFMA kernels (K1/K3 stage form)
+
+FFMA_SHAPES = [([2, 64, 2], "tanh"), ([3, 16, 3], "tanh"), ([4, 32, 32, 4], "softplus"), ([8, 64, 8], "relu"),
+               ([2, 64, 64, 64, 2], "softplus"), ([16, 128, 16], "tanh"), ([5, 24, 5], "tanh")]
+
+
+@pytest.mark.parametrize("dims,act", FFMA_SHAPES)
+@pytest.mark.parametrize("rows", [1, 16, 1000, 70001])
+def test_mlp_ffma_forward_matches_torch(dims, act, rows):
+    from torchdyn_b200 import fused
+    torch.manual_seed(sum(dims))
+    net = build_mlp(dims, act).to(DEV)
+    fm = fused.FusedMLP(net)
+    kern = _kernels.get(torch.empty(1, device=DEV))
+    assert fm.ready_ffma(kern)
+    y = torch.randn(rows, dims[0], device=DEV)
+    with torch.no_grad():
+        want = net.double()(y.double()).float()
+        net.float()
+    for sign in (1.0, -1.0):
+        out = kern.mlp_ffma_forward(fm._desc, y, torch.empty_like(y), sign, fm.flops_per_row)
+        assert_close(out, sign * want, f"ffma forward {dims} {act}", rtol=2e-6, atol_scale=1e-6)
+
+
+@pytest.mark.parametrize("dims,act", FFMA_SHAPES)
+@pytest.mark.parametrize("rows", [3, 64, 1024, 33333])
+def test_mlp_ffma_adjoint_matches_autograd(dims, act, rows):
+    """dx = f(x), dlam = -lam^T df/dx, dmu = -sum lam^T df/dtheta against fp64 autograd."""
+    from torchdyn_b200 import fused
+    torch.manual_seed(rows + sum(dims))
+    net = build_mlp(dims, act).to(DEV)
+    fm = fused.FusedMLP(net)
+    kern = _kernels.get(torch.empty(1, device=DEV))
+    assert fm.ready_ffma(kern)
+    D = dims[0]
+    x = torch.randn(rows, D, device=DEV)
+    lam = torch.randn(rows, D, device=DEV)
+    net64 = build_mlp(dims, act, [p.detach() for p in net.parameters()], DEV).double()
+    x64 = x.double().requires_grad_(True)
+    f64 = net64(x64)
+    grads = torch.autograd.grad(f64, (x64,) + tuple(net64.parameters()), -lam.double())
+    want_dlam, want_dmu = grads[0], torch.cat([g.flatten() for g in grads[1:]])
+    dx, dlam = torch.empty_like(x), torch.empty_like(x)
+    dmu = torch.empty(fm.n_params, device=DEV)
+    for sign in (1.0, -1.0):
+        kern.mlp_ffma_adjoint(fm._desc, x, lam, dx, dlam, dmu, fm.workspace(kern), rows, sign, fm.flops_per_row)
+        assert_close(dx, sign * f64.detach(), "dx", rtol=2e-6, atol_scale=1e-6)
+        assert_close(dlam, sign * want_dlam, "dlam", rtol=5e-6, atol_scale=2e-6)
+        assert_close(dmu, sign * want_dmu, "dmu", rtol=2e-5, atol_scale=5e-6)
+    first = dmu.clone()
+    kern.mlp_ffma_adjoint(fm._desc, x, lam, dx, dlam, dmu, fm.workspace(kern), rows, -1.0, fm.flops_per_row)
+    assert torch.equal(first, dmu), "parameter-gradient reduction must be deterministic"
+
+
+def test_c1_runs_on_fused_kernels_with_few_launches():
+    """cfg 1 (moons 1024x2, MLP 2-64-2, dopri5 + backsolve adjoint): vector field and adjoint dynamics are evaluated by
+    this library's kernels -- the reference's ~1000 ATen launches per iteration become < 150 launches of ours."""
+    fx = load_golden("c1_moons_dopri5_adjoint")
+    n0 = _kernels.launches()
+    out = run_neuralode_case(fx, DEV)
+    used = _kernels.launches() - n0
+    check_neuralode_case(fx, out)
+    assert out["model"].vf.nfe == fx["ref"]["nfe_total"] == 36
+    assert 40 < used < 150, used

@@ -99,21 +99,37 @@ class FusedMLP:
         self.act = _ACTS[type(a0)]
         self.dims = [linears[0].in_features] + [m.out_features for m in linears]
         self.flops_per_row = 2.0 * sum(a * b for a, b in zip(self.dims[:-1], self.dims[1:]))
+        self.n_params = sum(a * b + b for a, b in zip(self.dims[:-1], self.dims[1:]))
         self._key = None
         self._desc = None
         self._img = None
+        self._tc_ok = False
+        self._ffma_ok = False
+        self._ffma_ws = None
 
     def _params_key(self):
         return tuple((p.data_ptr(), p._version) for m in self.linears for p in (m.weight, m.bias))
 
     def ready(self, kern) -> bool:
-        """(Re)build descriptor + weight image if the parameters changed; False if this net has no fused kernel."""
+        """True if the tensor-core stage kernel can run this net (weight image rebuilt if the parameters changed)."""
+        return self._refresh(kern) and self._tc_ok
+
+    def ready_ffma(self, kern) -> bool:
+        """True if the narrow-net FFMA kernels can run this net."""
+        return self._refresh(kern) and self._ffma_ok
+
+    def workspace(self, kern):
+        if self._ffma_ws is None or self._ffma_ws.device != kern.device:
+            self._ffma_ws = kern.mlp_ffma_workspace(self._desc)
+        return self._ffma_ws
+
+    def _refresh(self, kern) -> bool:
         ps = [p for m in self.linears for p in (m.weight, m.bias)]
         if not all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in ps):
             return False
         key = self._params_key()
         if key == self._key:
-            return self._img is not None
+            return True
         d = _lib.MlpDesc()
         d.n_layers = len(self.linears)
         for i, v in enumerate(self.dims):
@@ -123,9 +139,10 @@ class FusedMLP:
             d.w[i] = m.weight.data_ptr()
             d.b[i] = m.bias.data_ptr()
         self._key, self._desc, self._img = key, d, None
-        if not kern.mlp_tc_supported(d):
-            return False
-        self._img = kern.mlp_tc_prepare(d)
+        self._tc_ok = kern.mlp_tc_supported(d)
+        self._ffma_ok = kern.mlp_ffma_supported(d)
+        if self._tc_ok:
+            self._img = kern.mlp_tc_prepare(d)
         return True
 
 
@@ -141,6 +158,87 @@ def _get_fused(f) -> Optional[tuple]:
             fm = False
         _cache[net] = fm
     return (fm, counters) if fm else None
+
+
+class FusedField:
+    """``f`` with a kernel-backed ``tdyn_eval``: the integration loops evaluate the MLP inside this library (FFMA
+    kernel for narrow nets, the tensor-core stage kernel for the 32-256-256-32 class) instead of calling torch.
+    ``__call__`` still forwards to the original callable (user code may call it directly)."""
+
+    def __init__(self, f, fm: FusedMLP, counters, kern):
+        self.f, self.fm, self.counters, self.kern = f, fm, counters, kern
+
+    def __call__(self, t, x, *a, **k):
+        return self.f(t, x, *a, **k)
+
+    def parameters(self):
+        return self.f.parameters()
+
+    def tdyn_eval(self, t_host, y, sign: float = 1.0):
+        fm, kern = self.fm, self.kern
+        if y.dim() != 2 or y.shape[1] != fm.dims[0] or not y.is_contiguous():
+            out = self.f(kern.time_tensor(t_host, y), y)
+            return out if sign == 1.0 else -out
+        out = torch.empty_like(y)
+        if fm.ready(kern) and sign == 1.0:
+            kern.mlp_tc_stage(fm._desc, fm._img, out, y, [], (), MODE_INNER, 0.0, None, (), fm.flops_per_row)
+        else:
+            kern.mlp_ffma_forward(fm._desc, y, out, sign, fm.flops_per_row)
+        for c in self.counters:
+            c.nfe += 1
+        return out
+
+
+def wrap(f, x):
+    """Return a FusedField for ``f`` when it is a fusable MLP on this device, else ``f`` unchanged."""
+    global _last
+    if DISABLED or isinstance(f, FusedField) or not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32):
+        return f
+    got = _get_fused(f)
+    if got is None:
+        return f
+    fm, counters = got
+    kern = _kernels.get(x)
+    if not getattr(kern, "is_cuda", False) or x.dim() != 2 or x.shape[1] != fm.dims[0]:
+        return f
+    if not (fm.ready(kern) or fm.ready_ffma(kern)):
+        return f
+    _last = "fused MLP vector field (tdyn_mlp_tc_stage)" if fm.ready(kern) else "fused MLP vector field (tdyn_mlp_ffma_forward)"
+    return FusedField(f, fm, counters, kern)
+
+
+class FusedAdjoint:
+    """Kernel-backed body of the adjoint dynamics for a fusable MLP: forward + VJP + batch-reduced parameter gradient
+    in one launch (``tdyn_mlp_ffma_adjoint``)."""
+
+    def __init__(self, fm: FusedMLP, counters, kern):
+        self.fm, self.counters, self.kern = fm, counters, kern
+
+    def __call__(self, x_flat, lam_flat, dx_out, dlam_out, dmu_out, rows, sign):
+        fm = self.fm
+        self.kern.mlp_ffma_adjoint(fm._desc, x_flat, lam_flat, dx_out, dlam_out, dmu_out, fm.workspace(self.kern), rows,
+                                   sign, fm.flops_per_row)
+        for c in self.counters:
+            c.nfe += 1
+
+
+def adjoint_for(vf, x_shape, device) -> Optional[FusedAdjoint]:
+    """FusedAdjoint for ``vf`` (as held by ODEProblem: DEFunc / DEFuncBase wrapped nn.Sequential) or None."""
+    if DISABLED or len(x_shape) != 2 or device.type != "cuda":
+        return None
+    got = _get_fused(vf)
+    if got is None:
+        return None
+    fm, counters = got
+    if x_shape[1] != fm.dims[0]:
+        return None
+    kern = _kernels.get(torch.empty(0, device=device))
+    if not getattr(kern, "is_cuda", False) or not fm.ready_ffma(kern):
+        return None
+    # the flat parameter vector of the problem must be exactly this net's parameters, in order
+    if sum(p.numel() for p in vf.parameters()) != fm.n_params:
+        return None
+    return FusedAdjoint(fm, counters, kern)
 
 
 def _isclose_count(t, save_at: np.ndarray) -> int:

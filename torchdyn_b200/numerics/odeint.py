@@ -62,6 +62,9 @@ def odeint(f: Callable, x: Tensor, t_span: Union[List, Tensor], solver: Union[st
     """Solve the IVP dx/dt = f(t, x), x(t_span[0]) = x.  Same arguments, warnings, errors and return
     convention as the reference (``(t_eval, sol)`` with ``sol[i]`` the state at ``t_eval[i]``)."""
     ts = _host_times(t_span)
+    if isinstance(x, Tensor) and x.is_cuda and (type(solver) == str or type(solver) in BUILTIN_TYPES):
+        from .. import fused
+        f = fused.wrap(f, x)            # MLP vector fields are evaluated by this library's kernels
     if ts[1] < ts[0]:   # reversed time: integrate -f(-t, x) over the negated span (odeint.py:54-58)
         if verbose:
             warn("You are integrating on a reversed time domain, adjusting the vector field automatically")

@@ -62,12 +62,25 @@ def _vjp(vf, t, x, lam, integral_loss):
 class BacksolveDynamics:
     """d/dt [x, lam, mu, lam_t] for the backsolve adjoint on the flat vector A (sensitivity.py:57-75)."""
 
-    def __init__(self, vf, x_shape, lam_shape, n_params, integral_loss):
+    def __init__(self, vf, x_shape, lam_shape, n_params, integral_loss, device=None):
         self.vf, self.x_shape, self.lam_shape, self.P, self.integral_loss = vf, x_shape, lam_shape, n_params, integral_loss
         self.n = int(np.prod(x_shape))
+        self.fused = None
+        if integral_loss is None and device is not None and tuple(x_shape) == tuple(lam_shape):
+            from .. import fused
+            self.fused = fused.adjoint_for(vf, tuple(x_shape), device)
 
-    def tdyn_eval(self, t_host, A):
-        return self(_time(t_host, A), A)
+    def tdyn_eval(self, t_host, A, sign: float = 1.0):
+        if self.fused is None or not A.is_contiguous():
+            out = self(_time(t_host, A), A)
+            return out if sign == 1.0 else -out
+        # MLP field: f, -lam^T df/dx and the batch-reduced -lam^T df/dtheta in ONE kernel, written straight into the
+        # flat [dx, dlam, dmu, dlam_t] layout (df/dt = 0 for an autonomous MLP -> dlam_t = 0, sensitivity.py:73)
+        n, P = self.n, self.P
+        out = torch.empty_like(A)
+        out[-1:].zero_()
+        self.fused(A[:n], A[n:2 * n], out[:n], out[n:2 * n], out[2 * n:2 * n + P], self.x_shape[0], sign)
+        return out
 
     def __call__(self, t, A):
         if t.dim() > 0:
@@ -81,12 +94,26 @@ class BacksolveDynamics:
 class InterpDynamics:
     """d/dt [lam, mu] with x(t) from the spline (sensitivity.py:130-147)."""
 
-    def __init__(self, vf, spline, lam_shape, n_params, integral_loss):
+    def __init__(self, vf, spline, lam_shape, n_params, integral_loss, device=None):
         self.vf, self.spline, self.lam_shape, self.P, self.integral_loss = vf, spline, lam_shape, n_params, integral_loss
         self.n = int(np.prod(lam_shape))
+        self.fused = None
+        if integral_loss is None and device is not None:
+            from .. import fused
+            self.fused = fused.adjoint_for(vf, tuple(lam_shape), device)
 
-    def tdyn_eval(self, t_host, A):
+    def tdyn_eval(self, t_host, A, sign: float = 1.0):
         x = self.spline.evaluate(t_host)
+        if self.fused is not None and A.is_contiguous() and x.is_contiguous():
+            n, P = self.n, self.P
+            out = torch.empty_like(A)
+            scratch = torch.empty_like(x)                     # f(x) itself is not part of [dlam, dmu]
+            self.fused(x, A[:n], scratch, out[:n], out[n:n + P], self.lam_shape[0], sign)
+            return out
+        out = self._eval_torch(t_host, A, x)
+        return out if sign == 1.0 else -out
+
+    def _eval_torch(self, t_host, A, x):
         lam = A[:self.n].reshape(self.lam_shape)
         _, dlam, dmu, _ = _vjp(self.vf, _time(t_host, A), x, lam, self.integral_loss)
         return torch.cat([dlam.flatten(), dmu.flatten()])
@@ -119,7 +146,7 @@ def _gather_odefunc_adjoint(vf, vf_params, solver, atol, rtol, interpolator, sol
             lam_flat = lamT.flatten()
             lam_t = lam_flat @ vf(t_sol[-1], xT).flatten()                                   # :53
             A = torch.cat([xT.flatten(), lam_flat, torch.zeros(P, dtype=xT.dtype, device=xT.device), lam_t[None]])
-            dyn = BacksolveDynamics(vf, xT.shape, lamT.shape, P, integral_loss)
+            dyn = BacksolveDynamics(vf, xT.shape, lamT.shape, P, integral_loss, device=xT.device)
 
             dLdt = torch.zeros(len(th)).to(xT)
             dLdt[-1] = lam_t
@@ -163,7 +190,7 @@ def _gather_odefunc_interp_adjoint(vf, vf_params, solver, atol, rtol, interpolat
             n = lamT.numel()
             A = torch.cat([lamT.flatten(), torch.zeros(P, dtype=lamT.dtype, device=lamT.device)])
             spline = NaturalCubicSpline(sol.detach(), ctx.t_host)
-            dyn = InterpDynamics(vf, spline, lamT.shape, P, integral_loss)
+            dyn = InterpDynamics(vf, spline, lamT.shape, P, integral_loss, device=lamT.device)
             for i in range(len(span) - 1, 0, -1):
                 # forward solver and tolerances, no seminorm (sensitivity.py:152)
                 _, As = odeint(dyn, A, np.array([span[i], span[i - 1]], dtype=np.float32), solver, atol=atol, rtol=rtol)

@@ -47,7 +47,11 @@ class Reversed:
         self.f = f
         inner = getattr(f, "tdyn_eval", None)
         if inner is not None:
-            self.tdyn_eval = lambda t_host, y: -inner(-t_host, y)
+            import inspect
+            if "sign" in inspect.signature(inner).parameters:     # kernels that fold the negation into their epilogue
+                self.tdyn_eval = lambda t_host, y: inner(-t_host, y, sign=-1.0)
+            else:
+                self.tdyn_eval = lambda t_host, y: -inner(-t_host, y)
 
     def __call__(self, t, x):
         return -self.f(-t, x)
