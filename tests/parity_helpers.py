@@ -103,7 +103,7 @@ def check_neuralode_case(fx, out, exact=False, state_rtol=STATE_RTOL):
         assert all(torch.equal(p.grad, g) for p, g in zip(out["net"].parameters(), ref["gp"]))
     # when a noise-driven call took slightly different steps the solutions agree to the SOLVER tolerance, not to 1e-5
     tol = max(fx["kw"].get("atol", 1e-3), fx["kw"].get("rtol", 1e-3), fx["kw"].get("atol_adjoint", 1e-4))
-    s_rtol, g_rtol, a_scale = (state_rtol, 2 * state_rtol, 0.5 * state_rtol) if strict else (20 * tol, 20 * tol, 20 * tol)
+    s_rtol, g_rtol, a_scale = (state_rtol, 2 * state_rtol, 0.5 * state_rtol) if strict else (20 * tol, 50 * tol, 50 * tol)
     if strict:
         assert out["sol"].shape[0] == ref["sol_len"]
         te = out["t_eval"].detach().cpu().numpy()

@@ -321,9 +321,9 @@ def test_mlp_ffma_forward_matches_torch(dims, act, rows):
     kern = _kernels.get(torch.empty(1, device=DEV))
     assert fm.ready_ffma(kern)
     y = torch.randn(rows, dims[0], device=DEV)
+    net64 = build_mlp(dims, act, [p.detach() for p in net.parameters()], DEV).double()   # separate copy: fm holds raw pointers
     with torch.no_grad():
-        want = net.double()(y.double()).float()
-        net.float()
+        want = net64(y.double()).float()
     for sign in (1.0, -1.0):
         out = kern.mlp_ffma_forward(fm._desc, y, torch.empty_like(y), sign, fm.flops_per_row)
         assert_close(out, sign * want, f"ffma forward {dims} {act}", rtol=2e-6, atol_scale=1e-6)

@@ -34,15 +34,16 @@ constexpr uint32_t kATile = kTileM * 128;           // 16 KB: one [128 x 32] ope
 constexpr uint32_t kAStage = 2 * kATile;            // hi + lo
 constexpr uint32_t kWStage = 65536;                 // one weight stage image
 constexpr int kWStagesPerTile = 10;                 // W1 | W2 k-blocks 0..7 | W3 (all k-blocks)
-constexpr uint32_t kSmemA1 = 0;
-constexpr uint32_t kSmemARing = kSmemA1 + kAStage;                  // 2 stages
-constexpr uint32_t kSmemWRing = kSmemARing + 2 * kAStage;           // 2 stages
+constexpr int kLoStages = 4;                        // ring of [128 x 32] TF32 "lo" operand tiles (the "hi" parts live in TMEM)
+constexpr uint32_t kSmemA1 = 0;                                     // layer-1 operand: hi tile | lo tile
+constexpr uint32_t kSmemLoRing = kSmemA1 + kAStage;                 // kLoStages x 16 KB
+constexpr uint32_t kSmemWRing = kSmemLoRing + kLoStages * kATile;   // 2 stages x 64 KB
 constexpr uint32_t kSmemBars = kSmemWRing + 2 * kWStage;
 constexpr uint32_t kSmemTotal = kSmemBars + 256 + 1024;   // + slack for the manual 1024-byte alignment
 constexpr uint32_t kTmemCols = 512;
 
-enum Bar { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, A_FULL0, A_FULL1, A_EMPTY0, A_EMPTY1, A1_FULL, D1_FULL, D2_FULL,
-           D3_FULL, D_FREE, D1_FREE, NUM_BARS };
+enum Bar { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, A_FULL0, A_FULL1, A_FULL2, A_FULL3, A_EMPTY0, A_EMPTY1, A_EMPTY2,
+           A_EMPTY3, A1_FULL, D1_FULL, D2_FULL, D3_FULL, D_FREE, NUM_BARS };
 
 struct Params {
     const uint8_t* wimg;       // 10 x 64 KB stage images
@@ -93,6 +94,20 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// A operand from TMEM (lane = row, 8 consecutive columns = the 8 K values of one kind::tf32 MMA), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // UMMA shared-memory descriptor: K-major operand tile, 128-byte swizzle, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -144,8 +159,9 @@ __device__ __forceinline__ void tmem_wait8(uint32_t (&r)[8]) {
                  :: "memory");
 }
 
-// 8 activations of one row -> hi/lo TF32 pieces into the [128 x 32] operand tiles at `stage` (hi) / +16 KB (lo).
-// hi = rna_tf32(a); lo = a - hi is exact in fp32 and is truncated to TF32 by the tensor core (error 2^-22 |a|).
+// hi = rna_tf32(a) (exactly representable: the tensor core's truncation is a no-op); lo = a - hi is exact in fp32 and
+// is truncated to TF32 by the tensor core (error 2^-22 |a|).
+// layer-1 operand: both parts to shared memory (K-major, 128B swizzle)
 __device__ __forceinline__ void store_split8(uint8_t* stage, int row, int sub, const float (&a)[8]) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -158,6 +174,24 @@ __device__ __forceinline__ void store_split8(uint8_t* stage, int row, int sub, c
         *reinterpret_cast<float4*>(stage + off) = hi;
         *reinterpret_cast<float4*>(stage + kATile + off) = lo;
     }
+}
+// hidden-layer operand: hi back into TMEM IN PLACE of the accumulator columns it came from (A-from-TMEM MMAs read it
+// without touching shared memory), lo into the shared-memory ring
+__device__ __forceinline__ void store_split8_tmem(uint32_t taddr, uint8_t* lo_tile, int row, int sub, const float (&a)[8]) {
+    uint32_t hi[8];
+    float lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float h = tf32_rna(a[i]);
+        hi[i] = __float_as_uint(h);
+        lo[i] = a[i] - h;
+    }
+    tmem_st8(taddr, hi);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+        *reinterpret_cast<float4*>(lo_tile + swz((uint32_t)row, (uint32_t)(sub * 2 + i))) =
+            make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+    tmem_wait_st();
 }
 
 // one 3xTF32 K-block (32 wide): D (+)= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, 4 MMAs of K = 8 per term
@@ -172,6 +206,17 @@ __device__ __forceinline__ void issue_kblock(uint32_t d_tmem, uint32_t a_hi, uin
             tc_mma_tf32(d_tmem, umma_desc(A[t] + k * 32), umma_desc(B[t] + k * 32), idesc, (first && t == 0 && k == 0) ? 0u : 1u);
         }
     }
+}
+
+// hidden-layer K-block: A_hi in TMEM (32 columns at a_hi_tmem), A_lo in shared memory
+__device__ __forceinline__ void issue_kblock_ts(uint32_t d_tmem, uint32_t a_hi_tmem, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                uint32_t idesc, bool first) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tc_mma_tf32(d_tmem, umma_desc(a_lo + k * 32), umma_desc(b_hi + k * 32), idesc, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d_tmem, a_hi_tmem + k * 8, umma_desc(b_lo + k * 32), idesc, 1u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d_tmem, a_hi_tmem + k * 8, umma_desc(b_hi + k * 32), idesc, 1u);
 }
 
 struct WorkerCtx {
@@ -247,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NUM_BARS; ++i) {
             uint32_t cnt = 1;
-            if (i == A_FULL0 || i == A_FULL1 || i == A1_FULL || i == D_FREE || i == D1_FREE) cnt = kWorkers;
+            if ((i >= A_FULL0 && i <= A_FULL3) || i == A1_FULL || i == D_FREE) cnt = kWorkers;
             mbar_init(bar(i), cnt);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -261,11 +306,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
     const int my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    // TMEM map: D1 = cols [0,256); D2 = cols [256,512); D3 = cols [256,288) (D2's first chunk, drained before L3 starts)
-    constexpr uint32_t kColD1 = 0, kColD2 = 256, kColD3 = 256;
+    // TMEM map: X = cols [0,256): D1, converted in place to layer 2's A_hi; Y = cols [256,512): D2 -> layer 3's A_hi;
+    // D3 = cols [0,32) (layer 2's A_hi is dead once layer 2 has been issued: the tensor pipe executes in order)
+    constexpr uint32_t kColD1 = 0, kColD2 = 256, kColD3 = 0;
 
     if (warp == 0) {
-        // ================= weight producer: W1(0) | per tile: W2[0..7], W1(next tile), W3 =================
+        // ================= weight producer: W1(0) | per tile: W2[0..7], W3, W1(next tile) =================
         if (lane == 0) {
             uint32_t it = 0;
             auto load = [&](int s) {
@@ -281,8 +327,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
             if (my_tiles > 0) load(0);
             for (int t = 0; t < my_tiles; ++t) {
                 for (int s = 1; s <= 8; ++s) load(s);
-                if (t + 1 < my_tiles) load(0);
                 load(9);
+                if (t + 1 < my_tiles) load(0);
             }
         }
     } else if (warp == 1) {
@@ -303,42 +349,41 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
             };
             if (my_tiles > 0) layer1(0);
             for (int t = 0; t < my_tiles; ++t) {
-                // ---- layer 2: 8 K-blocks -> D2; the previous tile's D3 lives in D2's first columns
-                if (t > 0) mbar_wait(bar(D_FREE), (t - 1) & 1);
+                // ---- layer 2: 8 K-blocks, A_hi = X (in TMEM), A_lo ring -> D2 = Y
                 for (int j = 0; j < kH / kKB; ++j, ++wit, ++ait) {
-                    const uint32_t ws = wit & 1, wu = wit >> 1, as = ait & 1, au = ait >> 1;
+                    const uint32_t ws = wit & 1, wu = wit >> 1, as = ait % kLoStages, au = ait / kLoStages;
                     mbar_wait(bar(A_FULL0 + as), au & 1);
                     mbar_wait(bar(W_FULL0 + ws), wu & 1);
                     tc_fence_after();
-                    const uint32_t a = sbase + kSmemARing + as * kAStage;
                     const uint32_t w = sbase + kSmemWRing + ws * kWStage;
-                    issue_kblock(tmem + kColD2, a, a + kATile, w, w + kWStage / 2, umma_idesc(kH), j == 0);
+                    issue_kblock_ts(tmem + kColD2, tmem + kColD1 + (uint32_t)(j * kKB), sbase + kSmemLoRing + as * kATile,
+                                    w, w + kWStage / 2, umma_idesc(kH), j == 0);
                     tc_commit(bar(W_EMPTY0 + ws));
                     tc_commit(bar(A_EMPTY0 + as));
                 }
                 tc_commit(bar(D2_FULL));
-                // ---- next tile's layer 1 runs on the tensor pipe while the workers convert D2
-                if (t + 1 < my_tiles) {
-                    mbar_wait(bar(D1_FREE), t & 1);
-                    layer1(t + 1);
-                }
-                // ---- layer 3: 8 K-blocks, N = 32 -> D3; W3 stage = 8 x [hi 4 KB | lo 4 KB]
+                // ---- layer 3: 8 K-blocks, N = 32, A_hi = Y -> D3 = X[0,32); W3 stage = 8 x [hi 4 KB | lo 4 KB]
                 {
                     const uint32_t ws = wit & 1, wu = wit >> 1;
                     mbar_wait(bar(W_FULL0 + ws), wu & 1);
                     const uint32_t w = sbase + kSmemWRing + ws * kWStage;
                     for (int j = 0; j < kH / kKB; ++j, ++ait) {
-                        const uint32_t as = ait & 1, au = ait >> 1;
+                        const uint32_t as = ait % kLoStages, au = ait / kLoStages;
                         mbar_wait(bar(A_FULL0 + as), au & 1);
                         tc_fence_after();
-                        const uint32_t a = sbase + kSmemARing + as * kAStage;
                         const uint32_t wj = w + (uint32_t)j * 8192u;
-                        issue_kblock(tmem + kColD3, a, a + kATile, wj, wj + 4096u, umma_idesc(kD), j == 0);
+                        issue_kblock_ts(tmem + kColD3, tmem + kColD2 + (uint32_t)(j * kKB), sbase + kSmemLoRing + as * kATile,
+                                        wj, wj + 4096u, umma_idesc(kD), j == 0);
                         tc_commit(bar(A_EMPTY0 + as));
                     }
                     tc_commit(bar(W_EMPTY0 + ws));
                     tc_commit(bar(D3_FULL));
                     ++wit;
+                }
+                // ---- next tile's layer 1 overwrites X: wait until this tile's D3 has been read out
+                if (t + 1 < my_tiles) {
+                    mbar_wait(bar(D_FREE), t & 1);
+                    layer1(t + 1);
                 }
             }
         }
@@ -379,22 +424,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                     v[2] = activate<ACT>(__uint_as_float(cur[2]) + b0.z); v[3] = activate<ACT>(__uint_as_float(cur[3]) + b0.w);
                     v[4] = activate<ACT>(__uint_as_float(cur[4]) + b1.x); v[5] = activate<ACT>(__uint_as_float(cur[5]) + b1.y);
                     v[6] = activate<ACT>(__uint_as_float(cur[6]) + b1.z); v[7] = activate<ACT>(__uint_as_float(cur[7]) + b1.w);
-                    const uint32_t as = ait & 1, au = ait >> 1;
+                    const uint32_t as = ait % kLoStages, au = ait / kLoStages;
                     mbar_wait(bar(A_EMPTY0 + as), (au & 1) ^ 1);
-                    store_split8(smem + kSmemARing + as * kAStage, w.row, w.sub, v);
+                    store_split8_tmem(src + (uint32_t)(j * kKB), smem + kSmemLoRing + as * kATile, w.row, w.sub, v);
                     fence_proxy_async();
+                    tc_fence_before();
                     mbar_arrive(bar(A_FULL0 + as));
                     if (j + 1 < kH / kKB) tmem_wait8(nxt);
                 }
-                if (layer == 0) {
-                    // D1 fully read: the tensor pipe may overwrite it with the next tile's layer 1 ...
-                    tc_fence_before();
-                    mbar_arrive(bar(D1_FREE));
-                    // ... whose stage input we produce now (A1 is free: this tile's layer 1 has completed)
-                    if (t + 1 < my_tiles) {
-                        prologue(P, smem, w, tile + gridDim.x);
-                        mbar_arrive(bar(A1_FULL));
-                    }
+                if (layer == 0 && t + 1 < my_tiles) {
+                    // next tile's stage input (A1 is free: this tile's layer 1 has completed)
+                    prologue(P, smem, w, tile + gridDim.x);
+                    mbar_arrive(bar(A1_FULL));
                 }
             }
             // ---- output: k_out = D3 + b3 (and x_new for the last stage of a fixed-step method)

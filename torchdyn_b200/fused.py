@@ -253,10 +253,13 @@ def try_fixed(f, x, ts, sv, solver) -> Optional[List[torch.Tensor]]:
     _last = None
     if DISABLED or not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
         return None
-    got = _get_fused(f)
-    if got is None:
-        return None
-    fm, counters = got
+    if isinstance(f, FusedField):
+        fm, counters = f.fm, f.counters
+    else:
+        got = _get_fused(f)
+        if got is None:
+            return None
+        fm, counters = got
     kern = _kernels.get(x)
     if not getattr(kern, "is_cuda", False) or x.shape[1] != fm.dims[0] or not fm.ready(kern):
         return None
