@@ -34,16 +34,17 @@ constexpr uint32_t kATile = kTileM * 128;           // 16 KB: one [128 x 32] ope
 constexpr uint32_t kAStage = 2 * kATile;            // hi + lo
 constexpr uint32_t kWStage = 65536;                 // one weight stage image
 constexpr int kWStagesPerTile = 10;                 // W1 | W2 k-blocks 0..7 | W3 (all k-blocks)
-constexpr int kLoStages = 4;                        // ring of [128 x 32] TF32 "lo" operand tiles (the "hi" parts live in TMEM)
+constexpr int kLoStages = 3;                        // ring of [128 x 32] TF32 "lo" operand tiles (the "hi" parts live in TMEM)
 constexpr uint32_t kSmemA1 = 0;                                     // layer-1 operand: hi tile | lo tile
 constexpr uint32_t kSmemLoRing = kSmemA1 + kAStage;                 // kLoStages x 16 KB
 constexpr uint32_t kSmemWRing = kSmemLoRing + kLoStages * kATile;   // 2 stages x 64 KB
-constexpr uint32_t kSmemBars = kSmemWRing + 2 * kWStage;
+constexpr uint32_t kSmemBias = kSmemWRing + 2 * kWStage;            // b1[256] | b2[256] | b3[32] (fp32)
+constexpr uint32_t kSmemBars = kSmemBias + (2 * kH + kD) * 4;
 constexpr uint32_t kSmemTotal = kSmemBars + 256 + 1024;   // + slack for the manual 1024-byte alignment
 constexpr uint32_t kTmemCols = 512;
 
-enum Bar { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, A_FULL0, A_FULL1, A_FULL2, A_FULL3, A_EMPTY0, A_EMPTY1, A_EMPTY2,
-           A_EMPTY3, A1_FULL, D1_FULL, D2_FULL, D3_FULL, D_FREE, NUM_BARS };
+enum Bar { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, A_FULL0, A_FULL1, A_FULL2, A_EMPTY0, A_EMPTY1, A_EMPTY2,
+           A1_FULL, D1_FULL, D2_FULL, D3_FULL, D_FREE, NUM_BARS };
 
 struct Params {
     const uint8_t* wimg;       // 10 x 64 KB stage images
@@ -292,10 +293,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NUM_BARS; ++i) {
             uint32_t cnt = 1;
-            if ((i >= A_FULL0 && i <= A_FULL3) || i == A1_FULL || i == D_FREE) cnt = kWorkers;
+            if ((i >= A_FULL0 && i <= A_FULL2) || i == A1_FULL || i == D_FREE) cnt = kWorkers;
             mbar_init(bar(i), cnt);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {   // biases -> shared memory (the L1 is almost entirely carved out as shared memory: global re-reads would go to L2)
+        float* sb = reinterpret_cast<float*>(smem + kSmemBias);
+        for (int i = threadIdx.x; i < 2 * kH + kD; i += kThreads)
+            sb[i] = i < kH ? __ldg(P.b1 + i) : (i < 2 * kH ? __ldg(P.b2 + i - kH) : __ldg(P.b3 + i - 2 * kH));
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols));
@@ -407,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
             for (int layer = 0; layer < 2; ++layer) {
                 mbar_wait(bar(layer == 0 ? D1_FULL : D2_FULL), tpar);
                 tc_fence_after();
-                const float* bias = (layer == 0 ? P.b1 : P.b2) + w.sub * 8;
+                const float* bias = reinterpret_cast<const float*>(smem + kSmemBias) + layer * kH + w.sub * 8;
                 const uint32_t src = w.lane_addr + (layer == 0 ? kColD1 : kColD2) + (uint32_t)(w.sub * 8);
                 uint32_t ra[8], rb[8];
                 tmem_ld8(src, ra);
@@ -417,8 +423,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                     uint32_t (&cur)[8] = (j & 1) ? rb : ra;
                     uint32_t (&nxt)[8] = (j & 1) ? ra : rb;
                     if (j + 1 < kH / kKB) tmem_ld8(src + (uint32_t)((j + 1) * kKB), nxt);     // prefetch next chunk
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + j * kKB));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + j * kKB) + 1);
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias + j * kKB);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bias + j * kKB + 4);
                     float v[8];
                     v[0] = activate<ACT>(__uint_as_float(cur[0]) + b0.x); v[1] = activate<ACT>(__uint_as_float(cur[1]) + b0.y);
                     v[2] = activate<ACT>(__uint_as_float(cur[2]) + b0.z); v[3] = activate<ACT>(__uint_as_float(cur[3]) + b0.w);
@@ -452,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                 float o[8];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const float4 bq = __ldg(reinterpret_cast<const float4*>(P.b3 + w.sub * 8) + i);
+                    const float4 bq = *reinterpret_cast<const float4*>(smem + kSmemBias + (2 * kH + w.sub * 8 + 4 * i) * 4);
                     o[4 * i] = __uint_as_float(ro[4 * i]) + bq.x; o[4 * i + 1] = __uint_as_float(ro[4 * i + 1]) + bq.y;
                     o[4 * i + 2] = __uint_as_float(ro[4 * i + 2]) + bq.z; o[4 * i + 3] = __uint_as_float(ro[4 * i + 3]) + bq.w;
                     reinterpret_cast<float4*>(P.k_out + goff)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
