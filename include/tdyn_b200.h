@@ -35,7 +35,7 @@ extern "C" {
 #define TDYN_API
 #endif
 
-#define TDYN_ABI_VERSION 4
+#define TDYN_ABI_VERSION 5
 #define TDYN_MAX_STAGES 7
 
 /* combination shapes of the reference steppers (numerics/solvers/ode.py) */
@@ -113,6 +113,32 @@ TDYN_API int64_t tdyn_mlp_ffma_workspace_bytes(const tdyn_mlp_t* mlp);
 TDYN_API int tdyn_mlp_ffma_forward(const tdyn_mlp_t* mlp, const float* y, float* out, int64_t rows, float sign, void* stream);
 TDYN_API int tdyn_mlp_ffma_adjoint(const tdyn_mlp_t* mlp, const float* x, const float* lam, float* dx, float* dlam,
                                    float* dmu, void* workspace, int64_t rows, float sign, void* stream);
+
+/* K1/K3 (persistent form). A whole `odeint` call (numerics/odeint.py:29-91 + :326-408: k1, init_step, the adaptive loop
+ * with checkpoint handling, FSAL, the step controller) for a narrow MLP vector field in ONE cooperative kernel; one
+ * grid barrier per attempted step carries the global error norm.  adjoint = 1 integrates one interval of the backsolve
+ * adjoint (numerics/sensitivity.py:55-84): y0/y1 are the flat A = [x, lam, mu, lam_t]; mu is integrated per CTA on
+ * its batch-partial and reduced once at the end.  `plan` restates the stepper (numerics/solvers/ode.py:145-178).
+ * status (device, 6 ints): n_out, n_attempt, n_accept, nfe, error (0 ok, 1 max_steps/NaN, 2 out_cap), index (0/1) of
+ * the y buffer holding the final state.  trace (device, optional): [0] = dt0, then (t, dt, error_ratio) per attempt.
+ * `k`: 7 stage buffers, contiguous, each (adjoint ? 2 : 1) * rows * D floats.  `out`: [out_cap][state elems]. */
+typedef struct {
+    int n_extra;                        /* stages after k1: 6 (dopri5/tsit5), 3 (rk4), 0 (euler) */
+    int mode[6];                        /* TDYN_MODE_* of each stage input */
+    int nk[6];
+    float a[6][TDYN_MAX_STAGES];
+    float c[6];
+    int n_sol; float bsol[TDYN_MAX_STAGES];
+    int n_err; float berr[TDYN_MAX_STAGES];   /* n_err == 0: fixed-step method */
+    int order;
+    float safety, min_factor, max_factor;
+} tdyn_rk_plan_t;
+TDYN_API int tdyn_mlp_solve_supported(const tdyn_mlp_t* mlp, int adjoint);
+TDYN_API int64_t tdyn_mlp_solve_workspace_bytes(const tdyn_mlp_t* mlp);
+TDYN_API int tdyn_mlp_solve(const tdyn_mlp_t* mlp, const tdyn_rk_plan_t* plan, int adjoint, float sign, float atol, float rtol,
+                            const float* t_span, int n_t, int return_all, float* y0, float* y1, float* k, float* out,
+                            float* t_out, int out_cap, void* workspace, int* status, float* trace, int trace_cap,
+                            int64_t rows, int max_steps, void* stream);
 
 /* K2. Tensor-core (tcgen05, 3xTF32) stage kernel for wide MLPs (all hidden widths multiples of 64, >= 128):
  *   y = combine(x, k[], coef, mode, dt)   (same semantics as tdyn_rk_combine; n_k == 0 -> y = x)

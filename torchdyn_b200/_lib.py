@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdyn_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_STAGES = 7
 MAX_LAYERS = 4
 MODE_CHAIN, MODE_INNER = 0, 1
@@ -29,6 +29,14 @@ class MlpDesc(C.Structure):
     """mirror of tdyn_mlp_t"""
     _fields_ = [("n_layers", C.c_int), ("dims", C.c_int * (MAX_LAYERS + 1)), ("act", C.c_int),
                 ("w", C.c_void_p * MAX_LAYERS), ("b", C.c_void_p * MAX_LAYERS)]
+
+
+class RkPlan(C.Structure):
+    """mirror of tdyn_rk_plan_t"""
+    _fields_ = [("n_extra", C.c_int), ("mode", C.c_int * 6), ("nk", C.c_int * 6), ("a", (C.c_float * MAX_STAGES) * 6),
+                ("c", C.c_float * 6), ("n_sol", C.c_int), ("bsol", C.c_float * MAX_STAGES), ("n_err", C.c_int),
+                ("berr", C.c_float * MAX_STAGES), ("order", C.c_int), ("safety", C.c_float), ("min_factor", C.c_float),
+                ("max_factor", C.c_float)]
 
 
 # name -> (restype, argtypes); every symbol include/tdyn_b200.h declares
@@ -54,6 +62,11 @@ SIGNATURES = {
     "tdyn_mlp_ffma_forward": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "tdyn_mlp_ffma_adjoint": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
+    "tdyn_mlp_solve_supported": (C.c_int, [C.POINTER(MlpDesc), C.c_int]),
+    "tdyn_mlp_solve_workspace_bytes": (C.c_int64, [C.POINTER(MlpDesc)]),
+    "tdyn_mlp_solve": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(RkPlan), C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
     "tdyn_mlp_tc_prepared_bytes": (C.c_int64, [C.POINTER(MlpDesc)]),
     "tdyn_mlp_tc_supported": (C.c_int, [C.POINTER(MlpDesc)]),
     "tdyn_mlp_tc_prepare": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_void_p]),

@@ -11,240 +11,8 @@
 // in) access), a CTA walks 16-row tiles, activations are kept feature-major ([feature][16 rows]) so one LDS.128
 // feeds 4 rows, every thread owns (4 rows x 1 neuron).  The parameter-gradient contraction (split-K over the batch)
 // is accumulated per CTA in shared memory and reduced across CTAs in a FIXED order by the last CTA (deterministic).
-#include "tdyn_common.cuh"
+#include "tdyn_mlp_ffma.cuh"
 
-namespace tdyn {
-namespace ffma {
-
-constexpr int kThreads = 256;
-constexpr int kRows = 16;            // rows per tile
-constexpr int kRG = kRows / 4;       // row groups of 4
-constexpr int kMaxWidth = 128;
-constexpr int kMaxGrid = 148 * 2;
-
-struct Net {
-    int L;
-    int dims[TDYN_MAX_LAYERS + 1];
-    int act;
-    const float* w[TDYN_MAX_LAYERS];
-    const float* b[TDYN_MAX_LAYERS];
-    int w_off[TDYN_MAX_LAYERS];      // float offsets into the shared weight area ([N][K+1])
-    int b_off[TDYN_MAX_LAYERS];
-    int p_off[TDYN_MAX_LAYERS];      // float offsets of layer l's (weight, bias) block in the flat parameter vector
-    int h_off[TDYN_MAX_LAYERS + 1];  // float offsets of h_l ([dims[l]][kRows]) in the activation area
-    int n_params, w_floats, h_floats, maxdim;
-};
-
-template <int ACT>
-__device__ __forceinline__ float act_fwd(float z) {
-    if (ACT == TDYN_ACT_RELU) return fmaxf(z, 0.f);
-    if (ACT == TDYN_ACT_SOFTPLUS) return z > 20.f ? z : log1pf(expf(z));
-    return tanhf(z);
-}
-// derivative of the activation expressed through its OUTPUT h
-template <int ACT>
-__device__ __forceinline__ float act_bwd(float h) {
-    if (ACT == TDYN_ACT_RELU) return h > 0.f ? 1.f : 0.f;
-    if (ACT == TDYN_ACT_SOFTPLUS) return 1.f - expf(-h);      // sigmoid(z) = 1 - exp(-softplus(z))
-    return 1.f - h * h;
-}
-
-__device__ __forceinline__ void load_weights(const Net& net, float* w_s) {
-    for (int l = 0; l < net.L; ++l) {
-        const int K = net.dims[l], N = net.dims[l + 1];
-        for (int i = threadIdx.x; i < N * K; i += kThreads) w_s[net.w_off[l] + (i / K) * (K + 1) + (i % K)] = __ldg(net.w[l] + i);
-        for (int i = threadIdx.x; i < N; i += kThreads) w_s[net.b_off[l] + i] = __ldg(net.b[l] + i);
-    }
-}
-
-// h_0[d][r] <- src[(row0 + r) * D + d]   (zero beyond `rows`)
-__device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ src, int D, int64_t row0, int64_t rows, float scale) {
-    for (int i = threadIdx.x; i < kRows * D; i += kThreads) {
-        const int r = i / D, d = i % D;
-        const int64_t gr = row0 + r;
-        dst[d * kRows + r] = gr < rows ? scale * __ldg(src + gr * D + d) : 0.f;
-    }
-}
-__device__ __forceinline__ void store_tile(float* __restrict__ dst, const float* src, int D, int64_t row0, int64_t rows, float sign) {
-    for (int i = threadIdx.x; i < kRows * D; i += kThreads) {
-        const int r = i / D, d = i % D;
-        const int64_t gr = row0 + r;
-        if (gr < rows) dst[gr * D + d] = sign * src[d * kRows + r];
-    }
-}
-
-// forward through all layers for the tile in h_s[h_off[0]]; leaves every h_l in shared memory
-template <int ACT>
-__device__ __forceinline__ void forward_tile(const Net& net, const float* w_s, float* h_s) {
-    for (int l = 0; l < net.L; ++l) {
-        const int K = net.dims[l], N = net.dims[l + 1];
-        const float* hin = h_s + net.h_off[l];
-        float* hout = h_s + net.h_off[l + 1];
-        const bool last = l == net.L - 1;
-        for (int i = threadIdx.x; i < kRG * N; i += kThreads) {
-            const int g = i / N, n = i % N;
-            const float* wr = w_s + net.w_off[l] + n * (K + 1);
-            const float bias = w_s[net.b_off[l] + n];
-            float4 acc = make_float4(bias, bias, bias, bias);
-            for (int k = 0; k < K; ++k) {
-                const float w = wr[k];
-                const float4 hv = *reinterpret_cast<const float4*>(hin + k * kRows + 4 * g);
-                acc.x = fmaf(w, hv.x, acc.x); acc.y = fmaf(w, hv.y, acc.y);
-                acc.z = fmaf(w, hv.z, acc.z); acc.w = fmaf(w, hv.w, acc.w);
-            }
-            if (!last) { acc.x = act_fwd<ACT>(acc.x); acc.y = act_fwd<ACT>(acc.y); acc.z = act_fwd<ACT>(acc.z); acc.w = act_fwd<ACT>(acc.w); }
-            *reinterpret_cast<float4*>(hout + n * kRows + 4 * g) = acc;
-        }
-        __syncthreads();
-    }
-}
-
-template <int ACT>
-__global__ void __launch_bounds__(kThreads) mlp_forward_kernel(const Net net, const float* __restrict__ y, float* __restrict__ out,
-                                                               int64_t rows, float sign) {
-    extern __shared__ __align__(16) float sm[];
-    float* w_s = sm;
-    float* h_s = sm + net.w_floats;
-    load_weights(net, w_s);
-    const int D = net.dims[0];
-    const int64_t tiles = (rows + kRows - 1) / kRows;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        __syncthreads();
-        load_tile(h_s + net.h_off[0], y, D, t * kRows, rows, 1.f);
-        __syncthreads();
-        forward_tile<ACT>(net, w_s, h_s);
-        store_tile(out, h_s + net.h_off[net.L], D, t * kRows, rows, sign);
-    }
-}
-
-struct AdjWs {
-    unsigned int ticket;
-    unsigned int pad[31];
-    float partials[1];       // [gridDim.x][n_params]
-};
-
-template <int ACT>
-__global__ void __launch_bounds__(kThreads) mlp_adjoint_kernel(const Net net, const float* __restrict__ x, const float* __restrict__ lam,
-                                                               float* __restrict__ dx, float* __restrict__ dlam,
-                                                               float* __restrict__ dmu, AdjWs* ws, int64_t rows, float sign) {
-    extern __shared__ __align__(16) float sm[];
-    float* w_s = sm;
-    float* h_s = w_s + net.w_floats;
-    float* d_s = h_s + net.h_floats;                 // two delta buffers [maxdim][kRows]
-    float* g_s = d_s + 2 * net.maxdim * kRows;       // parameter-gradient accumulator [n_params]
-    __shared__ bool is_last;
-    load_weights(net, w_s);
-    for (int i = threadIdx.x; i < net.n_params; i += kThreads) g_s[i] = 0.f;
-    const int D = net.dims[0];
-    const int64_t tiles = (rows + kRows - 1) / kRows;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        __syncthreads();
-        load_tile(h_s + net.h_off[0], x, D, t * kRows, rows, 1.f);
-        load_tile(d_s, lam, D, t * kRows, rows, -1.f);        // delta_L = -lam  (rows beyond the batch contribute 0)
-        __syncthreads();
-        forward_tile<ACT>(net, w_s, h_s);
-        store_tile(dx, h_s + net.h_off[net.L], D, t * kRows, rows, sign);
-        float* dcur = d_s;
-        float* dnxt = d_s + net.maxdim * kRows;
-        for (int l = net.L - 1; l >= 0; --l) {
-            const int K = net.dims[l], N = net.dims[l + 1];
-            const float* hin = h_s + net.h_off[l];
-            // wgrad: dW[n][k] += sum_r delta[n][r] * h_l[k][r];  db[n] += sum_r delta[n][r]
-            float* gw = g_s + net.p_off[l];
-            for (int i = threadIdx.x; i < N * K; i += kThreads) {
-                const int n = i / K, k = i % K;
-                float s = 0.f;
-#pragma unroll
-                for (int q = 0; q < kRG; ++q) {
-                    const float4 dv = *reinterpret_cast<const float4*>(dcur + n * kRows + 4 * q);
-                    const float4 hv = *reinterpret_cast<const float4*>(hin + k * kRows + 4 * q);
-                    s = fmaf(dv.x, hv.x, s); s = fmaf(dv.y, hv.y, s); s = fmaf(dv.z, hv.z, s); s = fmaf(dv.w, hv.w, s);
-                }
-                gw[i] += s;
-            }
-            for (int n = threadIdx.x; n < N; n += kThreads) {
-                float s = 0.f;
-#pragma unroll
-                for (int r = 0; r < kRows; ++r) s += dcur[n * kRows + r];
-                gw[N * K + n] += s;
-            }
-            // dgrad: delta_prev[k][r] = (sum_n delta[n][r] * W[n][k]) * act'(h_l[k][r])   (no act' into the input layer)
-            for (int i = threadIdx.x; i < kRG * K; i += kThreads) {
-                const int g = i / K, k = i % K;
-                const float* wc = w_s + net.w_off[l] + k;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int n = 0; n < N; ++n) {
-                    const float w = wc[n * (K + 1)];
-                    const float4 dv = *reinterpret_cast<const float4*>(dcur + n * kRows + 4 * g);
-                    acc.x = fmaf(w, dv.x, acc.x); acc.y = fmaf(w, dv.y, acc.y);
-                    acc.z = fmaf(w, dv.z, acc.z); acc.w = fmaf(w, dv.w, acc.w);
-                }
-                if (l > 0) {
-                    const float4 hv = *reinterpret_cast<const float4*>(hin + k * kRows + 4 * g);
-                    acc.x *= act_bwd<ACT>(hv.x); acc.y *= act_bwd<ACT>(hv.y); acc.z *= act_bwd<ACT>(hv.z); acc.w *= act_bwd<ACT>(hv.w);
-                }
-                *reinterpret_cast<float4*>(dnxt + k * kRows + 4 * g) = acc;
-            }
-            __syncthreads();
-            float* tmp = dcur; dcur = dnxt; dnxt = tmp;
-        }
-        store_tile(dlam, dcur, D, t * kRows, rows, sign);
-    }
-    // ---- deterministic cross-CTA reduction of the parameter gradient
-    __syncthreads();
-    float* mine = ws->partials + (size_t)blockIdx.x * net.n_params;
-    for (int i = threadIdx.x; i < net.n_params; i += kThreads) mine[i] = g_s[i];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int tk = atomicAdd(&ws->ticket, 1u);
-        is_last = tk == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    for (int i = threadIdx.x; i < net.n_params; i += kThreads) {
-        float s = 0.f;
-        for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(ws->partials + (size_t)b * net.n_params + i);
-        dmu[i] = sign * s;
-    }
-    if (threadIdx.x == 0) ws->ticket = 0u;
-}
-
-static int make_net(const tdyn_mlp_t* m, Net& net, const char* who) {
-    TDYN_REQUIRE(m && m->n_layers >= 1 && m->n_layers <= TDYN_MAX_LAYERS, "%s: n_layers out of range", who);
-    net.L = m->n_layers;
-    net.act = m->act;
-    int woff = 0, hoff = 0, poff = 0, maxdim = 0;
-    for (int l = 0; l <= net.L; ++l) {
-        net.dims[l] = m->dims[l];
-        TDYN_REQUIRE(net.dims[l] >= 1 && net.dims[l] <= kMaxWidth, "%s: width %d outside 1..%d", who, net.dims[l], kMaxWidth);
-        net.h_off[l] = hoff;
-        hoff += net.dims[l] * kRows;
-        if (net.dims[l] > maxdim) maxdim = net.dims[l];
-    }
-    TDYN_REQUIRE(net.dims[0] == net.dims[net.L], "%s: not an autonomous vector field (in %d != out %d)", who, net.dims[0], net.dims[net.L]);
-    for (int l = 0; l < net.L; ++l) {
-        TDYN_REQUIRE(m->w[l] && m->b[l], "%s: null weight/bias", who);
-        net.w[l] = m->w[l]; net.b[l] = m->b[l];
-        const int K = net.dims[l], N = net.dims[l + 1];
-        net.w_off[l] = woff; woff += N * (K + 1);
-        net.b_off[l] = woff; woff += N;
-        net.p_off[l] = poff; poff += N * K + N;
-    }
-    net.w_floats = (woff + 3) & ~3;
-    net.h_floats = hoff;
-    net.n_params = poff;
-    net.maxdim = maxdim;
-    return 0;
-}
-
-static size_t fwd_smem(const Net& n) { return sizeof(float) * (size_t)(n.w_floats + n.h_floats); }
-static size_t adj_smem(const Net& n) { return sizeof(float) * (size_t)(n.w_floats + n.h_floats + 2 * n.maxdim * kRows + n.n_params); }
-constexpr size_t kSmemLimit = 220 * 1024;
-
-}  // namespace ffma
-}  // namespace tdyn
 
 using namespace tdyn;
 

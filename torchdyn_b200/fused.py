@@ -118,6 +118,11 @@ class FusedMLP:
         """True if the narrow-net FFMA kernels can run this net."""
         return self._refresh(kern) and self._ffma_ok
 
+    def solve_workspace(self, kern):
+        if getattr(self, "_solve_ws", None) is None or self._solve_ws.device != kern.device:
+            self._solve_ws = kern.mlp_solve_workspace(self._desc)
+        return self._solve_ws
+
     def workspace(self, kern):
         if self._ffma_ws is None or self._ffma_ws.device != kern.device:
             self._ffma_ws = kern.mlp_ffma_workspace(self._desc)
@@ -239,6 +244,121 @@ def adjoint_for(vf, x_shape, device) -> Optional[FusedAdjoint]:
     if sum(p.numel() for p in vf.parameters()) != fm.n_params:
         return None
     return FusedAdjoint(fm, counters, kern)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# persistent solver: a whole adaptive odeint call in one cooperative kernel (tdyn_mlp_solve)
+# ------------------------------------------------------------------------------------------------------------------
+PERSISTENT = True         # set False to keep the host-driven loop (A/B runs)
+TRACE_CAP = 3 * 4096 + 1
+MAX_STEPS = 4000
+
+
+def _rk_plan(solver) -> "_lib.RkPlan":
+    p = solver.plan()
+    rp = _lib.RkPlan()
+    rp.n_extra = len(p.stages)
+    for s, st in enumerate(p.stages):
+        rp.mode[s], rp.nk[s], rp.c[s] = st.mode, len(st.coefs), float(st.c)
+        for j, v in enumerate(st.coefs):
+            rp.a[s][j] = v
+    rp.n_sol = len(p.bsol)
+    for j, v in enumerate(p.bsol):
+        rp.bsol[j] = v
+    rp.n_err = 0 if p.berr is None else len(p.berr)
+    for j, v in enumerate(p.berr or ()):
+        rp.berr[j] = v
+    rp.order = solver.order
+    rp.safety, rp.min_factor, rp.max_factor = solver.controller_constants()
+    return rp
+
+
+def _emit_trace(trace_dev, n_attempt):
+    from .numerics import odeint as _  # noqa: F401  (module object lives in sys.modules)
+    import sys
+    om = sys.modules["torchdyn_b200.numerics.odeint"]
+    if om.TRACE_SINK is None:
+        return
+    tr = trace_dev[:3 * n_attempt + 1].cpu().tolist()
+    rec = {"dt0": tr[0], "t": tr[1::3], "dt": tr[2::3], "ratio": tr[3::3]}
+    rec["accept"] = [r <= 1 for r in rec["ratio"]]
+    om.TRACE_SINK.append(rec)
+
+
+def _solver_ok(solver) -> bool:
+    from .numerics.solvers.ode import DormandPrince45, Tsitouras45
+    return type(solver) in (DormandPrince45, Tsitouras45)
+
+
+def try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, seminorm):
+    """Adaptive solve of a fusable narrow MLP field in ONE kernel launch.  ``f_`` is what odeint integrates (a
+    FusedField, or Reversed(FusedField) on a reversed span).  Returns (t_eval, sol) or None (generic path)."""
+    global _last
+    from .numerics.solvers.ode import Reversed
+    from . import distributed as _dist
+    if DISABLED or not PERSISTENT or _dist.is_enabled() or interpolator is not None or seminorm[0] or not _solver_ok(solver):
+        return None
+    sign, inner = 1.0, f_
+    if isinstance(f_, Reversed):
+        sign, inner = -1.0, f_.f
+    if not isinstance(inner, FusedField):
+        return None
+    fm, kern = inner.fm, inner.kern
+    if not (x.dim() == 2 and x.is_contiguous() and x.shape[1] == fm.dims[0] and kern.mlp_solve_supported(fm._desc, False)):
+        return None
+    rows, D = x.shape
+    n_t = len(ts)
+    cap = n_t + (512 if return_all_eval else 0)
+    dev = x.device
+    y0, y1 = x.clone(), torch.empty_like(x)
+    k = torch.empty(7 * rows * D, dtype=torch.float32, device=dev)
+    out = torch.empty(cap, rows, D, dtype=torch.float32, device=dev)
+    t_out = torch.empty(cap, dtype=torch.float32, device=dev)
+    status = torch.zeros(8, dtype=torch.int32, device=dev)
+    trace = torch.empty(TRACE_CAP, dtype=torch.float32, device=dev)
+    t_dev = torch.from_numpy(np.ascontiguousarray(ts, dtype=np.float32)).to(dev)
+    kern.mlp_solve(fm._desc, _rk_plan(solver), False, sign, atol, rtol, t_dev, return_all_eval, y0, y1, k, out, t_out, cap,
+                   fm.solve_workspace(kern), status, trace, rows, MAX_STEPS)
+    st = status.cpu().tolist()
+    n_out, n_attempt, nfe, err = st[0], st[1], st[3], st[4]
+    if err == 2:
+        return None                      # more accepted steps than the output buffer holds: let the host loop do it
+    if err != 0:
+        raise RuntimeError(f"torchdyn_b200.odeint: adaptive loop did not terminate ({n_attempt} attempts); the error "
+                           "estimate is probably NaN")
+    for c in inner.counters:
+        c.nfe += nfe
+    _emit_trace(trace, n_attempt)
+    _last = "persistent fused MLP integrator (tdyn_mlp_solve)"
+    return t_out[:n_out], out[:n_out]
+
+
+def try_adjoint_interval(dyn, A, t_from, t_to, solver, atol, rtol):
+    """One reverse-time interval of the backsolve adjoint (reference sensitivity.py:81-84) in ONE kernel launch.
+    ``A`` = flat [x, lam, mu, lam_t]; integrates from ``t_from`` down to ``t_to``.  Returns the new flat A or None."""
+    from . import distributed as _dist
+    fa = getattr(dyn, "fused", None)
+    if DISABLED or not PERSISTENT or fa is None or _dist.is_enabled() or not _solver_ok(solver) or not A.is_contiguous():
+        return None
+    fm, kern = fa.fm, fa.kern
+    if not kern.mlp_solve_supported(fm._desc, True):
+        return None
+    rows, D = dyn.x_shape
+    dev = A.device
+    y0, y1 = A.clone(), torch.empty_like(A)
+    k = torch.empty(7 * 2 * rows * D, dtype=torch.float32, device=dev)
+    status = torch.zeros(8, dtype=torch.int32, device=dev)
+    trace = torch.empty(TRACE_CAP, dtype=torch.float32, device=dev)
+    t_dev = torch.tensor([-float(t_from), -float(t_to)], dtype=torch.float32).to(dev)     # negated span (odeint.py:54-58)
+    kern.mlp_solve(fm._desc, _rk_plan(solver), True, -1.0, atol, rtol, t_dev, False, y0, y1, k, None, None, 0,
+                   fm.solve_workspace(kern), status, trace, rows, MAX_STEPS)
+    st = status.cpu().tolist()
+    if st[4] != 0:
+        raise RuntimeError(f"torchdyn_b200: adjoint solve did not terminate ({st[1]} attempts)")
+    for c in fa.counters:
+        c.nfe += st[3]
+    _emit_trace(trace, st[1])
+    return y0 if st[5] == 0 else y1
 
 
 def _isclose_count(t, save_at: np.ndarray) -> int:

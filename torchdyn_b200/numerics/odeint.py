@@ -94,6 +94,13 @@ def odeint(f: Callable, x: Tensor, t_span: Union[List, Tensor], solver: Union[st
         if isinstance(x, Tensor) and not x.is_contiguous():
             x = x.contiguous()
         t0 = f32(ts[0])
+        if type(solver) in BUILTIN_TYPES and isinstance(x, Tensor) and x.is_cuda:
+            from .. import fused
+            done = fused.try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, seminorm)
+            if done is not None:
+                if len(save_at) > 0:
+                    warn("Setting save_at has no effect on adaptive-step methods")
+                return done
         if type(solver) in BUILTIN_TYPES:
             kern = _kernels.get(x)
             k1 = call_vf(kern, f_, t0, x)

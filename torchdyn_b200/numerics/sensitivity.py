@@ -150,10 +150,13 @@ def _gather_odefunc_adjoint(vf, vf_params, solver, atol, rtol, interpolator, sol
 
             dLdt = torch.zeros(len(th)).to(xT)
             dLdt[-1] = lam_t
+            from .. import fused
             for i in range(len(th) - 1, 0, -1):
-                _, As = odeint(dyn, A, np.array([th[i], th[i - 1]], dtype=np.float32), solver_adjoint,
-                               atol=atol_adjoint, rtol=rtol_adjoint, seminorm=(True, 2 * n))
-                last = As[-1]
+                last = fused.try_adjoint_interval(dyn, A, th[i], th[i - 1], solver_adjoint, atol_adjoint, rtol_adjoint)
+                if last is None:
+                    _, As = odeint(dyn, A, np.array([th[i], th[i - 1]], dtype=np.float32), solver_adjoint,
+                                   atol=atol_adjoint, rtol=rtol_adjoint, seminorm=(True, 2 * n))
+                    last = As[-1]
                 xt = last[:n].reshape(xT.shape)
                 dLdt[i - 1] = last[n:2 * n] @ vf(t_sol[i], xt).flatten()                     # index i: reference quirk (:88)
                 lt = last[-1:] - g_t[i - 1]
