@@ -90,7 +90,7 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 }
 
 // stage input for flat element i: reference association order (ode.py:148-155, Appendix A.2 of SURVEY.md)
-__device__ __forceinline__ float combine_at(const float* __restrict__ y, float* const* K, const int* kidx, int nk, int mode,
+__device__ __forceinline__ float combine_at(const float* y, float* const* K, const int* kidx, int nk, int mode,
                                             const float* coef, float dt, int64_t i) {
     const float x = y[i];
     if (nk == 0) return x;
@@ -132,6 +132,21 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
 
     int cur = 0;
     int kidx[TDYN_MAX_STAGES] = {0, 1, 2, 3, 4, 5, 6};
+
+    // Element-wise passes touch ONLY the rows of this CTA's own tiles (x block and, for the adjoint, the lam block):
+    // a CTA then never reads what another CTA wrote, so stages and updates need no grid-wide synchronisation.
+    const int tile_elems = kRows * D;
+    const int64_t my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto for_own = [&](auto&& body) {
+        for (int64_t q = threadIdx.x; q < my_tiles * tile_elems; q += kThreads) {
+            const int64_t m = q / tile_elems;
+            const int64_t e = ((int64_t)blockIdx.x + m * gridDim.x) * tile_elems + (q % tile_elems);
+            if (e < n) {
+                body(e);
+                if (A.adjoint) body(e + n);
+            }
+        }
+    };
 
     // ---- evaluate the vector field of stage `so` (output K[kidx[so]]) at the stage input combine(Y[cur], ...)
     // gmode: 0 = none, 1 = into g_k1, 2 = into g_kl (last stage), 3 = weighted into g_step
@@ -267,12 +282,12 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
         // ================= init_step (utils.py:37-54); the un-negated f is used for the trial point (reference quirk):
         // f(t0 + h0, y0 + h0*f0_) with f0_ = k1 = sign*f: the trial STATE uses k1, the trial FIELD is +f (sign dropped)
         double a0 = 0.0, a1 = 0.0;
-        for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < n_state; e += (int64_t)gridDim.x * kThreads) {
+        for_own([&](int64_t e) {
             const float xv = A.Y[cur][e], fv = A.K[kidx[0]][e];
             const float scale = add_rn(A.atol, mul_rn(fabsf(xv), A.rtol));
             const float q0 = div_rn(xv, scale), q1 = div_rn(fv, scale);
             a0 += (double)mul_rn(q0, q0); a1 += (double)mul_rn(q1, q1);
-        }
+        });
         if (A.adjoint) {
             publish_g(g_k1, 0, A.sign);                  // mu part of f0 = f_(t0, A) = sign * (-lam^T df/dtheta)
             for (int i = blockIdx.x * kThreads + threadIdx.x; i < P; i += gridDim.x * kThreads) {
@@ -296,12 +311,12 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
         eval_stage(1, 1, TDYN_MODE_CHAIN, &one, h0, 2, 1.f);
         ++nfe;
         double a2 = 0.0;
-        for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < n_state; e += (int64_t)gridDim.x * kThreads) {
+        for_own([&](int64_t e) {
             const float xv = A.Y[cur][e], f0 = A.K[kidx[0]][e], f1 = mul_rn(A.sign, A.K[kidx[1]][e]);
             const float scale = add_rn(A.atol, mul_rn(fabsf(xv), A.rtol));
             const float q = div_rn(sub_rn(f1, f0), scale);
             a2 += (double)mul_rn(q, q);
-        }
+        });
         if (A.adjoint) {
             publish_g(g_kl, 1, 1.f);                      // un-negated field at the trial point
             for (int i = blockIdx.x * kThreads + threadIdx.x; i < P; i += gridDim.x * kThreads) {
@@ -321,6 +336,9 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
             h1 = (float)pow((double)base, 1.0 / (double)(pl.order + 1));
         }
         dt = fminf(mul_rn(100.f, h0), h1);
+        if (blockIdx.x == 0 && threadIdx.x == 0 && A.trace_cap >= 8) {     // init_step internals, for diagnostics
+            A.trace[A.trace_cap - 4] = d0; A.trace[A.trace_cap - 3] = d1; A.trace[A.trace_cap - 2] = d2; A.trace[A.trace_cap - 1] = h0;
+        }
     } else {
         dt = sub_rn(__ldg(A.t_span + 1), t0);
     }
@@ -334,7 +352,7 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
         if (A.out == nullptr) {
         } else if (n_out < A.out_cap) {
             float* dst = A.out + (size_t)n_out * (size_t)count_all;
-            for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < n_state; e += (int64_t)gridDim.x * kThreads) dst[e] = src[e];
+            for_own([&](int64_t e) { dst[e] = src[e]; });
             if (blockIdx.x == 0 && threadIdx.x == 0) A.t_out[n_out] = tv;
         } else {
             err_flag = 2;
@@ -373,7 +391,7 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
         // ---- x_new, err, scaled squared error
         float* ynew = A.Y[cur ^ 1];
         double acc = 0.0;
-        for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < n_state; e += (int64_t)gridDim.x * kThreads) {
+        for_own([&](int64_t e) {
             const float xv = A.Y[cur][e];
             float s = mul_rn(pl.bsol[0], A.K[kidx[0]][e]);
             for (int j = 1; j < pl.n_sol; ++j) s = add_rn(s, mul_rn(pl.bsol[j], A.K[kidx[j]][e]));
@@ -387,7 +405,7 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
                 const float r = div_rn(er, den);
                 if (e < count_norm) acc += (double)mul_rn(r, r);
             }
-        }
+        });
         float ratio = 0.f;
         bool accept = true;
         if (pl.n_err > 0) {
