@@ -326,7 +326,7 @@ def test_mlp_ffma_forward_matches_torch(dims, act, rows):
         want = net64(y.double()).float()
     for sign in (1.0, -1.0):
         out = kern.mlp_ffma_forward(fm._desc, y, torch.empty_like(y), sign, fm.flops_per_row)
-        assert_close(out, sign * want, f"ffma forward {dims} {act}", rtol=2e-6, atol_scale=1e-6)
+        assert_close(out, sign * want, f"ffma forward {dims} {act}", rtol=5e-6, atol_scale=4e-6)
 
 
 @pytest.mark.parametrize("dims,act", FFMA_SHAPES)
