@@ -70,6 +70,19 @@ def build(cfg, device, scale=1.0):
         kw = dict(solver="tsit5", sensitivity="interpolated_adjoint")
         return net, X, torch.linspace(0, 1, 2), kw, (lambda sol: sol[-1].pow(2).mean()), \
             f"c3 tsit5 + interpolated adjoint, MLP 128-1024-128, batch {B}"
+    if cfg == 4:
+        from torchdyn_b200.models import CNF, hutch_trace
+        from torchdyn_b200.nn import Augmenter
+        B = int(65536 * scale)
+        net = mlp([2, 64, 64, 64, 2], nn.Softplus)
+        noise_dist = torch.distributions.MultivariateNormal(torch.zeros(2, device=device), torch.eye(2, device=device))
+        cnf = CNF(net, trace_estimator=hutch_trace, noise_dist=noise_dist)
+        X = Augmenter(1, 1)(torch.randn(B, 2))
+        kw = dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="adjoint")
+
+        def loss(sol, nd=noise_dist):
+            return -(nd.log_prob(sol[-1][:, 1:]) - sol[-1][:, 0]).mean()
+        return cnf, X, torch.linspace(0, 1, 2), kw, loss, f"c4 CNF hutchinson, MLP 2-64-64-64-2 softplus, dopri5 1e-4, adjoint, batch {B}"
     if cfg == 5:
         B = int(4096 * scale)
         net = nn.Sequential(nn.Conv2d(11, 11, 3, padding=1), nn.Tanh())
@@ -138,7 +151,7 @@ def run_cpu(cfg, iters, scale):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="1,3,5")
+    ap.add_argument("--configs", default="1,3,4,5")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--scale", type=float, default=1.0, help="batch scale for configs 3 and 5")
@@ -147,4 +160,4 @@ if __name__ == "__main__":
     for c in [int(v) for v in a.configs.split(",")]:
         print(json.dumps(run_gpu(c, a.iters, a.scale)), flush=True)
         if a.cpu:
-            print(json.dumps(run_cpu(c, max(1, a.iters // 2), 1.0 if c == 1 else a.cpu_scale)), flush=True)
+            print(json.dumps(run_cpu(c, max(1, a.iters // 2), 1.0 if c == 1 else (1 / 8 if c == 4 else a.cpu_scale))), flush=True)

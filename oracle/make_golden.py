@@ -248,6 +248,39 @@ def main():
             torch.save(dict(kind="vdp", alpha=0.5, x=x, t_span=t_span, kw=kw, ref=out), os.path.join(OUT, name + ".pt"))
             print(f"{name}: nfe={out['nfe_total']:.0f} calls={len(out['traces'])}")
 
+    # cfg 4 reduced: CNF with Hutchinson trace (torchdyn/models/cnf.py:26-65), MLP 2-64-64-64-2 softplus, dopri5 1e-4,
+    # backsolve adjoint, B = 256, fixed noise (the reference samples it once per forward, core/neuralde.py:112-116)
+    from torchdyn.models import CNF, hutch_trace
+    from torchdyn.nn import Augmenter
+    torch.manual_seed(41)
+    xc = torch.randn(256, 2)
+    noise = torch.randn(256, 2)
+
+    class FixedNoise:
+        def __init__(self, v):
+            self.v = v
+
+        def sample(self, shape):
+            return self.v
+
+    netc = mlp([2, 64, 64, 64, 2], "softplus", 9)
+    cnf = CNF(netc, trace_estimator=hutch_trace, noise_dist=FixedNoise(noise))
+    kwc = dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="adjoint")
+
+    def cnf_loss(sol):
+        prior = torch.distributions.MultivariateNormal(torch.zeros(2), torch.eye(2))
+        return -(prior.log_prob(sol[-1][:, 1:]) - sol[-1][:, 0]).mean()
+
+    xa0 = Augmenter(1, 1)(xc)
+    outc = run_ref_neuralode(cnf, xa0, torch.linspace(0, 1, 2), cnf_loss, **kwc)
+    if args.check:
+        cnf.noise = noise
+        check_same(outc, run_oracle_neuralode(cnf, xa0, torch.linspace(0, 1, 2), cnf_loss, **kwc), "c4r_cnf_hutch")
+    torch.save(dict(kind="cnf", dims=[2, 64, 64, 64, 2], act="softplus", x=xc, noise=noise, t_span=torch.linspace(0, 1, 2),
+                    kw=kwc, params=[p.detach().clone() for p in netc.parameters()], ref=outc),
+               os.path.join(OUT, "c4r_cnf_hutch.pt"))
+    print(f"c4r_cnf_hutch: nfe={outc['nfe_total']:.0f} attempts={[len(r['t']) for r in outc['traces']]}")
+
     # spline: self-consistency vector (UNPINNED against torchcde, see oracle/__init__.py)
     torch.manual_seed(31)
     xs = torch.randn(5, 9, 3)

@@ -150,3 +150,33 @@ def check_functional_case(fx, t_eval, sol, traces, exact=False, state_rtol=STATE
         tol = 20 * max(fx["kw"].get("atol", 1e-3), fx["kw"].get("rtol", 1e-3))
         assert_close(sol[-1], ref["sol"][-1], "final state (noise-driven step sizes)", rtol=tol, atol_scale=tol)
     return strict
+
+
+class FixedNoise:
+    """noise 'distribution' returning the fixture's noise (NeuralODE samples it once per forward)"""
+
+    def __init__(self, v):
+        self.v = v
+
+    def sample(self, shape):
+        return self.v
+
+
+def run_cnf_case(fx, device):
+    """cfg 4 reduced: Augmenter -> NeuralODE(CNF(MLP, hutch_trace)) with dopri5 + backsolve adjoint."""
+    from torchdyn_b200.models import CNF, hutch_trace
+    from torchdyn_b200.nn import Augmenter
+    net = build_mlp(fx["dims"], fx["act"], fx["params"], device)
+    cnf = CNF(net, trace_estimator=hutch_trace, noise_dist=FixedNoise(fx["noise"].to(device)))
+    model = torchdyn_b200.NeuralODE(cnf, **fx["kw"])
+    x = Augmenter(1, 1)(fx["x"].to(device)).requires_grad_(True)
+    odeint_mod.TRACE_SINK = traces = []
+    try:
+        t_eval, sol = model(x, fx["t_span"])
+        nfe_f = model.vf.nfe
+        prior = torch.distributions.MultivariateNormal(torch.zeros(2, device=device), torch.eye(2, device=device))
+        loss = -(prior.log_prob(sol[-1][:, 1:]) - sol[-1][:, 0]).mean()
+        loss.backward()
+    finally:
+        odeint_mod.TRACE_SINK = None
+    return dict(model=model, net=net, x=x, t_eval=t_eval, sol=sol, loss=loss, traces=traces, nfe_fwd=nfe_f)

@@ -17,8 +17,8 @@ from torchdyn_b200.numerics.spline import NaturalCubicSpline
 from conftest import FUNCTIONAL_CASES, NEURALODE_CASES, VDP, VDP_CASES, build_mlp, load_golden
 from cpu_kernel_double import CpuKernels
 from oracle import erk_oracle as eo
-from parity_helpers import (assert_close, check_functional_case, check_neuralode_case, run_functional_case,
-                            run_neuralode_case)
+from parity_helpers import (assert_close, check_functional_case, check_neuralode_case, run_cnf_case,
+                            run_functional_case, run_neuralode_case)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -180,6 +180,12 @@ def test_active_controller_step_sequence_identical(name):
     dev = np.max(np.abs(np.array(g["t"]) - np.array(r["t"])) / np.maximum(np.abs(np.array(r["t"])), 1e-3))
     assert dev < 1e-3, f"forward step times deviate by {dev:.2e}"
     np.testing.assert_allclose(g["ratio"], r["ratio"], rtol=5e-2, atol=2e-3)
+
+
+def test_cnf_hutchinson_adjoint_matches_reference():
+    """cfg 4 (reduced) on the GPU: generic kernels, f and its VJPs via torch autograd."""
+    fx = load_golden("c4r_cnf_hutch")
+    check_neuralode_case(fx, run_cnf_case(fx, DEV))
 
 
 def test_generic_path_against_live_oracle_conv_state():

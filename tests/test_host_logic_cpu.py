@@ -16,7 +16,8 @@ from torchdyn_b200 import _kernels
 import torchdyn_b200.numerics.sensitivity as sens_mod
 from conftest import FUNCTIONAL_CASES, NEURALODE_CASES, VDP, VDP_CASES, load_golden
 from cpu_kernel_double import CpuKernels, OracleSpline
-from parity_helpers import (check_functional_case, check_neuralode_case, run_functional_case, run_neuralode_case)
+from parity_helpers import (check_functional_case, check_neuralode_case, run_cnf_case, run_functional_case,
+                            run_neuralode_case)
 
 
 @pytest.fixture(autouse=True)
@@ -46,6 +47,15 @@ def test_vdp_adjoint_matches_reference(name):
     fx = load_golden(name)
     f = VDP(fx["alpha"])
     out = run_neuralode_case(dict(fx, dims=None, act=None, params=None), "cpu", net=f)
+    check_neuralode_case(fx, out, exact=True)
+
+
+def test_cnf_hutchinson_adjoint_matches_reference():
+    """cfg 4 (reduced): the CNF vector field (autograd inside f, second-order autograd in the adjoint) through the
+    product's loops -- bit-identical to the executed reference with checker arithmetic below the ABI."""
+    fx = load_golden("c4r_cnf_hutch")
+    out = run_cnf_case(fx, "cpu")
+    # the fixture's gradient is w.r.t. the AUGMENTED input
     check_neuralode_case(fx, out, exact=True)
 
 
