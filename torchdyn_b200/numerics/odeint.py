@@ -29,7 +29,7 @@ from torch import Tensor
 from .. import _kernels
 from .. import distributed as _dist
 from .interpolators import FourthOrder, str_to_interp
-from .solvers.ode import BUILTIN_TYPES, Reversed, Tsitouras45, call_vf, str_to_solver
+from .solvers.ode import BUILTIN_TYPES, Reversed, Tsitouras45, call_vf, rk_combine, str_to_solver
 from .utils import adapt_step, init_step, rms_from_sumsq
 
 f32 = np.float32
@@ -62,9 +62,10 @@ def odeint(f: Callable, x: Tensor, t_span: Union[List, Tensor], solver: Union[st
     """Solve the IVP dx/dt = f(t, x), x(t_span[0]) = x.  Same arguments, warnings, errors and return
     convention as the reference (``(t_eval, sol)`` with ``sol[i]`` the state at ``t_eval[i]``)."""
     ts = _host_times(t_span)
-    if isinstance(x, Tensor) and x.is_cuda and (type(solver) == str or type(solver) in BUILTIN_TYPES):
+    if isinstance(x, Tensor) and x.is_cuda and (type(solver) == str or type(solver) in BUILTIN_TYPES) \
+            and not torch.is_grad_enabled():
         from .. import fused
-        f = fused.wrap(f, x)            # MLP vector fields are evaluated by this library's kernels
+        f = fused.wrap(f, x)            # MLP vector fields are evaluated by this library's kernels (no autograd graph)
     if ts[1] < ts[0]:   # reversed time: integrate -f(-t, x) over the negated span (odeint.py:54-58)
         if verbose:
             warn("You are integrating on a reversed time domain, adjusting the vector field automatically")
@@ -143,12 +144,16 @@ class _KernelAttempt:
         kern, p = self.kern, self.plan
         ks = self.solver.stages(kern, f, x, t, dt, k1)
         x_new = kern.empty_like(x)
-        kern.finish(x_new, None, x, ks, p.bsol, p.berr, dt, self.atol, self.rtol, self.norm_n)
+        dks = [k.detach() for k in ks]
+        kern.finish(x_new, None, x.detach(), dks, p.bsol, p.berr, dt, self.atol, self.rtol, self.norm_n)
         (sumsq,), count = _dist.reduce_sums(kern, 1, self.norm_n)
+        if torch.is_grad_enabled() and (x.requires_grad or any(k.requires_grad for k in ks)):
+            # sensitivity='autograd': the new state must stay on the graph (same values as the fused finish)
+            x_new = rk_combine(kern, x, ks[:len(p.bsol)], p.bsol, 1, dt)
         return ks[-1], x_new, ks, rms_from_sumsq(sumsq, count)
 
     def dense(self, x, x_new, ks, t, dt, t_out):
-        if type(self.interp) is FourthOrder:
+        if type(self.interp) is FourthOrder and not (torch.is_grad_enabled() and (x_new.requires_grad or x.requires_grad)):
             if self._bmid is None:
                 self._bmid = tuple(self.interp.bmid.detach().to("cpu", torch.float32).tolist())
             th = f32(f32(t_out - t) / f32(f32(t + dt) - t))
@@ -287,7 +292,7 @@ def _fixed_odeint(f, x, t_span, solver, save_at=(), args={}):
     proto = x if isinstance(x, Tensor) else x[next(iter(x))]
     if builtin:
         from .. import fused
-        out = fused.try_fixed(f, x, ts, sv, solver)
+        out = None if torch.is_grad_enabled() else fused.try_fixed(f, x, ts, sv, solver)
         if out is not None:
             sol = out
         else:
@@ -318,7 +323,7 @@ def _fixed_loop_kernels(f, x, ts, sv, solver):
     sol = [x] if _isclose_count(t, sv) else []
     for step in range(1, len(ts)):
         ks = solver.stages(kern, f, x, t, dt, None)
-        x = kern.combine(kern.empty_like(x), x, ks[:len(p.bsol)], p.bsol, mode_last, dt)
+        x = rk_combine(kern, x, ks[:len(p.bsol)], p.bsol, mode_last, dt)
         t = f32(t + dt)
         if _isclose_count(t, sv):
             sol.append(x)

@@ -60,18 +60,42 @@ class Reversed:
 def call_vf(kern, f, t_host, y):
     """Evaluate the vector field at host-side fp32 time ``t_host`` and make the result kernel-ready.
     Library-internal vector fields expose ``tdyn_eval(t_host, y)`` (no device time tensor, no sync); any
-    other callable gets the shape-[1] device tensor the reference would pass.  Raises if autograd is
-    recording: the kernels are not differentiable (use the adjoint sensitivities)."""
+    other callable gets the shape-[1] device tensor the reference would pass.  When autograd is recording
+    (sensitivity='autograd'), the result keeps its graph: the stage combinations are differentiable
+    (``rk_combine`` below)."""
     h = getattr(f, "tdyn_eval", None)
     k = h(t_host, y) if h is not None else f(kern.time_tensor(t_host, y), y)
-    if torch.is_grad_enabled() and isinstance(k, torch.Tensor) and k.requires_grad:
-        raise NotImplementedError(
-            "torchdyn_b200: back-propagating THROUGH the solver (sensitivity='autograd' with gradients enabled) is "
-            "not implemented on the CUDA kernel path; use sensitivity='adjoint' or 'interpolated_adjoint', or wrap "
-            "the call in torch.no_grad()")
     if k.dtype != y.dtype:
         k = k.to(y.dtype)
     return k if k.is_contiguous() else k.contiguous()
+
+
+class _CombineFn(torch.autograd.Function):
+    """y = combine(x, ks, coefs, mode, dt) on the CUDA kernel, differentiable w.r.t. x and every k_j
+    (sensitivity='autograd', reference core/problems.py:142-153: back-propagation THROUGH the solver).  The map is
+    linear: dy/dx = 1, dy/dk_j = dt*coef_j; dt is a constant of the graph (the reference computes its step sizes
+    under no_grad, numerics/utils.py:57, except for init_step's dependence of dt0 on x0, which is dropped here)."""
+
+    @staticmethod
+    def forward(ctx, kern, coefs, mode, dt, x, *ks):
+        ctx.scales = [float(f32(f32(dt) * f32(c))) for c in coefs]
+        ctx.has_x = x is not None
+        y = kern.combine(kern.empty_like(ks[0] if x is None else x), None if x is None else x.detach(),
+                         [k.detach() if k.is_contiguous() else k.detach().contiguous() for k in ks], coefs, mode, dt)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        gx = g if ctx.has_x else None
+        return (None, None, None, None, gx) + tuple(g * s for s in ctx.scales)
+
+
+def rk_combine(kern, x, ks, coefs, mode, dt):
+    """Stage combination: plain kernel launch, or its differentiable wrapper when autograd is recording."""
+    if torch.is_grad_enabled() and ((x is not None and x.requires_grad) or any(k.requires_grad for k in ks)):
+        return _CombineFn.apply(kern, tuple(coefs), mode, float(dt), x, *ks)
+    like = ks[0] if x is None else x
+    return kern.combine(kern.empty_like(like), x, ks, coefs, mode, dt)
 
 
 class _KernelSolver(DiffEqSolver):
@@ -102,7 +126,7 @@ class _KernelSolver(DiffEqSolver):
         p = self.plan()
         ks = [k1 if k1 is not None else call_vf(kern, f, t, x)]
         for st in p.stages:
-            y = kern.combine(kern.empty_like(x), x, ks[:len(st.coefs)], st.coefs, st.mode, dt)
+            y = rk_combine(kern, x, ks[:len(st.coefs)], st.coefs, st.mode, dt)
             ks.append(call_vf(kern, f, f32(t + st.c * dt), y))
         return ks
 
@@ -116,12 +140,10 @@ class _KernelSolver(DiffEqSolver):
         x = x if x.is_contiguous() else x.contiguous()
         p = self.plan()
         ks = self.stages(kern, f, x, t_h, dt_h, k1)
-        x_new = kern.empty_like(x)
+        x_new = rk_combine(kern, x, ks[:len(p.bsol)], p.bsol, MODE_INNER if len(p.bsol) > 1 else MODE_CHAIN, dt_h)
         if p.berr is None:
-            kern.combine(x_new, x, ks[:len(p.bsol)], p.bsol, MODE_INNER if len(p.bsol) > 1 else MODE_CHAIN, dt_h)
             return None, x_new, None
-        err = kern.empty_like(x)
-        kern.finish(x_new, err, x, ks, p.bsol, p.berr, dt_h, 1.0, 0.0, 0)
+        err = rk_combine(kern, None, ks[:len(p.berr)], p.berr, MODE_INNER, dt_h)
         return ks[-1], x_new, err, tuple(ks)
 
 

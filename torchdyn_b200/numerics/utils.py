@@ -40,6 +40,7 @@ def init_step(f, f0, x0, t0, order, atol, rtol):
     ``t0`` on reversed spans."""
     kern = _kernels.get(x0)
     t0 = f32(t0.item() if isinstance(t0, torch.Tensor) else t0)
+    x0, f0 = x0.detach(), f0.detach()       # step sizes are constants of the autograd graph
     kern.init_norms(x0, f0, None, atol, rtol)
     (s0, s1), count = _dist.reduce_sums(kern, 2, x0.numel())
     d0, d1 = rms_from_sumsq(s0, count), rms_from_sumsq(s1, count)
@@ -48,7 +49,8 @@ def init_step(f, f0, x0, t0, order, atol, rtol):
     else:
         h0 = f32(f32(0.01) * d0) / d1
     x_new = kern.combine(kern.empty_like(x0), x0, [f0], (1.0,), MODE_CHAIN, h0)     # x0 + h0*f0
-    f_new = call_vf(kern, f, f32(t0 + h0), x_new)
+    with torch.no_grad():
+        f_new = call_vf(kern, f, f32(t0 + h0), x_new)
     kern.init_norms(x0, f0, f_new, atol, rtol)
     s2 = _dist.reduce_sums(kern, 3, x0.numel())[0][2]
     d2 = f32(rms_from_sumsq(s2, count) / h0)
