@@ -8,15 +8,17 @@
 // One persistent CTA per SM walks 128-row tiles of the batch.  Per tile:
 //   workers (16 warps) : load x/k rows, combine in the reference's rounding order, split y into TF32 hi/lo and
 //                        store it K-major / 128B-swizzled in shared memory (the UMMA canonical layout);
-//   MMA warp (1 thread): layer 1 as tcgen05.mma kind::tf32  D1[128x256] (TMEM cols 0..255)
-//                        = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (3xTF32: fp32-accurate products, fp32 accumulate);
-//   workers            : D1 -> registers (tcgen05.ld), +bias, activation, hi/lo split -> next layer's A operand,
-//                        one 32-wide K-block at a time through a 2-stage ring, so layer 2's MMAs (TMEM cols
-//                        256..511) start while later K-blocks are still being produced; same again for layer 3
-//                        (N = 32, TMEM cols 0..31, D1 is dead by then);
+//   MMA warp (1 thread): layer 1 as tcgen05.mma kind::tf32  D1[128x256] (TMEM cols 0..255 = X)
+//                        = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (3xTF32: fp32-accurate products, fp32 accumulate);
+//   workers            : X -> registers (tcgen05.ld, next chunk prefetched), +bias (shared memory), activation, split:
+//                        hi goes back into the SAME TMEM columns (tcgen05.st) and is consumed by A-from-TMEM MMAs,
+//                        lo goes through a 3-stage shared-memory ring; one 32-wide K-block at a time, so layer 2's MMAs
+//                        (TMEM cols 256..511 = Y) start while later K-blocks are still being produced; same again for
+//                        layer 3 (N = 32, A_hi = Y in place, accumulator X[0,32));
 //   producer (1 thread): streams the pre-split, pre-swizzled weight images (tdyn_mlp_tc_prepare) from L2 into a
 //                        2 x 64 KB ring with cp.async.bulk + mbarrier complete_tx (weights total 640 KB per tile pass:
 //                        they cannot stay resident in 227 KB of shared memory).
+// The next tile's stage input is produced during layer 2; its layer 1 is issued once this tile's output left TMEM.
 // Algorithmic work: 163 840 FLOP per sample-NFE (x3 issued as TF32).  HBM traffic is negligible (128-256 B per
 // sample-NFE), the bound is the tensor pipe with the activation epilogue (512 tanh per sample-NFE) next.
 #include "tdyn_common.cuh"
