@@ -255,8 +255,12 @@ def main():
             # tensor bound: algorithmic FLOP/s against the 3xTF32 ceiling = measured bf16 peak / 6
             achieved = a["work"] / (a["ms"] * 1e-3) / 1e12
             peak = pk["bf16_sustained"] / 6.0
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "k2_traffic.json")
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")     # from the committed ncu --set full capture
             roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic,
                     "note": "achieved = algorithmic fp32-equivalent FLOP/s (2*sum(in*out) per sample-NFE); each is issued "
                             "as 3 TF32 MMAs (hi*hi + lo*hi + hi*lo); TF32 dense = 1/2 of bf16 dense, so the ceiling is "
                             f"bf16_sustained/6 of {pk['src']}; issued-TF32 TFLOP/s = 3x achieved"}
