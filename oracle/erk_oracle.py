@@ -84,13 +84,13 @@ _BMID_4TH = [0.10013431883002395, 0, 0.3918321794184259, -0.02982460176594817,
 
 # name -> (canonical, order, stepping class).  Reference registry: solvers/ode.py:320-325.
 _ALIASES = {
-    "euler": "euler",
+    "euler": "euler", "midpoint": "midpoint",
     "rk4": "rk4", "rk-4": "rk4", "RungeKutta4": "rk4",
     "dopri5": "dopri5", "DormandPrince45": "dopri5", "DormandPrince5": "dopri5",
     "tsit5": "tsit5", "Tsitouras45": "tsit5", "Tsitouras5": "tsit5",
 }
-_ORDER = {"euler": 1, "rk4": 4, "dopri5": 5, "tsit5": 5}
-_ADAPTIVE = {"euler": False, "rk4": False, "dopri5": True, "tsit5": True}
+_ORDER = {"euler": 1, "midpoint": 2, "rk4": 4, "dopri5": 5, "tsit5": 5}
+_ADAPTIVE = {"euler": False, "midpoint": False, "rk4": False, "dopri5": True, "tsit5": True}
 
 
 class Tableau:
@@ -98,7 +98,7 @@ class Tableau:
         self.name = _ALIASES[name]  # KeyError on unknown names, like SOLVER_DICT[...] (ode.py:335)
         self.order = _ORDER[self.name]
         self.adaptive = _ADAPTIVE[self.name]
-        spec = {"dopri5": _DOPRI5, "tsit5": _TSIT5, "rk4": _RK4, "euler": None}[self.name]
+        spec = {"dopri5": _DOPRI5, "tsit5": _TSIT5, "rk4": _RK4, "euler": None, "midpoint": None}[self.name]
         self.dtype = dtype
         if spec is None:
             self.c = self.a = self.bsol = self.berr = None
@@ -147,6 +147,9 @@ def rk_step(tab: Tableau, f: Callable, x: Tensor, t, dt, k1: Optional[Tensor] = 
         k1 = f(t, x)
     if tab.name == "euler":
         return None, x + dt * k1, None, None
+    if tab.name == "midpoint":                                   # ode.py:75-86
+        x_mid = x + 0.5 * dt * k1
+        return None, x + dt * f(t + 0.5 * dt, x_mid), None, None
     c, a, bs = tab.c, tab.a, tab.bsol
     if tab.name == "rk4":
         k2 = f(t + c[0] * dt, _inner(x, dt, [a[0]], [k1]))

@@ -165,7 +165,7 @@ def functional_cases():
     cases = {}
     torch.manual_seed(11)
     x = torch.randn(32, 3)
-    for solver in ("euler", "rk4", "dopri5", "tsit5"):
+    for solver in ("euler", "midpoint", "rk4", "dopri5", "tsit5"):
         cases[f"fn_{solver}_tspan10"] = dict(dims=[3, 16, 3], act="tanh", seed=7, x=x, t_span=torch.linspace(0, 2, 10),
                                              kw=dict(solver=solver, atol=1e-5, rtol=1e-5))
     cases["fn_dopri5_4th_tspan10"] = dict(dims=[3, 16, 3], act="tanh", seed=7, x=x, t_span=torch.linspace(0, 2, 10),

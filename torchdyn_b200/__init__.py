@@ -8,8 +8,8 @@ Python/PyTorch host code over hand-written sm_100a CUDA (``csrc/`` -> ``libtdyn_
 """
 from . import distributed  # noqa: F401
 from .core import DEFunc, DEFuncBase, NeuralODE, ODEProblem
-from .numerics import (SOLVER_DICT, DormandPrince45, Euler, RungeKutta4, Tsitouras45, odeint, str_to_solver)
+from .numerics import (SOLVER_DICT, DormandPrince45, Euler, Midpoint, RungeKutta4, Tsitouras45, odeint, str_to_solver)
 
 __version__ = "0.1.0"
-__all__ = ["odeint", "NeuralODE", "ODEProblem", "DEFunc", "DEFuncBase", "Euler", "RungeKutta4", "DormandPrince45",
+__all__ = ["odeint", "NeuralODE", "ODEProblem", "DEFunc", "DEFuncBase", "Euler", "Midpoint", "RungeKutta4", "DormandPrince45",
            "Tsitouras45", "SOLVER_DICT", "str_to_solver", "distributed"]

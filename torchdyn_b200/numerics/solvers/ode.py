@@ -156,6 +156,16 @@ class Euler(_KernelSolver):
         return Plan((), (1.0,), None, False)
 
 
+class Midpoint(_KernelSolver):
+    def __init__(self, dtype=torch.float32):
+        """Explicit midpoint, order 2 (ode.py:75-86): x_mid = x + 0.5*dt*k1; x + dt*f(t + 0.5*dt, x_mid)."""
+        super().__init__(2, "fixed", dtype)
+
+    def _build_plan(self):
+        # x + dt*(0*k1 + 1*k2) has the bits of x + dt*k2
+        return Plan((Stage(MODE_CHAIN, (0.5,), f32(0.5)),), (0.0, 1.0), None, False)
+
+
 class RungeKutta4(_KernelSolver):
     def __init__(self, dtype=torch.float32):
         """Classic RK4 (ode.py:89-104); every stage is x + dt*(a0*k1 + ...) including the literal zeros."""
@@ -194,11 +204,11 @@ class Tsitouras45(_Embedded54):
         self.tableau = construct_tsit5(dtype)
 
 
-BUILTIN_TYPES = (Euler, RungeKutta4, DormandPrince45, Tsitouras45)
+BUILTIN_TYPES = (Euler, Midpoint, RungeKutta4, DormandPrince45, Tsitouras45)
 
-# name registry of the hot-path solvers (reference ode.py:320-325; the other reference solvers -- midpoint,
-# alf, ieuler, multiple shooting -- are outside this implementation: unknown names raise KeyError as there)
-SOLVER_DICT = {'euler': Euler,
+# name registry of the explicit RK solvers (reference ode.py:320-325; the other reference solvers -- alf, ieuler,
+# multiple shooting -- are outside this implementation: unknown names raise KeyError as there)
+SOLVER_DICT = {'euler': Euler, 'midpoint': Midpoint,
                'rk4': RungeKutta4, 'rk-4': RungeKutta4, 'RungeKutta4': RungeKutta4,
                'dopri5': DormandPrince45, 'DormandPrince45': DormandPrince45, 'DormandPrince5': DormandPrince45,
                'tsit5': Tsitouras45, 'Tsitouras45': Tsitouras45, 'Tsitouras5': Tsitouras45}
