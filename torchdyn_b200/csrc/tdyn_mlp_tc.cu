@@ -40,13 +40,16 @@ constexpr int kLoStages = 3;                        // ring of [128 x 32] TF32 "
 constexpr uint32_t kSmemA1 = 0;                                     // layer-1 operand: hi tile | lo tile
 constexpr uint32_t kSmemLoRing = kSmemA1 + kAStage;                 // kLoStages x 16 KB
 constexpr uint32_t kSmemWRing = kSmemLoRing + kLoStages * kATile;   // 2 stages x 64 KB
-constexpr uint32_t kSmemBias = kSmemWRing + 2 * kWStage;            // b1[256] | b2[256] | b3[32] (fp32)
+constexpr uint32_t kSmemW1B = kSmemWRing + 2 * kWStage;             // W1 rows 224..255 (hi 4 KB | lo 4 KB), see layer1B
+constexpr uint32_t kW1BBytes = 8192;
+constexpr uint32_t kSmemBias = kSmemW1B + kW1BBytes;                // b1[256] | b2[256] | b3[32] (fp32)
 constexpr uint32_t kSmemBars = kSmemBias + (2 * kH + kD) * 4;
+constexpr int kNSplit = 224;                        // layer 1 is issued as N = 224 (early) + N = 32 (once D3 left TMEM)
 constexpr uint32_t kSmemTotal = kSmemBars + 256 + 1024;   // + slack for the manual 1024-byte alignment
 constexpr uint32_t kTmemCols = 512;
 
 enum Bar { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, A_FULL0, A_FULL1, A_FULL2, A_EMPTY0, A_EMPTY1, A_EMPTY2,
-           A1_FULL, D1_FULL, D2_FULL, D3_FULL, D_FREE, NUM_BARS };
+           A1_FULL, D1_FULL, D1B_FULL, D2_FULL, D3_FULL, D_FREE, W1B_FULL, W1B_EMPTY, NUM_BARS };
 
 struct Params {
     const uint8_t* wimg;       // 10 x 64 KB stage images
@@ -315,11 +318,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
     const uint32_t tmem = tmem_base_slot;
     const int my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     // TMEM map: X = cols [0,256): D1, converted in place to layer 2's A_hi; Y = cols [256,512): D2 -> layer 3's A_hi;
-    // D3 = cols [0,32) (layer 2's A_hi is dead once layer 2 has been issued: the tensor pipe executes in order)
-    constexpr uint32_t kColD1 = 0, kColD2 = 256, kColD3 = 0;
+    // D3 = cols [224,256) (layer 2's A_hi is dead once layer 2 has been issued: the tensor pipe executes in order).
+    // The NEXT tile's layer 1 is split: columns [0,224) are issued right after this tile's layer 2 (they run under the
+    // layer-2 -> 3 epilogue), columns [224,256) once this tile's D3 has been read out.
+    constexpr uint32_t kColD1 = 0, kColD2 = 256, kColD3 = kNSplit;
 
     if (warp == 0) {
-        // ================= weight producer: W1(0) | per tile: W2[0..7], W3, W1(next tile) =================
+        // ================= weight producer: W1(0) | per tile: W2[0..7], W1 + W1B(next tile), W3 =================
         if (lane == 0) {
             uint32_t it = 0;
             auto load = [&](int s) {
@@ -332,11 +337,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                 bulk_g2s(dst + kWStage / 2, src + kWStage / 2, kWStage / 2, bar(W_FULL0 + slot));
                 ++it;
             };
-            if (my_tiles > 0) load(0);
+            auto load_w1b = [&](int t) {
+                mbar_wait(bar(W1B_EMPTY), (t & 1) ^ 1);
+                mbar_expect_tx(bar(W1B_FULL), kW1BBytes);
+                bulk_g2s(sbase + kSmemW1B, P.wimg + (size_t)kWStagesPerTile * kWStage, kW1BBytes, bar(W1B_FULL));
+            };
+            if (my_tiles > 0) { load(0); load_w1b(0); }
             for (int t = 0; t < my_tiles; ++t) {
                 for (int s = 1; s <= 8; ++s) load(s);
+                if (t + 1 < my_tiles) { load(0); load_w1b(t + 1); }
                 load(9);
-                if (t + 1 < my_tiles) load(0);
             }
         }
     } else if (warp == 1) {
@@ -344,18 +354,26 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
         if (lane == 0) {
             uint32_t wit = 0, ait = 0;
             const uint32_t a1 = sbase + kSmemA1;
-            auto layer1 = [&](int t) {          // [128 x 32] x [256 x 32]^T -> D1
+            auto layer1a = [&](int t) {         // [128 x 32] x [224 x 32]^T -> D1 cols [0,224)
                 mbar_wait(bar(A1_FULL), t & 1);
                 const uint32_t slot = wit & 1, use = wit >> 1;
                 mbar_wait(bar(W_FULL0 + slot), use & 1);
                 tc_fence_after();
                 const uint32_t w = sbase + kSmemWRing + slot * kWStage;
-                issue_kblock(tmem + kColD1, a1, a1 + kATile, w, w + kWStage / 2, umma_idesc(kH), true);
+                issue_kblock(tmem + kColD1, a1, a1 + kATile, w, w + kWStage / 2, umma_idesc(kNSplit), true);
                 tc_commit(bar(W_EMPTY0 + slot));
                 tc_commit(bar(D1_FULL));
                 ++wit;
             };
-            if (my_tiles > 0) layer1(0);
+            auto layer1b = [&](int t) {         // remaining 32 output columns (W1 rows 224..255 from their own buffer)
+                mbar_wait(bar(W1B_FULL), t & 1);
+                tc_fence_after();
+                const uint32_t w = sbase + kSmemW1B;
+                issue_kblock(tmem + kColD1 + kNSplit, a1, a1 + kATile, w, w + 4096u, umma_idesc(kH - kNSplit), true);
+                tc_commit(bar(W1B_EMPTY));
+                tc_commit(bar(D1B_FULL));
+            };
+            if (my_tiles > 0) { layer1a(0); layer1b(0); }
             for (int t = 0; t < my_tiles; ++t) {
                 // ---- layer 2: 8 K-blocks, A_hi = X (in TMEM), A_lo ring -> D2 = Y
                 for (int j = 0; j < kH / kKB; ++j, ++wit, ++ait) {
@@ -370,7 +388,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                     tc_commit(bar(A_EMPTY0 + as));
                 }
                 tc_commit(bar(D2_FULL));
-                // ---- layer 3: 8 K-blocks, N = 32, A_hi = Y -> D3 = X[0,32); W3 stage = 8 x [hi 4 KB | lo 4 KB]
+                // ---- first 224 columns of the next tile's layer 1: tensor work for the layer-2 -> 3 epilogue phase
+                if (t + 1 < my_tiles) layer1a(t + 1);
+                // ---- layer 3: 8 K-blocks, N = 32, A_hi = Y -> D3 = X[224,256); W3 stage = 8 x [hi 4 KB | lo 4 KB]
                 {
                     const uint32_t ws = wit & 1, wu = wit >> 1;
                     mbar_wait(bar(W_FULL0 + ws), wu & 1);
@@ -388,10 +408,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                     tc_commit(bar(D3_FULL));
                     ++wit;
                 }
-                // ---- next tile's layer 1 overwrites X: wait until this tile's D3 has been read out
+                // ---- the last 32 columns of the next tile's layer 1 overwrite D3: wait until it has been read out
                 if (t + 1 < my_tiles) {
                     mbar_wait(bar(D_FREE), t & 1);
-                    layer1(t + 1);
+                    layer1b(t + 1);
                 }
             }
         }
@@ -424,7 +444,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                 for (int j = 0; j < kH / kKB; ++j, ++ait) {
                     uint32_t (&cur)[8] = (j & 1) ? rb : ra;
                     uint32_t (&nxt)[8] = (j & 1) ? ra : rb;
-                    if (j + 1 < kH / kKB) tmem_ld8(src + (uint32_t)((j + 1) * kKB), nxt);     // prefetch next chunk
+                    if (j + 1 < kH / kKB) {
+                        if (layer == 0 && (j + 1) * kKB == kNSplit) {       // last chunk of D1 is produced by layer1b
+                            mbar_wait(bar(D1B_FULL), tpar);
+                            tc_fence_after();
+                        }
+                        tmem_ld8(src + (uint32_t)((j + 1) * kKB), nxt);     // prefetch next chunk
+                    }
                     const float4 b0 = *reinterpret_cast<const float4*>(bias + j * kKB);
                     const float4 b1 = *reinterpret_cast<const float4*>(bias + j * kKB + 4);
                     float v[8];
@@ -514,6 +540,12 @@ __global__ void prepare_weights_kernel(const float* __restrict__ w1, const float
             w = w1[idx];
             hi_off = swz(n, k >> 2) + (k & 3) * 4;
             lo_off = hi_off + kWStage / 2;
+            if (n >= kNSplit) {                    // duplicate rows 224..255 into the W1B slab (stage index 10)
+                const size_t o = (size_t)kWStagesPerTile * kWStage + swz(n - kNSplit, k >> 2) + (k & 3) * 4;
+                const float h = tf32_rna(w);
+                *reinterpret_cast<float*>(img + o) = h;
+                *reinterpret_cast<float*>(img + o + 4096) = tf32_rna(w - h);
+            }
         } else if (idx < kD * kH + kH * kH) {      // W2[n][k]
             const int e = idx - kD * kH, n = e / kH, k = e % kH, kb = k / kKB, kk = k % kKB;
             w = w2[e];
@@ -545,7 +577,7 @@ int tdyn_mlp_tc_supported(const tdyn_mlp_t* m) {
 }
 
 int64_t tdyn_mlp_tc_prepared_bytes(const tdyn_mlp_t* m) {
-    return tdyn_mlp_tc_supported(m) ? (int64_t)tc::kWStagesPerTile * tc::kWStage : 0;
+    return tdyn_mlp_tc_supported(m) ? (int64_t)tc::kWStagesPerTile * tc::kWStage + tc::kW1BBytes : 0;
 }
 
 int tdyn_mlp_tc_prepare(const tdyn_mlp_t* m, void* wsplit, void* stream) {
