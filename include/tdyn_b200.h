@@ -35,8 +35,9 @@ extern "C" {
 #define TDYN_API
 #endif
 
-#define TDYN_ABI_VERSION 5
+#define TDYN_ABI_VERSION 6
 #define TDYN_MAX_STAGES 7
+#define TDYN_MAX_PEERS 8
 
 /* combination shapes of the reference steppers (numerics/solvers/ode.py) */
 #define TDYN_MODE_CHAIN 0 /* y = x + (dt*a0)*k0 + (dt*a1)*k1 + ...   left to right (ode.py:148,150-153 / :170,172-175) */
@@ -133,12 +134,24 @@ typedef struct {
     int order;
     float safety, min_factor, max_factor;
 } tdyn_rk_plan_t;
+/* Batch sharding over the GPUs of one box (one process per GPU).  `peer[r]` is rank r's exchange buffer
+ * (tdyn_comm_buffer_bytes() bytes, zero-initialised once) as mapped into THIS process (symmetric / peer memory over
+ * NVLink); `epoch` must increase with every collective launch and be equal on all ranks.  Each global reduction of the
+ * solve (init_step norms, the error norm of every attempted step) is then an in-kernel all-gather by direct peer
+ * stores + fixed-order sum -- the reference's single global controller without leaving the kernel.  comm == NULL or
+ * world == 1: single GPU.  Only the forward solve (adjoint = 0) can be sharded this way. */
+typedef struct {
+    int world, rank;
+    unsigned int epoch;
+    void* peer[TDYN_MAX_PEERS];
+} tdyn_comm_t;
+TDYN_API int64_t tdyn_comm_buffer_bytes(void);
 TDYN_API int tdyn_mlp_solve_supported(const tdyn_mlp_t* mlp, int adjoint);
 TDYN_API int64_t tdyn_mlp_solve_workspace_bytes(const tdyn_mlp_t* mlp);
 TDYN_API int tdyn_mlp_solve(const tdyn_mlp_t* mlp, const tdyn_rk_plan_t* plan, int adjoint, float sign, float atol, float rtol,
                             const float* t_span, int n_t, int return_all, float* y0, float* y1, float* k, float* out,
                             float* t_out, int out_cap, void* workspace, int* status, float* trace, int trace_cap,
-                            int64_t rows, int max_steps, void* stream);
+                            int64_t rows, int max_steps, const tdyn_comm_t* comm, void* stream);
 
 /* K2. Tensor-core (tcgen05, 3xTF32) stage kernel for wide MLPs (all hidden widths multiples of 64, >= 128):
  *   y = combine(x, k[], coef, mode, dt)   (same semantics as tdyn_rk_combine; n_k == 0 -> y = x)

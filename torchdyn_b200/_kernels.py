@@ -246,7 +246,7 @@ class CudaKernels:
 
     def mlp_solve(self, desc, plan, adjoint: bool, sign: float, atol: float, rtol: float, t_span: Tensor, return_all: bool,
                   y0: Tensor, y1: Tensor, k: Tensor, out: Optional[Tensor], t_out: Optional[Tensor], out_cap: int, ws: Tensor,
-                  status: Tensor, trace: Optional[Tensor], rows: int, max_steps: int):
+                  status: Tensor, trace: Optional[Tensor], rows: int, max_steps: int, comm=None):
         """Whole odeint call in one cooperative kernel (tdyn_mlp_solve); results are read from `status` by the caller."""
         global _launches
         with _Timed("mlp_solve", 0.0):
@@ -254,7 +254,7 @@ class CudaKernels:
                                          t_span.data_ptr(), t_span.numel(), int(return_all), y0.data_ptr(), y1.data_ptr(),
                                          k.data_ptr(), _ptr(out), _ptr(t_out), int(out_cap), ws.data_ptr(), status.data_ptr(),
                                          _ptr(trace), 0 if trace is None else trace.numel(), int(rows), int(max_steps),
-                                         self._stream())
+                                         None if comm is None else C.byref(comm), self._stream())
         _lib.check(rc, "tdyn_mlp_solve")
         _launches += 1
 

@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdyn_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_STAGES = 7
 MAX_LAYERS = 4
 MODE_CHAIN, MODE_INNER = 0, 1
@@ -37,6 +37,11 @@ class RkPlan(C.Structure):
                 ("c", C.c_float * 6), ("n_sol", C.c_int), ("bsol", C.c_float * MAX_STAGES), ("n_err", C.c_int),
                 ("berr", C.c_float * MAX_STAGES), ("order", C.c_int), ("safety", C.c_float), ("min_factor", C.c_float),
                 ("max_factor", C.c_float)]
+
+
+class Comm(C.Structure):
+    """mirror of tdyn_comm_t"""
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("epoch", C.c_uint), ("peer", C.c_void_p * 8)]
 
 
 # name -> (restype, argtypes); every symbol include/tdyn_b200.h declares
@@ -66,7 +71,8 @@ SIGNATURES = {
     "tdyn_mlp_solve_workspace_bytes": (C.c_int64, [C.POINTER(MlpDesc)]),
     "tdyn_mlp_solve": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(RkPlan), C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
-                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(Comm), C.c_void_p]),
+    "tdyn_comm_buffer_bytes": (C.c_int64, []),
     "tdyn_mlp_tc_prepared_bytes": (C.c_int64, [C.POINTER(MlpDesc)]),
     "tdyn_mlp_tc_supported": (C.c_int, [C.POINTER(MlpDesc)]),
     "tdyn_mlp_tc_prepare": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_void_p]),

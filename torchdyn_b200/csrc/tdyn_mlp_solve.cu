@@ -37,6 +37,12 @@ struct Plan {
     float safety, min_factor, max_factor;
 };
 
+constexpr int kXchgSlots = 64;
+struct XchgSlot {
+    double v[3];
+    unsigned long long tag;
+};
+
 struct Args {
     Net net;
     Plan plan;
@@ -55,6 +61,11 @@ struct Args {
     float* trace; int trace_cap;       // [0] = dt0, then (t, dt, ratio) per attempt
     int64_t rows;
     int max_steps;
+    // ---- batch sharded over GPUs: per-reduction exchange of the fp64 partial sums by direct peer stores (NVLink)
+    int world, rank;
+    unsigned int epoch;                // distinguishes launches: slots carry (epoch << 32 | sequence number)
+    XchgSlot* peer[TDYN_MAX_PEERS];    // every rank's exchange buffer (peer-mapped); [kXchgSlots][TDYN_MAX_PEERS]
+    double* gtot;                      // [3] device-local publication of the global totals
 };
 
 enum { ST_NOUT = 0, ST_ATTEMPT, ST_ACCEPT, ST_NFE, ST_ERROR, ST_FINAL, ST_COUNT };
@@ -231,8 +242,14 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
         __syncthreads();
     };
 
-    // ---- grid-wide sum of up to 3 per-thread fp64 values (fixed order) -> every thread gets the totals
+    // ---- grid-wide sum of up to 3 per-thread fp64 values (fixed order) -> every thread gets the totals.
+    // Sharded over GPUs (world > 1): CTA 0 then stores this GPU's totals into EVERY rank's exchange buffer through the
+    // peer mapping (NVLink stores, release at system scope), spins until all ranks' slots of this sequence number have
+    // arrived in its own buffer, and adds them in rank order -- the reference's single global controller, without
+    // leaving the kernel and without a host round trip.
     __shared__ double tot_sm[3];
+    unsigned int xseq = 0;
+    bool comm_timeout = false;
     auto grid_sum = [&](double v0, double v1, double v2, int nv) {
         const double s0 = block_sum(v0, red_sm);
         const double s1 = nv > 1 ? block_sum(v1, red_sm) : 0.0;
@@ -247,6 +264,37 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
             double s = 0.0;
             for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(A.partials + threadIdx.x * gridDim.x + b);
             tot_sm[threadIdx.x] = s;
+        }
+        if (A.world > 1) {
+            ++xseq;
+            __syncthreads();
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                const unsigned long long tag = ((unsigned long long)A.epoch << 32) | xseq;
+                const int slot = xseq % kXchgSlots;
+                for (int r = 0; r < A.world; ++r) {
+                    XchgSlot* dst = A.peer[r] + slot * TDYN_MAX_PEERS + A.rank;
+                    dst->v[0] = tot_sm[0]; dst->v[1] = tot_sm[1]; dst->v[2] = tot_sm[2];
+                    __threadfence_system();
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->tag), "l"(tag) : "memory");
+                }
+                double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+                for (int q = 0; q < A.world; ++q) {
+                    const XchgSlot* src = A.peer[A.rank] + slot * TDYN_MAX_PEERS + q;
+                    unsigned long long seen = 0;
+                    for (long long spin = 0; spin < (1ll << 27); ++spin) {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(&src->tag) : "memory");
+                        if (seen == tag) break;
+                        __nanosleep(64);
+                    }
+                    if (seen != tag) { g0 = g1 = g2 = __longlong_as_double(0x7ff8000000000000ll); break; }   // NaN -> loop exits with an error
+                    g0 += *(volatile const double*)&src->v[0]; g1 += *(volatile const double*)&src->v[1];
+                    g2 += *(volatile const double*)&src->v[2];
+                }
+                A.gtot[0] = g0; A.gtot[1] = g1; A.gtot[2] = g2;
+                __threadfence();
+            }
+            grid_sync(A.barrier);
+            if (threadIdx.x < 3) tot_sm[threadIdx.x] = __ldcg(A.gtot + threadIdx.x);
         }
         grid_sync(A.barrier);          // partials may be overwritten by the next reduction only after everyone has read
     };
@@ -266,8 +314,15 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
 
     const int nblk = A.adjoint ? 2 : 1;
     const int64_t n_state = nblk * n;                          // elements of the x (and lam) blocks
-    const int64_t count_norm = n_norm_blocks * n;              // error-norm count (seminorm)
-    const int64_t count_all = n_state + (A.adjoint ? P + 1 : 0);
+    int64_t count_norm = n_norm_blocks * n;                    // error-norm count (seminorm)
+    int64_t count_all = n_state + (A.adjoint ? P + 1 : 0);
+    const int64_t save_stride = count_all;                     // local size of one saved state
+    if (A.world > 1) {                                         // global element counts (shards may be unequal)
+        const bool one = blockIdx.x == 0 && threadIdx.x == 0;
+        grid_sum(one ? (double)count_norm : 0.0, one ? (double)count_all : 0.0, 0.0, 2);
+        count_norm = (int64_t)(tot_sm[0] + 0.5);
+        count_all = (int64_t)(tot_sm[1] + 0.5);
+    }
     const float* mu0 = A.adjoint ? A.Y[0] + 2 * n : nullptr;   // incoming mu (full) and lam_t
     const float t0 = __ldg(A.t_span);
     const float T = __ldg(A.t_span + A.n_t - 1);
@@ -351,7 +406,7 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
     auto save = [&](const float* src, float tv) {
         if (A.out == nullptr) {
         } else if (n_out < A.out_cap) {
-            float* dst = A.out + (size_t)n_out * (size_t)count_all;
+            float* dst = A.out + (size_t)n_out * (size_t)save_stride;
             for_own([&](int64_t e) { dst[e] = src[e]; });
             if (blockIdx.x == 0 && threadIdx.x == 0) A.t_out[n_out] = tv;
         } else {
@@ -403,7 +458,7 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
                 const float er = mul_rn(dt, ee);
                 const float den = add_rn(A.atol, mul_rn(A.rtol, fmaxf(fabsf(xv), fabsf(xn))));
                 const float r = div_rn(er, den);
-                if (e < count_norm) acc += (double)mul_rn(r, r);
+                if (e < (int64_t)n_norm_blocks * n) acc += (double)mul_rn(r, r);
             }
         });
         float ratio = 0.f;
@@ -492,6 +547,8 @@ int64_t tdyn_mlp_solve_workspace_bytes(const tdyn_mlp_t* m) {
     return (int64_t)(256 + 3 * 1024 * sizeof(double) + sizeof(float) * 2 * (size_t)1024 * net.n_params);
 }
 
+int64_t tdyn_comm_buffer_bytes(void) { return (int64_t)sizeof(solve::XchgSlot) * solve::kXchgSlots * TDYN_MAX_PEERS; }
+
 int tdyn_mlp_solve_supported(const tdyn_mlp_t* m, int adjoint) {
     ffma::Net net;
     if (!m || ffma::make_net(m, net, "tdyn_mlp_solve_supported") != 0) return 0;
@@ -504,7 +561,7 @@ int tdyn_mlp_solve_supported(const tdyn_mlp_t* m, int adjoint) {
 int tdyn_mlp_solve(const tdyn_mlp_t* m, const tdyn_rk_plan_t* plan, int adjoint, float sign, float atol, float rtol,
                    const float* t_span, int n_t, int return_all, float* y0, float* y1, float* k, float* out, float* t_out,
                    int out_cap, void* workspace, int* status, float* trace, int trace_cap, int64_t rows, int max_steps,
-                   void* stream) {
+                   const tdyn_comm_t* comm, void* stream) {
     solve::Args A{};
     if (int rc = ffma::make_net(m, A.net, "tdyn_mlp_solve")) return rc;
     TDYN_REQUIRE(tdyn_mlp_solve_supported(m, adjoint), "tdyn_mlp_solve: network not supported (shared memory)");
@@ -534,6 +591,17 @@ int tdyn_mlp_solve(const tdyn_mlp_t* m, const tdyn_rk_plan_t* plan, int adjoint,
     A.mu_partial = (float*)(ws + 256 + 3 * 1024 * sizeof(double));
     A.status = status; A.trace = trace; A.trace_cap = trace ? trace_cap : 0;
     A.rows = rows; A.max_steps = max_steps;
+    A.world = 1; A.rank = 0; A.epoch = 0;
+    A.gtot = (double*)(ws + 256 + 3 * 1024 * sizeof(double)) - 4;      // last 4 doubles of the partials area (grid <= 1020)
+    if (comm && comm->world > 1) {
+        TDYN_REQUIRE(!adjoint, "tdyn_mlp_solve: only the forward solve can be sharded in-kernel");
+        TDYN_REQUIRE(comm->world <= TDYN_MAX_PEERS && comm->rank >= 0 && comm->rank < comm->world, "tdyn_mlp_solve: bad comm");
+        A.world = comm->world; A.rank = comm->rank; A.epoch = comm->epoch;
+        for (int r = 0; r < comm->world; ++r) {
+            TDYN_REQUIRE(comm->peer[r], "tdyn_mlp_solve: comm->peer[%d] is null", r);
+            A.peer[r] = (solve::XchgSlot*)comm->peer[r];
+        }
+    }
 
     size_t smem = sizeof(float) * (size_t)(A.net.w_floats + A.net.h_floats);
     if (adjoint) smem += sizeof(float) * (size_t)(2 * A.net.maxdim * ffma::kRows + 4 * A.net.n_params);
@@ -550,7 +618,7 @@ int tdyn_mlp_solve(const tdyn_mlp_t* m, const tdyn_rk_plan_t* plan, int adjoint,
     const int64_t tiles = (rows + ffma::kRows - 1) / ffma::kRows;
     int64_t grid = (int64_t)per_sm * sms;
     if (grid > tiles) grid = tiles;
-    if (grid > 1024) grid = 1024;
+    if (grid > 1020) grid = 1020;
     cudaStream_t st = (cudaStream_t)stream;
     TDYN_CHECK_CUDA(cudaMemsetAsync(ws, 0, 256, st));          // barrier counter
     void* args[] = {(void*)&A};

@@ -18,7 +18,7 @@ from typing import Iterable, List, Optional, Tuple
 
 import torch
 
-_state = {"enabled": False, "group": None}
+_state = {"enabled": False, "group": None, "symm": None, "epoch": 0, "symm_failed": False}
 
 
 def enable(group=None):
@@ -30,6 +30,43 @@ def enable(group=None):
 
 def disable():
     _state["enabled"], _state["group"] = False, None
+
+
+def peer_comm(device):
+    """tdyn_comm_t for the in-kernel NVLink exchange of the persistent integrator, or None when peer-mapped
+    (symmetric) memory is unavailable -- callers then use the host-driven loop with the NCCL all-reduce.
+    Collective on first use (symmetric-memory rendezvous); every later call must be made by all ranks in the same
+    order (it advances the launch epoch)."""
+    if not _state["enabled"] or _state["symm_failed"] or device.type != "cuda":
+        return None
+    import torch.distributed as dist
+    from . import _lib
+    if _state["symm"] is None:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            lib = _lib.load()
+            nbytes = int(lib.tdyn_comm_buffer_bytes())
+            group = _state["group"] if _state["group"] is not None else dist.group.WORLD
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, group)
+            torch.cuda.synchronize(device)
+            dist.barrier(group)
+            if hdl.world_size > 8:
+                raise RuntimeError("more than 8 ranks")
+            _state["symm"] = (buf, hdl, [int(p) for p in hdl.buffer_ptrs])
+        except Exception as e:       # no peer access / API unavailable: stay on the NCCL path
+            import warnings
+            warnings.warn(f"torchdyn_b200: symmetric memory unavailable ({e}); sharded solves use the NCCL all-reduce path")
+            _state["symm_failed"] = True
+            return None
+    buf, hdl, ptrs = _state["symm"]
+    _state["epoch"] += 1
+    c = _lib.Comm()
+    c.world, c.rank, c.epoch = hdl.world_size, hdl.rank, _state["epoch"]
+    for r, p in enumerate(ptrs):
+        c.peer[r] = p
+    return c
 
 
 def is_enabled() -> bool:

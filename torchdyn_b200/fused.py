@@ -296,7 +296,7 @@ def try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, s
     global _last
     from .numerics.solvers.ode import Reversed
     from . import distributed as _dist
-    if DISABLED or not PERSISTENT or _dist.is_enabled() or interpolator is not None or seminorm[0] or not _solver_ok(solver):
+    if DISABLED or not PERSISTENT or interpolator is not None or seminorm[0] or not _solver_ok(solver):
         return None
     sign, inner = 1.0, f_
     if isinstance(f_, Reversed):
@@ -306,6 +306,11 @@ def try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, s
     fm, kern = inner.fm, inner.kern
     if not (x.dim() == 2 and x.is_contiguous() and x.shape[1] == fm.dims[0] and kern.mlp_solve_supported(fm._desc, False)):
         return None
+    comm = None
+    if _dist.is_enabled():
+        comm = _dist.peer_comm(x.device)      # in-kernel NVLink exchange of the error norm; None -> NCCL host path
+        if comm is None:
+            return None
     rows, D = x.shape
     n_t = len(ts)
     cap = n_t + (512 if return_all_eval else 0)
@@ -318,7 +323,7 @@ def try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, s
     trace = torch.empty(TRACE_CAP, dtype=torch.float32, device=dev)
     t_dev = torch.from_numpy(np.ascontiguousarray(ts, dtype=np.float32)).to(dev)
     kern.mlp_solve(fm._desc, _rk_plan(solver), False, sign, atol, rtol, t_dev, return_all_eval, y0, y1, k, out, t_out, cap,
-                   fm.solve_workspace(kern), status, trace, rows, MAX_STEPS)
+                   fm.solve_workspace(kern), status, trace, rows, MAX_STEPS, comm)
     st = status.cpu().tolist()
     n_out, n_attempt, nfe, err = st[0], st[1], st[3], st[4]
     if err == 2:
@@ -329,7 +334,7 @@ def try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, s
     for c in inner.counters:
         c.nfe += nfe
     _emit_trace(trace, n_attempt)
-    _last = "persistent fused MLP integrator (tdyn_mlp_solve)"
+    _last = "persistent fused MLP integrator (tdyn_mlp_solve)" + (", error norm exchanged by NVLink peer stores" if comm else "")
     return t_out[:n_out], out[:n_out]
 
 
