@@ -139,7 +139,8 @@ typedef struct {
  * NVLink); `epoch` must increase with every collective launch and be equal on all ranks.  Each global reduction of the
  * solve (init_step norms, the error norm of every attempted step) is then an in-kernel all-gather by direct peer
  * stores + fixed-order sum -- the reference's single global controller without leaving the kernel.  comm == NULL or
- * world == 1: single GPU.  Only the forward solve (adjoint = 0) can be sharded this way. */
+ * world == 1: single GPU.  For the adjoint the full-batch d(mu) needed by init_step is exchanged the same way (vectors of
+ * up to 16384 parameters); mu itself stays a per-rank partial sum (all-reduced by the caller, like a gradient). */
 typedef struct {
     int world, rank;
     unsigned int epoch;

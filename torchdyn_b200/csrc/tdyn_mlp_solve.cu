@@ -38,6 +38,10 @@ struct Plan {
 };
 
 constexpr int kXchgSlots = 64;
+constexpr int kVecMax = 16384;         // largest parameter count whose d(mu) can be exchanged in-kernel
+constexpr size_t kXchgScalarBytes = sizeof(double) * 4 * kXchgSlots * TDYN_MAX_PEERS;      // XchgSlot = 32 B
+constexpr size_t kXchgVecBytes = sizeof(float) * 2 * TDYN_MAX_PEERS * kVecMax;
+constexpr size_t kXchgFlagBytes = sizeof(unsigned long long) * 2 * TDYN_MAX_PEERS;
 struct XchgSlot {
     double v[3];
     unsigned long long tag;
@@ -65,6 +69,8 @@ struct Args {
     int world, rank;
     unsigned int epoch;                // distinguishes launches: slots carry (epoch << 32 | sequence number)
     XchgSlot* peer[TDYN_MAX_PEERS];    // every rank's exchange buffer (peer-mapped); [kXchgSlots][TDYN_MAX_PEERS]
+    float* vec_peer[TDYN_MAX_PEERS];   // every rank's vector exchange area: [2 regions][TDYN_MAX_PEERS][kVecMax] floats
+    unsigned long long* vflag_peer[TDYN_MAX_PEERS];   // [2 regions][TDYN_MAX_PEERS] tags
     double* gtot;                      // [3] device-local publication of the global totals
 };
 
@@ -311,6 +317,48 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
         for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(src + (size_t)b * P);
         return s;
     };
+    // full-batch d(mu) of region `reg` for index i: the cross-CTA sum and, when sharded, the cross-GPU sum.
+    // exchange_g() must have been called for the region (collective over the grid and over the ranks); afterwards
+    // gvec(reg, i) is valid for the indices i of THIS thread's slice (i == blockIdx*kThreads + threadIdx mod grid*kThreads).
+    float* gvec_store = A.mu_partial + (size_t)2 * gridDim.x * P;        // [2][P] device-local results
+    unsigned int vseq = 0;
+    auto exchange_g = [&](int reg) {
+        if (A.world == 1) {
+            for (int i = blockIdx.x * kThreads + threadIdx.x; i < P; i += gridDim.x * kThreads) gvec_store[reg * P + i] = full_g(reg, i);
+            return;
+        }
+        ++vseq;
+        const int vr = vseq & 1;
+        for (int i = blockIdx.x * kThreads + threadIdx.x; i < P; i += gridDim.x * kThreads) {
+            const float sv = full_g(reg, i);
+            for (int r = 0; r < A.world; ++r) A.vec_peer[r][((size_t)vr * TDYN_MAX_PEERS + A.rank) * kVecMax + i] = sv;
+        }
+        __threadfence_system();
+        grid_sync(A.barrier);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const unsigned long long tag = ((unsigned long long)A.epoch << 32) | vseq;
+            for (int r = 0; r < A.world; ++r)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.vflag_peer[r] + vr * TDYN_MAX_PEERS + A.rank), "l"(tag) : "memory");
+            for (int q = 0; q < A.world; ++q) {
+                unsigned long long seen = 0;
+                for (long long spin = 0; spin < (1ll << 27); ++spin) {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(A.vflag_peer[A.rank] + vr * TDYN_MAX_PEERS + q) : "memory");
+                    if (seen == tag) break;
+                    __nanosleep(64);
+                }
+                if (seen != tag) A.gtot[3] = __longlong_as_double(0x7ff8000000000000ll);     // poison: reported as an error
+            }
+            __threadfence();
+        }
+        grid_sync(A.barrier);
+        const float* own = A.vec_peer[A.rank] + (size_t)vr * TDYN_MAX_PEERS * kVecMax;
+        for (int i = blockIdx.x * kThreads + threadIdx.x; i < P; i += gridDim.x * kThreads) {
+            float sv = 0.f;
+            for (int q = 0; q < A.world; ++q) sv += *(volatile const float*)(own + (size_t)q * kVecMax + i);
+            gvec_store[reg * P + i] = sv;
+        }
+    };
+    auto gvec = [&](int reg, int i) { return gvec_store[reg * P + i]; };
 
     const int nblk = A.adjoint ? 2 : 1;
     const int64_t n_state = nblk * n;                          // elements of the x (and lam) blocks
@@ -319,7 +367,8 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
     const int64_t save_stride = count_all;                     // local size of one saved state
     if (A.world > 1) {                                         // global element counts (shards may be unequal)
         const bool one = blockIdx.x == 0 && threadIdx.x == 0;
-        grid_sum(one ? (double)count_norm : 0.0, one ? (double)count_all : 0.0, 0.0, 2);
+        const int64_t mine_all = n_state + ((A.adjoint && A.rank == 0) ? P + 1 : 0);     // replicated mu, lam_t: once
+        grid_sum(one ? (double)count_norm : 0.0, one ? (double)mine_all : 0.0, 0.0, 2);
         count_norm = (int64_t)(tot_sm[0] + 0.5);
         count_all = (int64_t)(tot_sm[1] + 0.5);
     }
@@ -345,13 +394,15 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
         });
         if (A.adjoint) {
             publish_g(g_k1, 0, A.sign);                  // mu part of f0 = f_(t0, A) = sign * (-lam^T df/dtheta)
-            for (int i = blockIdx.x * kThreads + threadIdx.x; i < P; i += gridDim.x * kThreads) {
-                const float mv = mu0[i], fv = full_g(0, i);
+            exchange_g(0);
+            // the mu block is replicated across ranks: it enters the global norm once (rank 0)
+            for (int i = blockIdx.x * kThreads + threadIdx.x; i < (A.rank == 0 ? P : 0); i += gridDim.x * kThreads) {
+                const float mv = mu0[i], fv = gvec(0, i);
                 const float scale = add_rn(A.atol, mul_rn(fabsf(mv), A.rtol));
                 const float q0 = div_rn(mv, scale), q1 = div_rn(fv, scale);
                 a0 += (double)mul_rn(q0, q0); a1 += (double)mul_rn(q1, q1);
             }
-            if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (blockIdx.x == 0 && threadIdx.x == 0 && A.rank == 0) {
                 const float lt = mu0[P];
                 const float q0 = div_rn(lt, add_rn(A.atol, mul_rn(fabsf(lt), A.rtol)));
                 a0 += (double)mul_rn(q0, q0);          // d(lam_t)/dt = 0 for an autonomous field
@@ -374,10 +425,11 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
         });
         if (A.adjoint) {
             publish_g(g_kl, 1, 1.f);                      // un-negated field at the trial point
-            for (int i = blockIdx.x * kThreads + threadIdx.x; i < P; i += gridDim.x * kThreads) {
+            exchange_g(1);
+            for (int i = blockIdx.x * kThreads + threadIdx.x; i < (A.rank == 0 ? P : 0); i += gridDim.x * kThreads) {
                 const float mv = mu0[i];
                 const float scale = add_rn(A.atol, mul_rn(fabsf(mv), A.rtol));
-                const float q = div_rn(sub_rn(full_g(1, i), full_g(0, i)), scale);
+                const float q = div_rn(sub_rn(gvec(1, i), gvec(0, i)), scale);
                 a2 += (double)mul_rn(q, q);
             }
             // lam_t: f1 - f0 = 0
@@ -527,6 +579,7 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) yfin[2 * n + P] = mu0[P];
     }
+    if (A.world > 1 && A.gtot[3] != A.gtot[3]) err_flag = 3;      // a peer never showed up in a vector exchange
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         A.status[ST_NOUT] = n_out; A.status[ST_ATTEMPT] = n_attempt; A.status[ST_ACCEPT] = n_accept;
         A.status[ST_NFE] = nfe; A.status[ST_ERROR] = err_flag; A.status[ST_FINAL] = cur;
@@ -547,7 +600,10 @@ int64_t tdyn_mlp_solve_workspace_bytes(const tdyn_mlp_t* m) {
     return (int64_t)(256 + 3 * 1024 * sizeof(double) + sizeof(float) * 2 * (size_t)1024 * net.n_params);
 }
 
-int64_t tdyn_comm_buffer_bytes(void) { return (int64_t)sizeof(solve::XchgSlot) * solve::kXchgSlots * TDYN_MAX_PEERS; }
+int64_t tdyn_comm_buffer_bytes(void) {
+    static_assert(sizeof(solve::XchgSlot) == 32, "exchange slot layout");
+    return (int64_t)(solve::kXchgScalarBytes + solve::kXchgVecBytes + solve::kXchgFlagBytes);
+}
 
 int tdyn_mlp_solve_supported(const tdyn_mlp_t* m, int adjoint) {
     ffma::Net net;
@@ -594,12 +650,15 @@ int tdyn_mlp_solve(const tdyn_mlp_t* m, const tdyn_rk_plan_t* plan, int adjoint,
     A.world = 1; A.rank = 0; A.epoch = 0;
     A.gtot = (double*)(ws + 256 + 3 * 1024 * sizeof(double)) - 4;      // last 4 doubles of the partials area (grid <= 1020)
     if (comm && comm->world > 1) {
-        TDYN_REQUIRE(!adjoint, "tdyn_mlp_solve: only the forward solve can be sharded in-kernel");
+        TDYN_REQUIRE(!adjoint || A.net.n_params <= solve::kVecMax,
+                     "tdyn_mlp_solve: %d parameters exceed the in-kernel exchange capacity (%d)", A.net.n_params, solve::kVecMax);
         TDYN_REQUIRE(comm->world <= TDYN_MAX_PEERS && comm->rank >= 0 && comm->rank < comm->world, "tdyn_mlp_solve: bad comm");
         A.world = comm->world; A.rank = comm->rank; A.epoch = comm->epoch;
         for (int r = 0; r < comm->world; ++r) {
             TDYN_REQUIRE(comm->peer[r], "tdyn_mlp_solve: comm->peer[%d] is null", r);
             A.peer[r] = (solve::XchgSlot*)comm->peer[r];
+            A.vec_peer[r] = (float*)((uint8_t*)comm->peer[r] + solve::kXchgScalarBytes);
+            A.vflag_peer[r] = (unsigned long long*)((uint8_t*)comm->peer[r] + solve::kXchgScalarBytes + solve::kXchgVecBytes);
         }
     }
 
@@ -621,6 +680,7 @@ int tdyn_mlp_solve(const tdyn_mlp_t* m, const tdyn_rk_plan_t* plan, int adjoint,
     if (grid > 1020) grid = 1020;
     cudaStream_t st = (cudaStream_t)stream;
     TDYN_CHECK_CUDA(cudaMemsetAsync(ws, 0, 256, st));          // barrier counter
+    TDYN_CHECK_CUDA(cudaMemsetAsync(A.gtot, 0, 4 * sizeof(double), st));
     void* args[] = {(void*)&A};
     TDYN_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(solve::kThreads), args, smem, st));
     return 0;

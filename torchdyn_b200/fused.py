@@ -343,11 +343,18 @@ def try_adjoint_interval(dyn, A, t_from, t_to, solver, atol, rtol):
     ``A`` = flat [x, lam, mu, lam_t]; integrates from ``t_from`` down to ``t_to``.  Returns the new flat A or None."""
     from . import distributed as _dist
     fa = getattr(dyn, "fused", None)
-    if DISABLED or not PERSISTENT or fa is None or _dist.is_enabled() or not _solver_ok(solver) or not A.is_contiguous():
+    if DISABLED or not PERSISTENT or fa is None or not _solver_ok(solver) or not A.is_contiguous():
         return None
     fm, kern = fa.fm, fa.kern
     if not kern.mlp_solve_supported(fm._desc, True):
         return None
+    comm = None
+    if _dist.is_enabled():
+        if fm.n_params > 16384:
+            return None
+        comm = _dist.peer_comm(A.device)
+        if comm is None:
+            return None
     rows, D = dyn.x_shape
     dev = A.device
     y0, y1 = A.clone(), torch.empty_like(A)
@@ -356,7 +363,7 @@ def try_adjoint_interval(dyn, A, t_from, t_to, solver, atol, rtol):
     trace = torch.empty(TRACE_CAP, dtype=torch.float32, device=dev)
     t_dev = torch.tensor([-float(t_from), -float(t_to)], dtype=torch.float32).to(dev)     # negated span (odeint.py:54-58)
     kern.mlp_solve(fm._desc, _rk_plan(solver), True, -1.0, atol, rtol, t_dev, False, y0, y1, k, None, None, 0,
-                   fm.solve_workspace(kern), status, trace, rows, MAX_STEPS)
+                   fm.solve_workspace(kern), status, trace, rows, MAX_STEPS, comm)
     st = status.cpu().tolist()
     if st[4] != 0:
         raise RuntimeError(f"torchdyn_b200: adjoint solve did not terminate ({st[1]} attempts)")
