@@ -407,3 +407,32 @@ def test_persistent_solver_matches_host_loop():
     np.testing.assert_allclose(tra["dt"], trb["dt"], rtol=1e-4, atol=1e-7)
     assert torch.equal(ta.cpu(), tb.cpu()) and sa.shape == sb.shape
     assert_close(sa, sb, "persistent vs host loop", rtol=1e-5, atol_scale=2e-6)
+
+
+def test_training_loop_tracks_the_oracle():
+    """Five Adam steps of a NeuralODE classifier (dopri5 + backsolve adjoint) on the GPU against the same loop with
+    the CPU oracle: parameters are updated in place between iterations (the fused kernels must pick the new values up)."""
+    from oracle import erk_oracle as eo
+    torch.manual_seed(3)
+    net_c = build_mlp([2, 32, 2], "tanh")
+    net_g = build_mlp([2, 32, 2], "tanh", [p.detach() for p in net_c.parameters()], DEV)
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(512, 2, generator=g)
+    y = (X[:, 0] * X[:, 1] > 0).long()
+    kw = dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="adjoint")
+    m_c, m_g = eo.OracleNeuralODE(net_c, **kw), torchdyn_b200.NeuralODE(net_g, **kw)
+    o_c, o_g = torch.optim.Adam(net_c.parameters(), lr=5e-3), torch.optim.Adam(net_g.parameters(), lr=5e-3)
+    ce = torch.nn.CrossEntropyLoss()
+    losses = []
+    for _ in range(5):
+        o_c.zero_grad(); o_g.zero_grad()
+        lc = ce(m_c(X, torch.linspace(0, 1, 2))[1][-1], y)
+        lg = ce(m_g(X.to(DEV), torch.linspace(0, 1, 2))[1][-1], y.to(DEV))
+        lc.backward(); lg.backward()
+        o_c.step(); o_g.step()
+        losses.append((float(lc), float(lg)))
+    for lc, lg in losses:
+        assert abs(lc - lg) <= 2e-5 * max(1.0, abs(lc)), losses
+    assert losses[-1][1] < losses[0][1]
+    for pc, pg in zip(net_c.parameters(), net_g.parameters()):
+        assert torch.allclose(pc, pg.cpu(), rtol=1e-3, atol=2e-5)
