@@ -35,7 +35,7 @@ extern "C" {
 #define TDYN_API
 #endif
 
-#define TDYN_ABI_VERSION 6
+#define TDYN_ABI_VERSION 7
 #define TDYN_MAX_STAGES 7
 #define TDYN_MAX_PEERS 8
 
@@ -153,6 +153,17 @@ TDYN_API int tdyn_mlp_solve(const tdyn_mlp_t* mlp, const tdyn_rk_plan_t* plan, i
                             const float* t_span, int n_t, int return_all, float* y0, float* y1, float* k, float* out,
                             float* t_out, int out_cap, void* workspace, int* status, float* trace, int trace_cap,
                             int64_t rows, int max_steps, const tdyn_comm_t* comm, void* stream);
+
+/* K4. One interval of the interpolated adjoint (numerics/sensitivity.py:130-152) for a narrow MLP in one cooperative
+ * kernel: state y = [lam (rows*D), mu (P)], x(t) from the natural cubic spline built by tdyn_spline_build (sol, kd,
+ * two_c, three_d, knots = device array of n_knots times), no seminorm (mu is inside the error norm: its batch-partial
+ * sums are reduced across the grid every attempted step).  t_start/t_end: the NEGATED span (-t_hi, -t_lo).
+ * `k`: 7 stage buffers of rows*D floats.  status/trace/workspace as for tdyn_mlp_solve. */
+TDYN_API int tdyn_mlp_solve_interp(const tdyn_mlp_t* mlp, const tdyn_rk_plan_t* plan, float atol, float rtol, float t_start,
+                                   float t_end, float* y0, float* y1, float* k, const float* sol, const float* kd,
+                                   const float* two_c, const float* three_d, const float* knots, int n_knots,
+                                   void* workspace, int* status, float* trace, int trace_cap, int64_t rows, int max_steps,
+                                   void* stream);
 
 /* K2. Tensor-core (tcgen05, 3xTF32) stage kernel for wide MLPs (all hidden widths multiples of 64, >= 128):
  *   y = combine(x, k[], coef, mode, dt)   (same semantics as tdyn_rk_combine; n_k == 0 -> y = x)

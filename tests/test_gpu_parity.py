@@ -436,3 +436,43 @@ def test_training_loop_tracks_the_oracle():
     assert losses[-1][1] < losses[0][1]
     for pc, pg in zip(net_c.parameters(), net_g.parameters()):
         assert torch.allclose(pc, pg.cpu(), rtol=1e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("sens", ["adjoint", "interpolated_adjoint"])
+def test_persistent_adjoints_match_host_loop(sens):
+    """Backward passes in one kernel per interval (tdyn_mlp_solve / tdyn_mlp_solve_interp) against the host-driven loop
+    over the stage kernels: same step sequences, gradients to 1e-5."""
+    import sys
+    from torchdyn_b200 import fused
+    om = sys.modules["torchdyn_b200.numerics.odeint"]
+    torch.manual_seed(11)
+    net = build_mlp([4, 48, 4], "softplus").to(DEV)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(2.0)
+    x0 = torch.randn(777, 4, device=DEV)
+    t_span = torch.linspace(0, 1.5, 3)
+    res = {}
+    for mode in (True, False):
+        fused.PERSISTENT = mode
+        for p in net.parameters():
+            p.grad = None
+        model = torchdyn_b200.NeuralODE(net, solver="tsit5", atol=1e-5, rtol=1e-5, sensitivity=sens,
+                                        atol_adjoint=1e-5, rtol_adjoint=1e-5)
+        x = x0.clone().requires_grad_(True)
+        om.TRACE_SINK = tr = []
+        try:
+            _, sol = model(x, t_span)
+            (sol[-1].pow(2).sum() + sol[1].sum()).backward()
+        finally:
+            om.TRACE_SINK = None
+            fused.PERSISTENT = True
+        res[mode] = (tr, x.grad.clone(), [p.grad.clone() for p in net.parameters()], model.vf.nfe)
+    (tra, gxa, gpa, nfa), (trb, gxb, gpb, nfb) = res[True], res[False]
+    assert nfa == nfb and len(tra) == len(trb)
+    for a, b in zip(tra, trb):
+        assert a["accept"] == b["accept"], (a["ratio"], b["ratio"])
+        np.testing.assert_allclose(a["t"], b["t"], rtol=2e-4, atol=1e-6)
+    assert_close(gxa, gxb, "dL/dx0", rtol=2e-5, atol_scale=5e-6)
+    for i, (a, b) in enumerate(zip(gpa, gpb)):
+        assert_close(a, b, f"dL/dtheta[{i}]", rtol=2e-5, atol_scale=5e-6)

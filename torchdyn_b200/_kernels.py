@@ -258,6 +258,20 @@ class CudaKernels:
         _lib.check(rc, "tdyn_mlp_solve")
         _launches += 1
 
+    def mlp_solve_interp(self, desc, plan, atol, rtol, t_start, t_end, y0, y1, k, sol, kd, two_c, three_d, knots, ws, status,
+                         trace, rows, max_steps):
+        """One interval of the interpolated adjoint in one cooperative kernel (tdyn_mlp_solve_interp)."""
+        global _launches
+        with _Timed("mlp_solve_interp", 0.0):
+            rc = self.lib.tdyn_mlp_solve_interp(C.byref(desc), C.byref(plan), float(atol), float(rtol), float(t_start),
+                                                float(t_end), y0.data_ptr(), y1.data_ptr(), k.data_ptr(), sol.data_ptr(),
+                                                kd.data_ptr(), two_c.data_ptr(), three_d.data_ptr(), knots.data_ptr(),
+                                                knots.numel(), ws.data_ptr(), status.data_ptr(), _ptr(trace),
+                                                0 if trace is None else trace.numel(), int(rows), int(max_steps),
+                                                self._stream())
+        _lib.check(rc, "tdyn_mlp_solve_interp")
+        _launches += 1
+
     def read_reduction(self, n: int = 1):
         """Device -> pinned host read of the first ``n`` reduction results (the step's ONE host sync)."""
         self.red_host[:n].copy_(self.red[:n], non_blocking=True)

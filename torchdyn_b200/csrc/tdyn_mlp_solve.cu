@@ -586,6 +586,313 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
     }
 }
 
+
+// =====================================================================================================================
+// K4: one interval of the INTERPOLATED adjoint (reference numerics/sensitivity.py:130-152) in one cooperative kernel.
+// State A = [lam (rows*D), mu (P)]; x(t) comes from the natural cubic spline of the forward trajectory (sol, kd, two_c,
+// three_d as built by tdyn_spline_build; piece = clamp(#knots < t - 1, 0, M-2), like CubicSpline.evaluate).  Unlike the
+// backsolve adjoint there is NO seminorm: mu is inside the error norm, so every attempted step reduces the CTAs'
+// batch-partials of sum_j b_j dmu_j and sum_j berr_j dmu_j (two P-vectors) across the grid before the norm.
+struct InterpArgs {
+    Net net;
+    Plan plan;
+    float atol, rtol;
+    float t_start, t_end;              // negated span: integrate from -t_hi up to -t_lo
+    float* Y[2];                       // [lam | mu]
+    float* K[TDYN_MAX_STAGES];         // lam blocks
+    const float* sol; const float* kd; const float* two_c; const float* three_d; const float* knots; int n_knots;
+    double* partials; float* mu_partial; unsigned int* barrier;
+    int* status; float* trace; int trace_cap;
+    int64_t rows; int max_steps;
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(kThreads) interp_adjoint_kernel(const InterpArgs A) {
+    extern __shared__ __align__(16) float sm[];
+    const Net& net = A.net;
+    const Plan& pl = A.plan;
+    float* w_s = sm;
+    float* h_s = w_s + net.w_floats;
+    float* d_s = h_s + net.h_floats;
+    float* g_k1 = d_s + 2 * net.maxdim * kRows;        // d(mu) batch-partial of the current k1 (raw: delta_L = -lam)
+    float* g_kl = g_k1 + net.n_params;                 // ... of the last stage (next step's k1 under FSAL)
+    float* s_b = g_kl + net.n_params;                  // sum_j>=1 bsol_j * dmu_j partial
+    float* s_e = s_b + net.n_params;                   // sum_j>=1 berr_j * dmu_j partial
+    __shared__ double red_sm[kThreads / 32];
+    __shared__ double tot_sm[3];
+    constexpr float sign = -1.f;                       // reversed time: f_(t, A) = -dyn(-t, A)
+
+    ffma::load_weights(net, w_s);
+    const int D = net.dims[0];
+    const int P = net.n_params;
+    const int64_t n = A.rows * D;
+    const int64_t tiles = (A.rows + kRows - 1) / kRows;
+    for (int i = threadIdx.x; i < 4 * P; i += kThreads) g_k1[i] = 0.f;
+    __syncthreads();
+    int cur = 0;
+    int kidx[TDYN_MAX_STAGES] = {0, 1, 2, 3, 4, 5, 6};
+    const int tile_elems = kRows * D;
+    const int64_t my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto for_own = [&](auto&& body) {
+        for (int64_t q = threadIdx.x; q < my_tiles * tile_elems; q += kThreads) {
+            const int64_t m = q / tile_elems;
+            const int64_t e = ((int64_t)blockIdx.x + m * gridDim.x) * tile_elems + (q % tile_elems);
+            if (e < n) body(e);
+        }
+    };
+    // mu indices owned by this thread (norm / update slices)
+    auto for_mu = [&](auto&& body) {
+        for (int i = blockIdx.x * kThreads + threadIdx.x; i < P; i += gridDim.x * kThreads) body(i);
+    };
+
+    // gmode: 1 -> g_k1, 2 -> g_kl (both raw, weight 1), 3 -> s_b += wb * g, s_e += we * g
+    auto eval_stage = [&](int so, int nk, int mode, const float* coef, float dt, float tau, int gmode, float wb, float we) {
+        float* gdst = gmode == 1 ? g_k1 : g_kl;
+        if (gmode != 3)
+            for (int i = threadIdx.x; i < P; i += kThreads) gdst[i] = 0.f;
+        // spline piece for the ACTUAL time tau (CubicSpline.evaluate: bucketize(t) - 1, clamped)
+        int cnt = 0;
+        for (int m = 0; m < A.n_knots; ++m) cnt += (__ldg(A.knots + m) < tau) ? 1 : 0;
+        int idx = cnt - 1;
+        idx = idx < 0 ? 0 : (idx > A.n_knots - 2 ? A.n_knots - 2 : idx);
+        const float sfrac = sub_rn(tau, __ldg(A.knots + idx));
+        const float* pa = A.sol + (size_t)idx * n;
+        const float* pb = A.kd + (size_t)idx * n;
+        const float* pc = A.two_c + (size_t)idx * n;
+        const float* pd = A.three_d + (size_t)idx * n;
+        const float* y = A.Y[cur];
+        float* kout = A.K[kidx[so]];
+        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+            __syncthreads();
+            const int64_t row0 = t * kRows;
+            for (int i = threadIdx.x; i < kRows * D; i += kThreads) {
+                const int r = i / D, d = i % D;
+                const int64_t gr = row0 + r;
+                float xv = 0.f, lv = 0.f;
+                if (gr < A.rows) {
+                    const int64_t e = gr * D + d;
+                    float inner = add_rn(mul_rn(0.5f, __ldg(pc + e)), div_rn(mul_rn(__ldg(pd + e), sfrac), 3.f));
+                    inner = add_rn(__ldg(pb + e), mul_rn(inner, sfrac));
+                    xv = add_rn(__ldg(pa + e), mul_rn(inner, sfrac));
+                    lv = -combine_at(y, A.K, kidx, nk, mode, coef, dt, e);
+                }
+                h_s[net.h_off[0] + d * kRows + r] = xv;
+                d_s[d * kRows + r] = lv;                  // delta_L = -lam
+            }
+            __syncthreads();
+            ffma::forward_tile<ACT>(net, w_s, h_s);
+            float* dcur = d_s;
+            float* dnxt = d_s + net.maxdim * kRows;
+            for (int l = net.L - 1; l >= 0; --l) {
+                const int K = net.dims[l], N = net.dims[l + 1];
+                const float* hin = h_s + net.h_off[l];
+                const int po = net.p_off[l];
+                for (int i = threadIdx.x; i < N * K + N; i += kThreads) {
+                    float sv = 0.f;
+                    if (i < N * K) {
+                        const int nn = i / K, k = i % K;
+#pragma unroll
+                        for (int q = 0; q < kRG; ++q) {
+                            const float4 dv = *reinterpret_cast<const float4*>(dcur + nn * kRows + 4 * q);
+                            const float4 hv = *reinterpret_cast<const float4*>(hin + k * kRows + 4 * q);
+                            sv = fmaf(dv.x, hv.x, sv); sv = fmaf(dv.y, hv.y, sv); sv = fmaf(dv.z, hv.z, sv); sv = fmaf(dv.w, hv.w, sv);
+                        }
+                    } else {
+                        const int nn = i - N * K;
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) sv += dcur[nn * kRows + r];
+                    }
+                    if (gmode == 3) { s_b[po + i] = fmaf(wb, sv, s_b[po + i]); s_e[po + i] = fmaf(we, sv, s_e[po + i]); }
+                    else gdst[po + i] += sv;
+                }
+                for (int i = threadIdx.x; i < kRG * K; i += kThreads) {
+                    const int g = i / K, k = i % K;
+                    const float* wc = w_s + net.w_off[l] + k;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int nn = 0; nn < N; ++nn) {
+                        const float w = wc[nn * (K + 1)];
+                        const float4 dv = *reinterpret_cast<const float4*>(dcur + nn * kRows + 4 * g);
+                        acc.x = fmaf(w, dv.x, acc.x); acc.y = fmaf(w, dv.y, acc.y);
+                        acc.z = fmaf(w, dv.z, acc.z); acc.w = fmaf(w, dv.w, acc.w);
+                    }
+                    if (l > 0) {
+                        const float4 hv = *reinterpret_cast<const float4*>(hin + k * kRows + 4 * g);
+                        acc.x *= ffma::act_bwd<ACT>(hv.x); acc.y *= ffma::act_bwd<ACT>(hv.y);
+                        acc.z *= ffma::act_bwd<ACT>(hv.z); acc.w *= ffma::act_bwd<ACT>(hv.w);
+                    }
+                    *reinterpret_cast<float4*>(dnxt + k * kRows + 4 * g) = acc;
+                }
+                __syncthreads();
+                float* tmp = dcur; dcur = dnxt; dnxt = tmp;
+            }
+            ffma::store_tile(kout, dcur, D, row0, A.rows, sign);
+        }
+        __syncthreads();
+    };
+
+    auto grid_sum = [&](double v0, double v1, double v2, int nv) {
+        const double s0 = block_sum(v0, red_sm);
+        const double s1 = nv > 1 ? block_sum(v1, red_sm) : 0.0;
+        const double s2 = nv > 2 ? block_sum(v2, red_sm) : 0.0;
+        if (threadIdx.x == 0) {
+            A.partials[0 * gridDim.x + blockIdx.x] = s0;
+            A.partials[1 * gridDim.x + blockIdx.x] = s1;
+            A.partials[2 * gridDim.x + blockIdx.x] = s2;
+        }
+        grid_sync(A.barrier);
+        if (threadIdx.x < 3) {
+            double s = 0.0;
+            for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(A.partials + threadIdx.x * gridDim.x + b);
+            tot_sm[threadIdx.x] = s;
+        }
+        grid_sync(A.barrier);
+    };
+    // publish two per-CTA P-vectors (region r0 <- scale0*v0, region r1 <- scale1*v1), then grid barrier
+    auto publish2 = [&](const float* v0, float sc0, const float* v1, float sc1) {
+        float* d0 = A.mu_partial + ((size_t)0 * gridDim.x + blockIdx.x) * P;
+        float* d1 = A.mu_partial + ((size_t)1 * gridDim.x + blockIdx.x) * P;
+        for (int i = threadIdx.x; i < P; i += kThreads) { d0[i] = sc0 * v0[i]; d1[i] = v1 ? sc1 * v1[i] : 0.f; }
+        grid_sync(A.barrier);
+    };
+    auto full_g = [&](int reg, int i) {
+        float sv = 0.f;
+        const float* src = A.mu_partial + (size_t)reg * gridDim.x * P + i;
+        for (unsigned int b = 0; b < gridDim.x; ++b) sv += __ldcg(src + (size_t)b * P);
+        return sv;
+    };
+    float* keep = A.mu_partial + (size_t)2 * gridDim.x * P;       // [P] device-local: full signed d(mu) of k1 at t0
+
+    const int64_t count_all = n + P;
+    const float t0 = A.t_start, T = A.t_end;
+    int nfe = 0;
+    const float* mu_in = A.Y[0] + n;
+
+    eval_stage(0, 0, 0, nullptr, 0.f, -t0, 1, 0.f, 0.f);            // k1 = f_(t0, A) = -dyn(-t0, A)
+    ++nfe;
+    // ---- init_step (utils.py:37-54); trial point uses the UN-negated dynamics at time (t0 + h0): reference quirk
+    float dt;
+    {
+        double a0 = 0.0, a1 = 0.0;
+        for_own([&](int64_t e) {
+            const float xv = A.Y[cur][e], fv = A.K[kidx[0]][e];
+            const float scale = add_rn(A.atol, mul_rn(fabsf(xv), A.rtol));
+            const float q0 = div_rn(xv, scale), q1 = div_rn(fv, scale);
+            a0 += (double)mul_rn(q0, q0); a1 += (double)mul_rn(q1, q1);
+        });
+        publish2(g_k1, sign, nullptr, 0.f);
+        for_mu([&](int i) {
+            const float mv = mu_in[i], fv = full_g(0, i);
+            keep[i] = fv;
+            const float scale = add_rn(A.atol, mul_rn(fabsf(mv), A.rtol));
+            const float q0 = div_rn(mv, scale), q1 = div_rn(fv, scale);
+            a0 += (double)mul_rn(q0, q0); a1 += (double)mul_rn(q1, q1);
+        });
+        grid_sum(a0, a1, 0.0, 2);
+        const float d0 = sqrtf((float)(tot_sm[0] / (double)count_all)), d1 = sqrtf((float)(tot_sm[1] / (double)count_all));
+        const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : div_rn(mul_rn(0.01f, d0), d1);
+        const float one = 1.f;
+        eval_stage(1, 1, TDYN_MODE_CHAIN, &one, h0, add_rn(t0, h0), 2, 0.f, 0.f);
+        ++nfe;
+        double a2 = 0.0;
+        for_own([&](int64_t e) {
+            const float xv = A.Y[cur][e], f0 = A.K[kidx[0]][e], f1 = mul_rn(sign, A.K[kidx[1]][e]);
+            const float scale = add_rn(A.atol, mul_rn(fabsf(xv), A.rtol));
+            const float q = div_rn(sub_rn(f1, f0), scale);
+            a2 += (double)mul_rn(q, q);
+        });
+        publish2(g_kl, 1.f, nullptr, 0.f);
+        for_mu([&](int i) {
+            const float mv = mu_in[i];
+            const float scale = add_rn(A.atol, mul_rn(fabsf(mv), A.rtol));
+            const float q = div_rn(sub_rn(full_g(0, i), keep[i]), scale);
+            a2 += (double)mul_rn(q, q);
+        });
+        grid_sum(a2, 0.0, 0.0, 1);
+        const float d2 = div_rn(sqrtf((float)(tot_sm[0] / (double)count_all)), h0);
+        float h1;
+        if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, mul_rn(h0, 1e-3f));
+        else h1 = (float)pow((double)mul_rn(div_rn(1.f, fmaxf(d1, d2)), 0.01f), 1.0 / (double)(pl.order + 1));
+        dt = fminf(mul_rn(100.f, h0), h1);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && A.trace_cap > 0) A.trace[0] = dt;
+
+    float t = t0;
+    int ck = 0, n_attempt = 0, n_accept = 0, err_flag = 0;
+    while (t < T) {
+        if (n_attempt >= A.max_steps || dt != dt) { err_flag = 1; break; }
+        ++n_attempt;
+        float dt_keep = 0.f;
+        bool ck_flag = false;
+        if (add_rn(t, dt) > T) dt = sub_rn(T, t);
+        if (ck < 1 && add_rn(t, dt) > T) { dt_keep = dt; ck_flag = true; dt = sub_rn(T, t); }
+        // weighted d(mu) sums of this attempt start from k1's contribution
+        for (int i = threadIdx.x; i < P; i += kThreads) { s_b[i] = pl.bsol[0] * g_k1[i]; s_e[i] = pl.berr[0] * g_k1[i]; }
+        for (int s = 0; s < pl.n_extra; ++s) {
+            const int so = s + 1;
+            const bool last = so == pl.n_extra;
+            const float wb = so < pl.n_sol ? pl.bsol[so] : 0.f;
+            const float we = so < pl.n_err ? pl.berr[so] : 0.f;
+            const float ts = add_rn(t, mul_rn(pl.c[s], dt));
+            eval_stage(so, pl.nk[s], pl.mode[s], pl.a[s], dt, -ts, last ? 2 : 3, wb, we);
+            ++nfe;
+            if (last)     // FSAL stage: raw partial kept in g_kl for the next step; its weights (b = 0, berr_7) applied here
+                for (int i = threadIdx.x; i < P; i += kThreads) { s_b[i] = fmaf(wb, g_kl[i], s_b[i]); s_e[i] = fmaf(we, g_kl[i], s_e[i]); }
+        }
+        float* ynew = A.Y[cur ^ 1];
+        double acc = 0.0;
+        for_own([&](int64_t e) {
+            const float xv = A.Y[cur][e];
+            float sv = mul_rn(pl.bsol[0], A.K[kidx[0]][e]);
+            for (int j = 1; j < pl.n_sol; ++j) sv = add_rn(sv, mul_rn(pl.bsol[j], A.K[kidx[j]][e]));
+            const float xn = add_rn(xv, mul_rn(dt, sv));
+            ynew[e] = xn;
+            float ee = mul_rn(pl.berr[0], A.K[kidx[0]][e]);
+            for (int j = 1; j < pl.n_err; ++j) ee = add_rn(ee, mul_rn(pl.berr[j], A.K[kidx[j]][e]));
+            const float r = div_rn(mul_rn(dt, ee), add_rn(A.atol, mul_rn(A.rtol, fmaxf(fabsf(xv), fabsf(xn)))));
+            acc += (double)mul_rn(r, r);
+        });
+        // mu block: full-batch weighted sums (signed: reversed field) -> mu_new, err, scaled error
+        __syncthreads();
+        publish2(s_b, sign, s_e, sign);
+        for_mu([&](int i) {
+            const float mv = A.Y[cur][n + i];
+            const float mn = add_rn(mv, mul_rn(dt, full_g(0, i)));
+            ynew[n + i] = mn;
+            const float r = div_rn(mul_rn(dt, full_g(1, i)), add_rn(A.atol, mul_rn(A.rtol, fmaxf(fabsf(mv), fabsf(mn)))));
+            acc += (double)mul_rn(r, r);
+        });
+        grid_sum(acc, 0.0, 0.0, 1);
+        const float ratio = sqrtf((float)(tot_sm[0] / (double)count_all));
+        const bool accept = ratio <= 1.f;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && 3 * n_attempt < A.trace_cap) {
+            A.trace[3 * n_attempt - 2] = t; A.trace[3 * n_attempt - 1] = dt; A.trace[3 * n_attempt] = ratio;
+        }
+        if (accept) {
+            ++n_accept;
+            const float tn = add_rn(t, dt);
+            if (ck < 1 && tn == T) ++ck;
+            const int tmp = kidx[0]; kidx[0] = kidx[pl.n_extra]; kidx[pl.n_extra] = tmp;
+            for (int i = threadIdx.x; i < P; i += kThreads) g_k1[i] = g_kl[i];
+            t = tn;
+            cur ^= 1;
+        }
+        if (ck_flag) dt = sub_rn(dt_keep, dt);
+        if (ratio == 0.f) dt = mul_rn(dt, pl.max_factor);
+        else {
+            const float lo = ratio < 1.f ? 1.f : pl.min_factor;
+            const float pw = (float)pow((double)ratio, (double)div_rn(1.f, (float)pl.order));
+            const float cand = div_rn(pl.safety, pw);
+            const float fac = (cand != cand) ? cand : fminf(pl.max_factor, fmaxf(cand, lo));
+            dt = mul_rn(dt, fac);
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        A.status[ST_NOUT] = 0; A.status[ST_ATTEMPT] = n_attempt; A.status[ST_ACCEPT] = n_accept;
+        A.status[ST_NFE] = nfe; A.status[ST_ERROR] = err_flag; A.status[ST_FINAL] = cur;
+    }
+}
+
 }  // namespace solve
 }  // namespace tdyn
 
@@ -681,6 +988,57 @@ int tdyn_mlp_solve(const tdyn_mlp_t* m, const tdyn_rk_plan_t* plan, int adjoint,
     cudaStream_t st = (cudaStream_t)stream;
     TDYN_CHECK_CUDA(cudaMemsetAsync(ws, 0, 256, st));          // barrier counter
     TDYN_CHECK_CUDA(cudaMemsetAsync(A.gtot, 0, 4 * sizeof(double), st));
+    void* args[] = {(void*)&A};
+    TDYN_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(solve::kThreads), args, smem, st));
+    return 0;
+}
+
+int tdyn_mlp_solve_interp(const tdyn_mlp_t* m, const tdyn_rk_plan_t* plan, float atol, float rtol, float t_start, float t_end,
+                          float* y0, float* y1, float* k, const float* sol, const float* kd, const float* two_c,
+                          const float* three_d, const float* knots, int n_knots, void* workspace, int* status, float* trace,
+                          int trace_cap, int64_t rows, int max_steps, void* stream) {
+    solve::InterpArgs A{};
+    if (int rc = ffma::make_net(m, A.net, "tdyn_mlp_solve_interp")) return rc;
+    TDYN_REQUIRE(tdyn_mlp_solve_supported(m, 1), "tdyn_mlp_solve_interp: network not supported (shared memory)");
+    TDYN_REQUIRE(plan && y0 && y1 && k && sol && kd && two_c && three_d && knots && workspace && status, "tdyn_mlp_solve_interp: null argument");
+    TDYN_REQUIRE(n_knots >= 2 && rows > 0 && plan->n_err > 0, "tdyn_mlp_solve_interp: need >= 2 knots, rows > 0 and an embedded pair");
+    solve::Plan& pl = A.plan;
+    pl.n_extra = plan->n_extra;
+    for (int s = 0; s < solve::kMaxExtra; ++s) {
+        pl.mode[s] = plan->mode[s]; pl.nk[s] = plan->nk[s]; pl.c[s] = plan->c[s];
+        for (int j = 0; j < TDYN_MAX_STAGES; ++j) pl.a[s][j] = plan->a[s][j];
+    }
+    pl.n_sol = plan->n_sol; pl.n_err = plan->n_err; pl.order = plan->order;
+    for (int j = 0; j < TDYN_MAX_STAGES; ++j) { pl.bsol[j] = plan->bsol[j]; pl.berr[j] = plan->berr[j]; }
+    pl.safety = plan->safety; pl.min_factor = plan->min_factor; pl.max_factor = plan->max_factor;
+    A.atol = atol; A.rtol = rtol; A.t_start = t_start; A.t_end = t_end;
+    const int64_t n = rows * A.net.dims[0];
+    A.Y[0] = y0; A.Y[1] = y1;
+    for (int j = 0; j < TDYN_MAX_STAGES; ++j) A.K[j] = k + (size_t)j * n;
+    A.sol = sol; A.kd = kd; A.two_c = two_c; A.three_d = three_d; A.knots = knots; A.n_knots = n_knots;
+    uint8_t* ws = (uint8_t*)workspace;
+    A.barrier = (unsigned int*)ws;
+    A.partials = (double*)(ws + 256);
+    A.mu_partial = (float*)(ws + 256 + 3 * 1024 * sizeof(double));
+    A.status = status; A.trace = trace; A.trace_cap = trace ? trace_cap : 0;
+    A.rows = rows; A.max_steps = max_steps;
+    const size_t smem = sizeof(float) * (size_t)(A.net.w_floats + A.net.h_floats + 2 * A.net.maxdim * ffma::kRows + 4 * A.net.n_params);
+    const void* fn = A.net.act == TDYN_ACT_TANH ? (const void*)solve::interp_adjoint_kernel<TDYN_ACT_TANH>
+                   : A.net.act == TDYN_ACT_SOFTPLUS ? (const void*)solve::interp_adjoint_kernel<TDYN_ACT_SOFTPLUS>
+                                                    : (const void*)solve::interp_adjoint_kernel<TDYN_ACT_RELU>;
+    TDYN_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    TDYN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, solve::kThreads, smem));
+    TDYN_REQUIRE(per_sm >= 1, "tdyn_mlp_solve_interp: kernel does not fit on an SM");
+    int dev = 0, sms = 0;
+    TDYN_CHECK_CUDA(cudaGetDevice(&dev));
+    TDYN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t tiles = (rows + ffma::kRows - 1) / ffma::kRows;
+    int64_t grid = (int64_t)per_sm * sms;
+    if (grid > tiles) grid = tiles;
+    if (grid > 1020) grid = 1020;
+    cudaStream_t st = (cudaStream_t)stream;
+    TDYN_CHECK_CUDA(cudaMemsetAsync(ws, 0, 256, st));
     void* args[] = {(void*)&A};
     TDYN_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(solve::kThreads), args, smem, st));
     return 0;

@@ -373,6 +373,38 @@ def try_adjoint_interval(dyn, A, t_from, t_to, solver, atol, rtol):
     return y0 if st[5] == 0 else y1
 
 
+def try_interp_interval(dyn, A, t_from, t_to, solver, atol, rtol):
+    """One reverse-time interval of the INTERPOLATED adjoint (reference sensitivity.py:151-152) in ONE kernel launch.
+    ``A`` = flat [lam, mu]; x(t) comes from ``dyn.spline`` (built by tdyn_spline_build).  Returns the new A or None."""
+    from . import distributed as _dist
+    fa = getattr(dyn, "fused", None)
+    sp = getattr(dyn, "spline", None)
+    if DISABLED or not PERSISTENT or fa is None or _dist.is_enabled() or not _solver_ok(solver) or not A.is_contiguous():
+        return None
+    if not all(hasattr(sp, a) for a in ("sol", "kd", "two_c", "three_d", "t")):
+        return None
+    fm, kern = fa.fm, fa.kern
+    if not kern.mlp_solve_supported(fm._desc, True):
+        return None
+    rows, D = dyn.lam_shape
+    dev = A.device
+    if getattr(sp, "t_dev", None) is None:
+        sp.t_dev = torch.from_numpy(np.ascontiguousarray(sp.t, dtype=np.float32)).to(dev)
+    y0, y1 = A.clone(), torch.empty_like(A)
+    k = torch.empty(7 * rows * D, dtype=torch.float32, device=dev)
+    status = torch.zeros(8, dtype=torch.int32, device=dev)
+    trace = torch.empty(TRACE_CAP, dtype=torch.float32, device=dev)
+    kern.mlp_solve_interp(fm._desc, _rk_plan(solver), atol, rtol, -float(t_from), -float(t_to), y0, y1, k, sp.sol, sp.kd,
+                          sp.two_c, sp.three_d, sp.t_dev, fm.solve_workspace(kern), status, trace, rows, MAX_STEPS)
+    st = status.cpu().tolist()
+    if st[4] != 0:
+        raise RuntimeError(f"torchdyn_b200: interpolated-adjoint solve did not terminate ({st[1]} attempts)")
+    for c in fa.counters:
+        c.nfe += st[3]
+    _emit_trace(trace, st[1])
+    return y0 if st[5] == 0 else y1
+
+
 def _isclose_count(t, save_at: np.ndarray) -> int:
     return int(np.sum(np.abs(f32(t) - save_at) <= (1e-8 + 1e-5 * np.abs(save_at))))
 

@@ -194,10 +194,16 @@ def _gather_odefunc_interp_adjoint(vf, vf_params, solver, atol, rtol, interpolat
             A = torch.cat([lamT.flatten(), torch.zeros(P, dtype=lamT.dtype, device=lamT.device)])
             spline = NaturalCubicSpline(sol.detach(), ctx.t_host)
             dyn = InterpDynamics(vf, spline, lamT.shape, P, integral_loss, device=lamT.device)
+            from .. import fused
+            solver_obj = solver if not isinstance(solver, str) else None
             for i in range(len(span) - 1, 0, -1):
                 # forward solver and tolerances, no seminorm (sensitivity.py:152)
-                _, As = odeint(dyn, A, np.array([span[i], span[i - 1]], dtype=np.float32), solver, atol=atol, rtol=rtol)
-                last = As[-1]
+                last = None
+                if solver_obj is not None:
+                    last = fused.try_interp_interval(dyn, A, span[i], span[i - 1], solver_obj, atol, rtol)
+                if last is None:
+                    _, As = odeint(dyn, A, np.array([span[i], span[i - 1]], dtype=np.float32), solver, atol=atol, rtol=rtol)
+                    last = As[-1]
                 A = torch.cat([last[:n] + g_sol[i - 1].flatten(), last[-P:]])
             lam, mu = A[:n].reshape(lamT.shape), A[-P:]
             return (mu, lam, None, None, None)
