@@ -122,7 +122,8 @@ TDYN_API int tdyn_mlp_ffma_adjoint(const tdyn_mlp_t* mlp, const float* x, const 
  * its batch-partial and reduced once at the end.  `plan` restates the stepper (numerics/solvers/ode.py:145-178).
  * status (device, 6 ints): n_out, n_attempt, n_accept, nfe, error (0 ok, 1 max_steps/NaN, 2 out_cap), index (0/1) of
  * the y buffer holding the final state.  trace (device, optional): [0] = dt0, then (t, dt, error_ratio) per attempt.
- * `k`: 7 stage buffers, contiguous, each (adjoint ? 2 : 1) * rows * D floats.  `out`: [out_cap][state elems]. */
+ * `k`: 7 stage buffers, contiguous, each (adjoint ? 2 : 1) * rows * D floats.  `out`: [out_cap][state elems].
+ * `t_span` is a HOST array of n_t <= 1024 times (already negated for reversed spans); everything else is device memory. */
 typedef struct {
     int n_extra;                        /* stages after k1: 6 (dopri5/tsit5), 3 (rk4), 0 (euler) */
     int mode[6];                        /* TDYN_MODE_* of each stage input */

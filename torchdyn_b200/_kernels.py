@@ -244,14 +244,14 @@ class CudaKernels:
     def mlp_solve_workspace(self, desc) -> Tensor:
         return torch.zeros(int(self.lib.tdyn_mlp_solve_workspace_bytes(C.byref(desc))), dtype=torch.uint8, device=self.device)
 
-    def mlp_solve(self, desc, plan, adjoint: bool, sign: float, atol: float, rtol: float, t_span: Tensor, return_all: bool,
+    def mlp_solve(self, desc, plan, adjoint: bool, sign: float, atol: float, rtol: float, t_span, return_all: bool,
                   y0: Tensor, y1: Tensor, k: Tensor, out: Optional[Tensor], t_out: Optional[Tensor], out_cap: int, ws: Tensor,
                   status: Tensor, trace: Optional[Tensor], rows: int, max_steps: int, comm=None):
         """Whole odeint call in one cooperative kernel (tdyn_mlp_solve); results are read from `status` by the caller."""
         global _launches
         with _Timed("mlp_solve", 0.0):
             rc = self.lib.tdyn_mlp_solve(C.byref(desc), C.byref(plan), int(adjoint), float(sign), float(atol), float(rtol),
-                                         t_span.data_ptr(), t_span.numel(), int(return_all), y0.data_ptr(), y1.data_ptr(),
+                                         t_span.ctypes.data, t_span.size, int(return_all), y0.data_ptr(), y1.data_ptr(),
                                          k.data_ptr(), _ptr(out), _ptr(t_out), int(out_cap), ws.data_ptr(), status.data_ptr(),
                                          _ptr(trace), 0 if trace is None else trace.numel(), int(rows), int(max_steps),
                                          None if comm is None else C.byref(comm), self._stream())

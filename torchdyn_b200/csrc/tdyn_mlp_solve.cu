@@ -903,8 +903,8 @@ extern "C" {
 int64_t tdyn_mlp_solve_workspace_bytes(const tdyn_mlp_t* m) {
     ffma::Net net;
     if (!m || ffma::make_net(m, net, "tdyn_mlp_solve_workspace_bytes") != 0) return 0;
-    // barrier (256 B) | partials 3 x 1024 doubles | mu partials 2 x grid x P floats
-    return (int64_t)(256 + 3 * 1024 * sizeof(double) + sizeof(float) * 2 * (size_t)1024 * net.n_params);
+    // barrier (256 B) | partials 3 x 1024 doubles | mu partials 2 x grid x P floats | t_span copy (4 KB)
+    return (int64_t)(256 + 3 * 1024 * sizeof(double) + sizeof(float) * 2 * (size_t)1024 * net.n_params + 4096);
 }
 
 int64_t tdyn_comm_buffer_bytes(void) {
@@ -929,7 +929,7 @@ int tdyn_mlp_solve(const tdyn_mlp_t* m, const tdyn_rk_plan_t* plan, int adjoint,
     if (int rc = ffma::make_net(m, A.net, "tdyn_mlp_solve")) return rc;
     TDYN_REQUIRE(tdyn_mlp_solve_supported(m, adjoint), "tdyn_mlp_solve: network not supported (shared memory)");
     TDYN_REQUIRE(plan && t_span && y0 && y1 && k && workspace && status, "tdyn_mlp_solve: null argument");
-    TDYN_REQUIRE(n_t >= 2 && rows > 0, "tdyn_mlp_solve: need n_t >= 2 and rows > 0");
+    TDYN_REQUIRE(n_t >= 2 && n_t <= 1024 && rows > 0, "tdyn_mlp_solve: need 2 <= n_t <= 1024 and rows > 0");
     TDYN_REQUIRE(plan->n_extra >= 0 && plan->n_extra <= solve::kMaxExtra && plan->n_sol >= 1 && plan->n_sol <= TDYN_MAX_STAGES &&
                  plan->n_err >= 0 && plan->n_err <= TDYN_MAX_STAGES, "tdyn_mlp_solve: bad plan");
     solve::Plan& pl = A.plan;
@@ -942,7 +942,7 @@ int tdyn_mlp_solve(const tdyn_mlp_t* m, const tdyn_rk_plan_t* plan, int adjoint,
     for (int j = 0; j < TDYN_MAX_STAGES; ++j) { pl.bsol[j] = plan->bsol[j]; pl.berr[j] = plan->berr[j]; }
     pl.safety = plan->safety; pl.min_factor = plan->min_factor; pl.max_factor = plan->max_factor;
     A.adjoint = adjoint ? 1 : 0; A.sign = sign; A.atol = atol; A.rtol = rtol;
-    A.t_span = t_span; A.n_t = n_t; A.return_all = return_all;
+    A.n_t = n_t; A.return_all = return_all;
     const int64_t n = rows * A.net.dims[0];
     const int64_t stride = (adjoint ? 2 : 1) * n;
     A.Y[0] = y0; A.Y[1] = y1;
@@ -952,6 +952,8 @@ int tdyn_mlp_solve(const tdyn_mlp_t* m, const tdyn_rk_plan_t* plan, int adjoint,
     A.barrier = (unsigned int*)ws;
     A.partials = (double*)(ws + 256);
     A.mu_partial = (float*)(ws + 256 + 3 * 1024 * sizeof(double));
+    float* t_dev = (float*)(ws + 256 + 3 * 1024 * sizeof(double) + sizeof(float) * 2 * (size_t)1024 * A.net.n_params);
+    A.t_span = t_dev;                      // `t_span` is a HOST array: staged into the workspace below
     A.status = status; A.trace = trace; A.trace_cap = trace ? trace_cap : 0;
     A.rows = rows; A.max_steps = max_steps;
     A.world = 1; A.rank = 0; A.epoch = 0;
@@ -988,6 +990,7 @@ int tdyn_mlp_solve(const tdyn_mlp_t* m, const tdyn_rk_plan_t* plan, int adjoint,
     cudaStream_t st = (cudaStream_t)stream;
     TDYN_CHECK_CUDA(cudaMemsetAsync(ws, 0, 256, st));          // barrier counter
     TDYN_CHECK_CUDA(cudaMemsetAsync(A.gtot, 0, 4 * sizeof(double), st));
+    TDYN_CHECK_CUDA(cudaMemcpyAsync(t_dev, t_span, sizeof(float) * (size_t)n_t, cudaMemcpyHostToDevice, st));
     void* args[] = {(void*)&A};
     TDYN_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(solve::kThreads), args, smem, st));
     return 0;

@@ -118,6 +118,17 @@ class FusedMLP:
         """True if the narrow-net FFMA kernels can run this net."""
         return self._refresh(kern) and self._ffma_ok
 
+    def scratch(self, key, make):
+        """Per-network cache of solver scratch buffers (stage storage, ping-pong state, status, trace): they are
+        consumed within the call, so they can be reused by the next one (stream-ordered)."""
+        cache = self.__dict__.setdefault("_scratch", {})
+        buf = cache.get(key)
+        if buf is None:
+            if len(cache) > 8:
+                cache.clear()
+            buf = cache[key] = make()
+        return buf
+
     def solve_workspace(self, kern):
         if getattr(self, "_solve_ws", None) is None or self._solve_ws.device != kern.device:
             self._solve_ws = kern.mlp_solve_workspace(self._desc)
@@ -212,6 +223,23 @@ def wrap(f, x):
     return FusedField(f, fm, counters, kern)
 
 
+def eval_field(vf, t, x):
+    """``vf(t, x)`` for the adjoint's boundary terms (sensitivity.py:53, :88): the FFMA kernel when ``vf`` is a
+    fusable MLP (one launch, NFE counted as the wrappers would), the module itself otherwise."""
+    if not DISABLED and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 \
+            and x.is_contiguous():
+        got = _get_fused(vf)
+        if got is not None:
+            fm, counters = got
+            kern = _kernels.get(x)
+            if getattr(kern, "is_cuda", False) and x.shape[1] == fm.dims[0] and fm.ready_ffma(kern):
+                out = kern.mlp_ffma_forward(fm._desc, x, torch.empty_like(x), 1.0, fm.flops_per_row)
+                for c in counters:
+                    c.nfe += 1
+                return out
+    return vf(t, x)
+
+
 class FusedAdjoint:
     """Kernel-backed body of the adjoint dynamics for a fusable MLP: forward + VJP + batch-reduced parameter gradient
     in one launch (``tdyn_mlp_ffma_adjoint``)."""
@@ -256,6 +284,9 @@ MAX_STEPS = 4000
 
 def _rk_plan(solver) -> "_lib.RkPlan":
     p = solver.plan()
+    cached = solver.__dict__.get("_tdyn_rk_plan")
+    if cached is not None and cached[0] is p:
+        return cached[1]
     rp = _lib.RkPlan()
     rp.n_extra = len(p.stages)
     for s, st in enumerate(p.stages):
@@ -270,6 +301,7 @@ def _rk_plan(solver) -> "_lib.RkPlan":
         rp.berr[j] = v
     rp.order = solver.order
     rp.safety, rp.min_factor, rp.max_factor = solver.controller_constants()
+    solver.__dict__["_tdyn_rk_plan"] = (p, rp)
     return rp
 
 
@@ -315,14 +347,14 @@ def try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, s
     n_t = len(ts)
     cap = n_t + (512 if return_all_eval else 0)
     dev = x.device
-    y0, y1 = x.clone(), torch.empty_like(x)
-    k = torch.empty(7 * rows * D, dtype=torch.float32, device=dev)
-    out = torch.empty(cap, rows, D, dtype=torch.float32, device=dev)
+    y0 = x.clone()
+    y1, k, status, trace = fm.scratch(("fwd", rows, dev.index), lambda: (
+        torch.empty_like(x), torch.empty(7 * rows * D, dtype=torch.float32, device=dev),
+        torch.zeros(8, dtype=torch.int32, device=dev), torch.empty(TRACE_CAP, dtype=torch.float32, device=dev)))
+    out = torch.empty(cap, rows, D, dtype=torch.float32, device=dev)       # returned to the caller: always fresh
     t_out = torch.empty(cap, dtype=torch.float32, device=dev)
-    status = torch.zeros(8, dtype=torch.int32, device=dev)
-    trace = torch.empty(TRACE_CAP, dtype=torch.float32, device=dev)
-    t_dev = torch.from_numpy(np.ascontiguousarray(ts, dtype=np.float32)).to(dev)
-    kern.mlp_solve(fm._desc, _rk_plan(solver), False, sign, atol, rtol, t_dev, return_all_eval, y0, y1, k, out, t_out, cap,
+    t_host = np.ascontiguousarray(ts, dtype=np.float32)
+    kern.mlp_solve(fm._desc, _rk_plan(solver), False, sign, atol, rtol, t_host, return_all_eval, y0, y1, k, out, t_out, cap,
                    fm.solve_workspace(kern), status, trace, rows, MAX_STEPS, comm)
     st = status.cpu().tolist()
     n_out, n_attempt, nfe, err = st[0], st[1], st[3], st[4]
@@ -357,12 +389,13 @@ def try_adjoint_interval(dyn, A, t_from, t_to, solver, atol, rtol):
             return None
     rows, D = dyn.x_shape
     dev = A.device
-    y0, y1 = A.clone(), torch.empty_like(A)
-    k = torch.empty(7 * 2 * rows * D, dtype=torch.float32, device=dev)
-    status = torch.zeros(8, dtype=torch.int32, device=dev)
-    trace = torch.empty(TRACE_CAP, dtype=torch.float32, device=dev)
-    t_dev = torch.tensor([-float(t_from), -float(t_to)], dtype=torch.float32).to(dev)     # negated span (odeint.py:54-58)
-    kern.mlp_solve(fm._desc, _rk_plan(solver), True, -1.0, atol, rtol, t_dev, False, y0, y1, k, None, None, 0,
+    y0 = A.clone()                           # the result is returned in y0 or y1: both fresh per call
+    y1 = torch.empty_like(A)
+    k, status, trace = fm.scratch(("adj", rows, dev.index), lambda: (
+        torch.empty(7 * 2 * rows * D, dtype=torch.float32, device=dev), torch.zeros(8, dtype=torch.int32, device=dev),
+        torch.empty(TRACE_CAP, dtype=torch.float32, device=dev)))
+    t_host = np.array([-float(t_from), -float(t_to)], dtype=np.float32)     # negated span (odeint.py:54-58)
+    kern.mlp_solve(fm._desc, _rk_plan(solver), True, -1.0, atol, rtol, t_host, False, y0, y1, k, None, None, 0,
                    fm.solve_workspace(kern), status, trace, rows, MAX_STEPS, comm)
     st = status.cpu().tolist()
     if st[4] != 0:

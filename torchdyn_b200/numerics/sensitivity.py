@@ -143,14 +143,14 @@ def _gather_odefunc_adjoint(vf, vf_params, solver, atol, rtol, interpolator, sol
             P = _flat(vf).numel()
             xT, lamT = sol[-1], g_sol[-1]
             n = xT.numel()
+            from .. import fused
             lam_flat = lamT.flatten()
-            lam_t = lam_flat @ vf(t_sol[-1], xT).flatten()                                   # :53
+            lam_t = lam_flat @ fused.eval_field(vf, t_sol[-1], xT).flatten()                 # :53
             A = torch.cat([xT.flatten(), lam_flat, torch.zeros(P, dtype=xT.dtype, device=xT.device), lam_t[None]])
             dyn = BacksolveDynamics(vf, xT.shape, lamT.shape, P, integral_loss, device=xT.device)
 
             dLdt = torch.zeros(len(th)).to(xT)
             dLdt[-1] = lam_t
-            from .. import fused
             for i in range(len(th) - 1, 0, -1):
                 last = fused.try_adjoint_interval(dyn, A, th[i], th[i - 1], solver_adjoint, atol_adjoint, rtol_adjoint)
                 if last is None:
@@ -158,7 +158,7 @@ def _gather_odefunc_adjoint(vf, vf_params, solver, atol, rtol, interpolator, sol
                                    atol=atol_adjoint, rtol=rtol_adjoint, seminorm=(True, 2 * n))
                     last = As[-1]
                 xt = last[:n].reshape(xT.shape)
-                dLdt[i - 1] = last[n:2 * n] @ vf(t_sol[i], xt).flatten()                     # index i: reference quirk (:88)
+                dLdt[i - 1] = last[n:2 * n] @ fused.eval_field(vf, t_sol[i], xt.contiguous()).flatten()   # index i: reference quirk (:88)
                 lt = last[-1:] - g_t[i - 1]
                 A = torch.cat([last[:n], last[n:2 * n] + g_sol[i - 1].flatten(), last[-P - 1:-1], lt])
             lam = A[n:2 * n].reshape(lamT.shape)
