@@ -64,7 +64,7 @@ def test_rk_combine_misaligned_and_no_x():
     coefs = [0.5, 0.25, -1.5]
     want = cpu.combine(torch.empty(n), x.cpu(), [k.cpu() for k in ks], coefs, MODE_CHAIN, 0.1)
     kern = _kernels.get(x)
-    got = kern.combine(torch.empty(n, device=DEV), x.contiguous() if False else x, ks, coefs, MODE_CHAIN, 0.1)
+    got = kern.combine(torch.empty(n, device=DEV), x, ks, coefs, MODE_CHAIN, 0.1)
     assert torch.equal(got.cpu(), want)
     want2 = cpu.combine(torch.empty(n), None, [k.cpu() for k in ks], coefs, MODE_INNER, 0.1)   # err = dt*(...)
     got2 = kern.combine(torch.empty(n, device=DEV), None, ks, coefs, MODE_INNER, 0.1)
@@ -401,7 +401,6 @@ def test_persistent_solver_matches_host_loop():
             fused.PERSISTENT = True
             om.TRACE_SINK = None
     (ta, sa, tra), (tb, sb, trb) = res[True], res[False]
-    assert "persistent" in fused.last_used() or True
     assert len(tra["t"]) == len(trb["t"]) and tra["accept"] == trb["accept"]
     np.testing.assert_allclose(tra["t"], trb["t"], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(tra["dt"], trb["dt"], rtol=1e-4, atol=1e-7)

@@ -13,7 +13,6 @@
 // Adjoint: mu never feeds back into the dynamics and is excluded from the error norm by the reference's seminorm, so
 // each CTA integrates ITS batch-partial of mu locally (accepted steps only) and the partials are summed across CTAs
 // in a fixed order once at the end; the full-batch d(mu) is only formed for the two init_step norms.
-#include <cooperative_groups.h>
 #include "tdyn_mlp_ffma.cuh"
 
 namespace tdyn {
@@ -134,8 +133,6 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
     float* g_step = g_kl + net.n_params;
     float* mu_acc = g_step + net.n_params;
     __shared__ double red_sm[kThreads / 32];
-    __shared__ float ctl_f[4];
-    __shared__ int ctl_i[4];
 
     ffma::load_weights(net, w_s);
     const int D = net.dims[0];
@@ -255,7 +252,6 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
     // leaving the kernel and without a host round trip.
     __shared__ double tot_sm[3];
     unsigned int xseq = 0;
-    bool comm_timeout = false;
     auto grid_sum = [&](double v0, double v1, double v2, int nv) {
         const double s0 = block_sum(v0, red_sm);
         const double s1 = nv > 1 ? block_sum(v1, red_sm) : 0.0;
