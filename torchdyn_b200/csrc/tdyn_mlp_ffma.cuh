@@ -8,6 +8,8 @@ namespace ffma {
 constexpr int kThreads = 256;
 constexpr int kRows = 16;            // rows per tile
 constexpr int kRG = kRows / 4;       // row groups of 4
+constexpr int kLd = kRows + 4;       // row stride of the feature-major tiles: 80 B, so that 8 lanes reading consecutive
+                                     // features with LDS.128 touch 8 distinct 16-byte bank groups (64 B would be 4-way conflicted)
 constexpr int kMaxWidth = 128;
 constexpr int kMaxGrid = 148 * 2;
 
@@ -20,7 +22,7 @@ struct Net {
     int w_off[TDYN_MAX_LAYERS];      // float offsets into the shared weight area ([N][K+1])
     int b_off[TDYN_MAX_LAYERS];
     int p_off[TDYN_MAX_LAYERS];      // float offsets of layer l's (weight, bias) block in the flat parameter vector
-    int h_off[TDYN_MAX_LAYERS + 1];  // float offsets of h_l ([dims[l]][kRows]) in the activation area
+    int h_off[TDYN_MAX_LAYERS + 1];  // float offsets of h_l ([dims[l]][kLd]) in the activation area
     int n_params, w_floats, h_floats, maxdim;
 };
 
@@ -51,14 +53,14 @@ __device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ 
     for (int i = threadIdx.x; i < kRows * D; i += kThreads) {
         const int r = i / D, d = i % D;
         const int64_t gr = row0 + r;
-        dst[d * kRows + r] = gr < rows ? scale * __ldg(src + gr * D + d) : 0.f;
+        dst[d * kLd + r] = gr < rows ? scale * __ldg(src + gr * D + d) : 0.f;
     }
 }
 __device__ __forceinline__ void store_tile(float* __restrict__ dst, const float* src, int D, int64_t row0, int64_t rows, float sign) {
     for (int i = threadIdx.x; i < kRows * D; i += kThreads) {
         const int r = i / D, d = i % D;
         const int64_t gr = row0 + r;
-        if (gr < rows) dst[gr * D + d] = sign * src[d * kRows + r];
+        if (gr < rows) dst[gr * D + d] = sign * src[d * kLd + r];
     }
 }
 
@@ -77,15 +79,87 @@ __device__ __forceinline__ void forward_tile(const Net& net, const float* w_s, f
             float4 acc = make_float4(bias, bias, bias, bias);
             for (int k = 0; k < K; ++k) {
                 const float w = wr[k];
-                const float4 hv = *reinterpret_cast<const float4*>(hin + k * kRows + 4 * g);
+                const float4 hv = *reinterpret_cast<const float4*>(hin + k * kLd + 4 * g);
                 acc.x = fmaf(w, hv.x, acc.x); acc.y = fmaf(w, hv.y, acc.y);
                 acc.z = fmaf(w, hv.z, acc.z); acc.w = fmaf(w, hv.w, acc.w);
             }
             if (!last) { acc.x = act_fwd<ACT>(acc.x); acc.y = act_fwd<ACT>(acc.y); acc.z = act_fwd<ACT>(acc.z); acc.w = act_fwd<ACT>(acc.w); }
-            *reinterpret_cast<float4*>(hout + n * kRows + 4 * g) = acc;
+            *reinterpret_cast<float4*>(hout + n * kLd + 4 * g) = acc;
         }
         __syncthreads();
     }
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float s) {
+    s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); return fmaf(a.w, b.w, s);
+}
+
+// VJP of the tile whose activations h_l are in h_s and whose output cotangent delta_L is in dcur ([dims[L]][kLd]):
+// for every layer, the tile's parameter-gradient contribution (weight [N][K] then bias [N], flat index p_off[l] + ...)
+// is handed to `gacc(flat_index, value)` (each index is produced by exactly one thread), and delta is pulled back
+// through W_l and the activation derivative.  Returns the buffer holding delta_0 = (delta_L)^T df/dx.
+// wgrad mapping: a thread owns 4 consecutive neurons x 1 input feature, lanes run over the input feature -- the
+// h loads are conflict-free (stride kLd), the delta loads are warp broadcasts: 5 LDS.128 per 16 FFMA per row group.
+template <int ACT, class GAcc>
+__device__ __forceinline__ float* backward_tile(const Net& net, const float* w_s, const float* h_s, float* dcur, float* dnxt,
+                                                GAcc&& gacc) {
+    for (int l = net.L - 1; l >= 0; --l) {
+        const int K = net.dims[l], N = net.dims[l + 1];
+        const float* hin = h_s + net.h_off[l];
+        const int po = net.p_off[l];
+        if ((N & 3) == 0) {
+            for (int i = threadIdx.x; i < (N >> 2) * K; i += kThreads) {
+                const int nb = i / K, k = i - nb * K;
+                const float* d0 = dcur + (4 * nb) * kLd;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int q = 0; q < kRG; ++q) {
+                    const float4 hv = *reinterpret_cast<const float4*>(hin + k * kLd + 4 * q);
+                    s0 = dot4(*reinterpret_cast<const float4*>(d0 + 4 * q), hv, s0);
+                    s1 = dot4(*reinterpret_cast<const float4*>(d0 + kLd + 4 * q), hv, s1);
+                    s2 = dot4(*reinterpret_cast<const float4*>(d0 + 2 * kLd + 4 * q), hv, s2);
+                    s3 = dot4(*reinterpret_cast<const float4*>(d0 + 3 * kLd + 4 * q), hv, s3);
+                }
+                const int base = po + (4 * nb) * K + k;
+                gacc(base, s0); gacc(base + K, s1); gacc(base + 2 * K, s2); gacc(base + 3 * K, s3);
+            }
+        } else {
+            for (int i = threadIdx.x; i < N * K; i += kThreads) {
+                const int nn = i / K, k = i - nn * K;
+                float s = 0.f;
+#pragma unroll
+                for (int q = 0; q < kRG; ++q)
+                    s = dot4(*reinterpret_cast<const float4*>(dcur + nn * kLd + 4 * q), *reinterpret_cast<const float4*>(hin + k * kLd + 4 * q), s);
+                gacc(po + i, s);
+            }
+        }
+        for (int nn = threadIdx.x; nn < N; nn += kThreads) {
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) s += dcur[nn * kLd + r];
+            gacc(po + N * K + nn, s);
+        }
+        // dgrad: delta_prev[k][r] = (sum_n delta[n][r] * W[n][k]) * act'(h_l[k][r])   (no act' into the input layer)
+        for (int i = threadIdx.x; i < kRG * K; i += kThreads) {
+            const int g = i / K, k = i - g * K;
+            const float* wc = w_s + net.w_off[l] + k;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int nn = 0; nn < N; ++nn) {
+                const float w = wc[nn * (K + 1)];
+                const float4 dv = *reinterpret_cast<const float4*>(dcur + nn * kLd + 4 * g);
+                acc.x = fmaf(w, dv.x, acc.x); acc.y = fmaf(w, dv.y, acc.y);
+                acc.z = fmaf(w, dv.z, acc.z); acc.w = fmaf(w, dv.w, acc.w);
+            }
+            if (l > 0) {
+                const float4 hv = *reinterpret_cast<const float4*>(hin + k * kLd + 4 * g);
+                acc.x *= act_bwd<ACT>(hv.x); acc.y *= act_bwd<ACT>(hv.y); acc.z *= act_bwd<ACT>(hv.z); acc.w *= act_bwd<ACT>(hv.w);
+            }
+            *reinterpret_cast<float4*>(dnxt + k * kLd + 4 * g) = acc;
+        }
+        __syncthreads();
+        float* tmp = dcur; dcur = dnxt; dnxt = tmp;
+    }
+    return dcur;
 }
 
 template <int ACT>
@@ -119,8 +193,8 @@ __global__ void __launch_bounds__(kThreads) mlp_adjoint_kernel(const Net net, co
     extern __shared__ __align__(16) float sm[];
     float* w_s = sm;
     float* h_s = w_s + net.w_floats;
-    float* d_s = h_s + net.h_floats;                 // two delta buffers [maxdim][kRows]
-    float* g_s = d_s + 2 * net.maxdim * kRows;       // parameter-gradient accumulator [n_params]
+    float* d_s = h_s + net.h_floats;                 // two delta buffers [maxdim][kLd]
+    float* g_s = d_s + 2 * net.maxdim * kLd;         // parameter-gradient accumulator [n_params]
     __shared__ bool is_last;
     load_weights(net, w_s);
     for (int i = threadIdx.x; i < net.n_params; i += kThreads) g_s[i] = 0.f;
@@ -133,51 +207,8 @@ __global__ void __launch_bounds__(kThreads) mlp_adjoint_kernel(const Net net, co
         __syncthreads();
         forward_tile<ACT>(net, w_s, h_s);
         store_tile(dx, h_s + net.h_off[net.L], D, t * kRows, rows, sign);
-        float* dcur = d_s;
-        float* dnxt = d_s + net.maxdim * kRows;
-        for (int l = net.L - 1; l >= 0; --l) {
-            const int K = net.dims[l], N = net.dims[l + 1];
-            const float* hin = h_s + net.h_off[l];
-            // wgrad: dW[n][k] += sum_r delta[n][r] * h_l[k][r];  db[n] += sum_r delta[n][r]
-            float* gw = g_s + net.p_off[l];
-            for (int i = threadIdx.x; i < N * K; i += kThreads) {
-                const int n = i / K, k = i % K;
-                float s = 0.f;
-#pragma unroll
-                for (int q = 0; q < kRG; ++q) {
-                    const float4 dv = *reinterpret_cast<const float4*>(dcur + n * kRows + 4 * q);
-                    const float4 hv = *reinterpret_cast<const float4*>(hin + k * kRows + 4 * q);
-                    s = fmaf(dv.x, hv.x, s); s = fmaf(dv.y, hv.y, s); s = fmaf(dv.z, hv.z, s); s = fmaf(dv.w, hv.w, s);
-                }
-                gw[i] += s;
-            }
-            for (int n = threadIdx.x; n < N; n += kThreads) {
-                float s = 0.f;
-#pragma unroll
-                for (int r = 0; r < kRows; ++r) s += dcur[n * kRows + r];
-                gw[N * K + n] += s;
-            }
-            // dgrad: delta_prev[k][r] = (sum_n delta[n][r] * W[n][k]) * act'(h_l[k][r])   (no act' into the input layer)
-            for (int i = threadIdx.x; i < kRG * K; i += kThreads) {
-                const int g = i / K, k = i % K;
-                const float* wc = w_s + net.w_off[l] + k;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int n = 0; n < N; ++n) {
-                    const float w = wc[n * (K + 1)];
-                    const float4 dv = *reinterpret_cast<const float4*>(dcur + n * kRows + 4 * g);
-                    acc.x = fmaf(w, dv.x, acc.x); acc.y = fmaf(w, dv.y, acc.y);
-                    acc.z = fmaf(w, dv.z, acc.z); acc.w = fmaf(w, dv.w, acc.w);
-                }
-                if (l > 0) {
-                    const float4 hv = *reinterpret_cast<const float4*>(hin + k * kRows + 4 * g);
-                    acc.x *= act_bwd<ACT>(hv.x); acc.y *= act_bwd<ACT>(hv.y); acc.z *= act_bwd<ACT>(hv.z); acc.w *= act_bwd<ACT>(hv.w);
-                }
-                *reinterpret_cast<float4*>(dnxt + k * kRows + 4 * g) = acc;
-            }
-            __syncthreads();
-            float* tmp = dcur; dcur = dnxt; dnxt = tmp;
-        }
-        store_tile(dlam, dcur, D, t * kRows, rows, sign);
+        float* dfin = backward_tile<ACT>(net, w_s, h_s, d_s, d_s + net.maxdim * kLd, [&](int idx, float v) { g_s[idx] += v; });
+        store_tile(dlam, dfin, D, t * kRows, rows, sign);
     }
     // ---- deterministic cross-CTA reduction of the parameter gradient
     __syncthreads();
@@ -209,7 +240,7 @@ inline int make_net(const tdyn_mlp_t* m, Net& net, const char* who) {
         net.dims[l] = m->dims[l];
         TDYN_REQUIRE(net.dims[l] >= 1 && net.dims[l] <= kMaxWidth, "%s: width %d outside 1..%d", who, net.dims[l], kMaxWidth);
         net.h_off[l] = hoff;
-        hoff += net.dims[l] * kRows;
+        hoff += net.dims[l] * kLd;
         if (net.dims[l] > maxdim) maxdim = net.dims[l];
     }
     TDYN_REQUIRE(net.dims[0] == net.dims[net.L], "%s: not an autonomous vector field (in %d != out %d)", who, net.dims[0], net.dims[net.L]);
@@ -229,7 +260,7 @@ inline int make_net(const tdyn_mlp_t* m, Net& net, const char* who) {
 }
 
 inline size_t fwd_smem(const Net& n) { return sizeof(float) * (size_t)(n.w_floats + n.h_floats); }
-inline size_t adj_smem(const Net& n) { return sizeof(float) * (size_t)(n.w_floats + n.h_floats + 2 * n.maxdim * kRows + n.n_params); }
+inline size_t adj_smem(const Net& n) { return sizeof(float) * (size_t)(n.w_floats + n.h_floats + 2 * n.maxdim * kLd + n.n_params); }
 constexpr size_t kSmemLimit = 220 * 1024;
 
 }  // namespace ffma

@@ -21,6 +21,7 @@ namespace solve {
 using ffma::Net;
 using ffma::kRows;
 using ffma::kRG;
+using ffma::kLd;
 constexpr int kThreads = ffma::kThreads;
 constexpr int kMaxExtra = 6;
 
@@ -127,8 +128,8 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
     const Plan& pl = A.plan;
     float* w_s = sm;
     float* h_s = w_s + net.w_floats;
-    float* d_s = h_s + net.h_floats;                                   // adjoint only: 2 x [maxdim][kRows]
-    float* g_k1 = d_s + (A.adjoint ? 2 * net.maxdim * kRows : 0);      // adjoint only: 4 x [P]
+    float* d_s = h_s + net.h_floats;                                   // adjoint only: 2 x [maxdim][kLd]
+    float* g_k1 = d_s + (A.adjoint ? 2 * net.maxdim * kLd : 0);        // adjoint only: 4 x [P]
     float* g_kl = g_k1 + net.n_params;
     float* g_step = g_kl + net.n_params;
     float* mu_acc = g_step + net.n_params;
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
             for (int i = threadIdx.x; i < kRows * D; i += kThreads) {
                 const int r = i / D, d = i % D;
                 const int64_t gr = row0 + r;
-                h_s[net.h_off[0] + d * kRows + r] = gr < A.rows ? combine_at(y, A.K, kidx, nk, mode, coef, dt, gr * D + d) : 0.f;
+                h_s[net.h_off[0] + d * kLd + r] = gr < A.rows ? combine_at(y, A.K, kidx, nk, mode, coef, dt, gr * D + d) : 0.f;
             }
             if (A.adjoint) {
                 // lam block of the stage input: K buffers hold [x-block | lam-block], so offset every pointer by n
@@ -189,57 +190,16 @@ __global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
                         const int64_t e = n + gr * D + d;
                         lv = -combine_at(y, A.K, kidx, nk, mode, coef, dt, e);
                     }
-                    d_s[d * kRows + r] = lv;      // delta_L = -lam
+                    d_s[d * kLd + r] = lv;        // delta_L = -lam
                 }
             }
             __syncthreads();
             ffma::forward_tile<ACT>(net, w_s, h_s);
             ffma::store_tile(kout, h_s + net.h_off[net.L], D, row0, A.rows, A.sign);
             if (A.adjoint) {
-                float* dcur = d_s;
-                float* dnxt = d_s + net.maxdim * kRows;
-                for (int l = net.L - 1; l >= 0; --l) {
-                    const int K = net.dims[l], N = net.dims[l + 1];
-                    const float* hin = h_s + net.h_off[l];
-                    float* gw = gdst + net.p_off[l];
-                    for (int i = threadIdx.x; i < N * K; i += kThreads) {
-                        const int nn = i / K, k = i % K;
-                        float s = 0.f;
-#pragma unroll
-                        for (int q = 0; q < kRG; ++q) {
-                            const float4 dv = *reinterpret_cast<const float4*>(dcur + nn * kRows + 4 * q);
-                            const float4 hv = *reinterpret_cast<const float4*>(hin + k * kRows + 4 * q);
-                            s = fmaf(dv.x, hv.x, s); s = fmaf(dv.y, hv.y, s); s = fmaf(dv.z, hv.z, s); s = fmaf(dv.w, hv.w, s);
-                        }
-                        gw[i] = fmaf(gweight, s, gw[i]);
-                    }
-                    for (int nn = threadIdx.x; nn < N; nn += kThreads) {
-                        float s = 0.f;
-#pragma unroll
-                        for (int r = 0; r < kRows; ++r) s += dcur[nn * kRows + r];
-                        gw[N * K + nn] = fmaf(gweight, s, gw[N * K + nn]);
-                    }
-                    for (int i = threadIdx.x; i < kRG * K; i += kThreads) {
-                        const int g = i / K, k = i % K;
-                        const float* wc = w_s + net.w_off[l] + k;
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int nn = 0; nn < N; ++nn) {
-                            const float w = wc[nn * (K + 1)];
-                            const float4 dv = *reinterpret_cast<const float4*>(dcur + nn * kRows + 4 * g);
-                            acc.x = fmaf(w, dv.x, acc.x); acc.y = fmaf(w, dv.y, acc.y);
-                            acc.z = fmaf(w, dv.z, acc.z); acc.w = fmaf(w, dv.w, acc.w);
-                        }
-                        if (l > 0) {
-                            const float4 hv = *reinterpret_cast<const float4*>(hin + k * kRows + 4 * g);
-                            acc.x *= ffma::act_bwd<ACT>(hv.x); acc.y *= ffma::act_bwd<ACT>(hv.y);
-                            acc.z *= ffma::act_bwd<ACT>(hv.z); acc.w *= ffma::act_bwd<ACT>(hv.w);
-                        }
-                        *reinterpret_cast<float4*>(dnxt + k * kRows + 4 * g) = acc;
-                    }
-                    __syncthreads();
-                    float* tmp = dcur; dcur = dnxt; dnxt = tmp;
-                }
-                ffma::store_tile(kout + n, dcur, D, row0, A.rows, A.sign);
+                float* dfin = ffma::backward_tile<ACT>(net, w_s, h_s, d_s, d_s + net.maxdim * kLd,
+                                                       [&](int idx, float v) { gdst[idx] = fmaf(gweight, v, gdst[idx]); });
+                ffma::store_tile(kout + n, dfin, D, row0, A.rows, A.sign);
             }
         }
         __syncthreads();
@@ -610,7 +570,7 @@ __global__ void __launch_bounds__(kThreads) interp_adjoint_kernel(const InterpAr
     float* w_s = sm;
     float* h_s = w_s + net.w_floats;
     float* d_s = h_s + net.h_floats;
-    float* g_k1 = d_s + 2 * net.maxdim * kRows;        // d(mu) batch-partial of the current k1 (raw: delta_L = -lam)
+    float* g_k1 = d_s + 2 * net.maxdim * kLd;          // d(mu) batch-partial of the current k1 (raw: delta_L = -lam)
     float* g_kl = g_k1 + net.n_params;                 // ... of the last stage (next step's k1 under FSAL)
     float* s_b = g_kl + net.n_params;                  // sum_j>=1 bsol_j * dmu_j partial
     float* s_e = s_b + net.n_params;                   // sum_j>=1 berr_j * dmu_j partial
@@ -672,56 +632,16 @@ __global__ void __launch_bounds__(kThreads) interp_adjoint_kernel(const InterpAr
                     xv = add_rn(__ldg(pa + e), mul_rn(inner, sfrac));
                     lv = -combine_at(y, A.K, kidx, nk, mode, coef, dt, e);
                 }
-                h_s[net.h_off[0] + d * kRows + r] = xv;
-                d_s[d * kRows + r] = lv;                  // delta_L = -lam
+                h_s[net.h_off[0] + d * kLd + r] = xv;
+                d_s[d * kLd + r] = lv;                    // delta_L = -lam
             }
             __syncthreads();
             ffma::forward_tile<ACT>(net, w_s, h_s);
-            float* dcur = d_s;
-            float* dnxt = d_s + net.maxdim * kRows;
-            for (int l = net.L - 1; l >= 0; --l) {
-                const int K = net.dims[l], N = net.dims[l + 1];
-                const float* hin = h_s + net.h_off[l];
-                const int po = net.p_off[l];
-                for (int i = threadIdx.x; i < N * K + N; i += kThreads) {
-                    float sv = 0.f;
-                    if (i < N * K) {
-                        const int nn = i / K, k = i % K;
-#pragma unroll
-                        for (int q = 0; q < kRG; ++q) {
-                            const float4 dv = *reinterpret_cast<const float4*>(dcur + nn * kRows + 4 * q);
-                            const float4 hv = *reinterpret_cast<const float4*>(hin + k * kRows + 4 * q);
-                            sv = fmaf(dv.x, hv.x, sv); sv = fmaf(dv.y, hv.y, sv); sv = fmaf(dv.z, hv.z, sv); sv = fmaf(dv.w, hv.w, sv);
-                        }
-                    } else {
-                        const int nn = i - N * K;
-#pragma unroll
-                        for (int r = 0; r < kRows; ++r) sv += dcur[nn * kRows + r];
-                    }
-                    if (gmode == 3) { s_b[po + i] = fmaf(wb, sv, s_b[po + i]); s_e[po + i] = fmaf(we, sv, s_e[po + i]); }
-                    else gdst[po + i] += sv;
-                }
-                for (int i = threadIdx.x; i < kRG * K; i += kThreads) {
-                    const int g = i / K, k = i % K;
-                    const float* wc = w_s + net.w_off[l] + k;
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int nn = 0; nn < N; ++nn) {
-                        const float w = wc[nn * (K + 1)];
-                        const float4 dv = *reinterpret_cast<const float4*>(dcur + nn * kRows + 4 * g);
-                        acc.x = fmaf(w, dv.x, acc.x); acc.y = fmaf(w, dv.y, acc.y);
-                        acc.z = fmaf(w, dv.z, acc.z); acc.w = fmaf(w, dv.w, acc.w);
-                    }
-                    if (l > 0) {
-                        const float4 hv = *reinterpret_cast<const float4*>(hin + k * kRows + 4 * g);
-                        acc.x *= ffma::act_bwd<ACT>(hv.x); acc.y *= ffma::act_bwd<ACT>(hv.y);
-                        acc.z *= ffma::act_bwd<ACT>(hv.z); acc.w *= ffma::act_bwd<ACT>(hv.w);
-                    }
-                    *reinterpret_cast<float4*>(dnxt + k * kRows + 4 * g) = acc;
-                }
-                __syncthreads();
-                float* tmp = dcur; dcur = dnxt; dnxt = tmp;
-            }
-            ffma::store_tile(kout, dcur, D, row0, A.rows, sign);
+            float* dfin = ffma::backward_tile<ACT>(net, w_s, h_s, d_s, d_s + net.maxdim * kLd, [&](int idx, float v) {
+                if (gmode == 3) { s_b[idx] = fmaf(wb, v, s_b[idx]); s_e[idx] = fmaf(we, v, s_e[idx]); }
+                else gdst[idx] += v;
+            });
+            ffma::store_tile(kout, dfin, D, row0, A.rows, sign);
         }
         __syncthreads();
     };
@@ -913,7 +833,7 @@ int tdyn_mlp_solve_supported(const tdyn_mlp_t* m, int adjoint) {
     if (!m || ffma::make_net(m, net, "tdyn_mlp_solve_supported") != 0) return 0;
     if (!(m->act == TDYN_ACT_TANH || m->act == TDYN_ACT_SOFTPLUS || m->act == TDYN_ACT_RELU)) return 0;
     size_t smem = sizeof(float) * (size_t)(net.w_floats + net.h_floats);
-    if (adjoint) smem += sizeof(float) * (size_t)(2 * net.maxdim * ffma::kRows + 4 * net.n_params);
+    if (adjoint) smem += sizeof(float) * (size_t)(2 * net.maxdim * ffma::kLd + 4 * net.n_params);
     return smem <= ffma::kSmemLimit ? 1 : 0;
 }
 
@@ -968,7 +888,7 @@ int tdyn_mlp_solve(const tdyn_mlp_t* m, const tdyn_rk_plan_t* plan, int adjoint,
     }
 
     size_t smem = sizeof(float) * (size_t)(A.net.w_floats + A.net.h_floats);
-    if (adjoint) smem += sizeof(float) * (size_t)(2 * A.net.maxdim * ffma::kRows + 4 * A.net.n_params);
+    if (adjoint) smem += sizeof(float) * (size_t)(2 * A.net.maxdim * ffma::kLd + 4 * A.net.n_params);
     const void* fn = A.net.act == TDYN_ACT_TANH ? (const void*)solve::ode_solve_kernel<TDYN_ACT_TANH>
                    : A.net.act == TDYN_ACT_SOFTPLUS ? (const void*)solve::ode_solve_kernel<TDYN_ACT_SOFTPLUS>
                                                     : (const void*)solve::ode_solve_kernel<TDYN_ACT_RELU>;
@@ -1021,7 +941,7 @@ int tdyn_mlp_solve_interp(const tdyn_mlp_t* m, const tdyn_rk_plan_t* plan, float
     A.mu_partial = (float*)(ws + 256 + 3 * 1024 * sizeof(double));
     A.status = status; A.trace = trace; A.trace_cap = trace ? trace_cap : 0;
     A.rows = rows; A.max_steps = max_steps;
-    const size_t smem = sizeof(float) * (size_t)(A.net.w_floats + A.net.h_floats + 2 * A.net.maxdim * ffma::kRows + 4 * A.net.n_params);
+    const size_t smem = sizeof(float) * (size_t)(A.net.w_floats + A.net.h_floats + 2 * A.net.maxdim * ffma::kLd + 4 * A.net.n_params);
     const void* fn = A.net.act == TDYN_ACT_TANH ? (const void*)solve::interp_adjoint_kernel<TDYN_ACT_TANH>
                    : A.net.act == TDYN_ACT_SOFTPLUS ? (const void*)solve::interp_adjoint_kernel<TDYN_ACT_SOFTPLUS>
                                                     : (const void*)solve::interp_adjoint_kernel<TDYN_ACT_RELU>;
