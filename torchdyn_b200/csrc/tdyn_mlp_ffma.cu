@@ -8,7 +8,7 @@
 //
 // Narrow nets are latency / issue bound, not tensor-core work (north_star: FFMA below width 256): all weights sit in
 // shared memory ([out][in+1] padded -> conflict-free for both the forward (lanes over out) and the dgrad (lanes over
-// in) access), a CTA walks 16-row tiles, activations are kept feature-major ([feature][16 rows]) so one LDS.128
+// in) access), a CTA walks 32-row tiles, activations are kept feature-major ([feature][32 rows + pad]) so one LDS.128
 // feeds 4 rows, every thread owns (4 rows x 1 neuron).  The parameter-gradient contraction (split-K over the batch)
 // is accumulated per CTA in shared memory and reduced across CTAs in a FIXED order by the last CTA (deterministic).
 #include "tdyn_mlp_ffma.cuh"

@@ -6,10 +6,11 @@ namespace tdyn {
 namespace ffma {
 
 constexpr int kThreads = 256;
-constexpr int kRows = 16;            // rows per tile
+constexpr int kRows = 32;            // rows per tile
 constexpr int kRG = kRows / 4;       // row groups of 4
-constexpr int kLd = kRows + 4;       // row stride of the feature-major tiles: 80 B, so that 8 lanes reading consecutive
-                                     // features with LDS.128 touch 8 distinct 16-byte bank groups (64 B would be 4-way conflicted)
+constexpr int kLd = kRows + 4;       // row stride of the feature-major tiles: 36 floats = 9 x 16 B (odd), so that 8 lanes
+                                     // reading consecutive features with LDS.128 touch 8 distinct 16-byte bank groups
+                                     // (an unpadded stride of 8 x 16 B would be 8-way conflicted)
 constexpr int kMaxWidth = 128;
 constexpr int kMaxGrid = 148 * 2;
 

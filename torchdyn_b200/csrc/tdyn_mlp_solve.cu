@@ -3,7 +3,7 @@
 //   forward  (adjoint = 0): state x [rows, D]                  -- reference numerics/odeint.py:29-91, :326-408, :411-445
 //   backsolve (adjoint = 1): flat A = [x, lam, mu, lam_t]      -- reference numerics/sensitivity.py:55-84 (one interval)
 //
-// Every CTA owns a fixed set of 16-row tiles for the whole solve.  RK stages never cross rows, so they need no
+// Every CTA owns a fixed set of 32-row tiles for the whole solve.  RK stages never cross rows, so they need no
 // grid-wide synchronisation: per stage a CTA forms the stage input of its tiles (reference rounding order), runs the
 // MLP (and, for the adjoint, its VJP) from shared-memory weights and writes k_i.  The only global coupling is the
 // reference's single step controller: per attempted step ONE grid barrier carries the fp64 partial sums of the
