@@ -158,6 +158,33 @@ def test_user_adaptive_solver_module_runs_its_own_step():
     assert MyDopri.calls > 0 and torch.allclose(s1, s2, rtol=1e-6) and torch.equal(t1, t2)
 
 
+def test_hypersolvers_match_the_oracle_formula():
+    """Base step on the kernels + dt**(p+1) * g(t, x) (reference numerics/solvers/hyper.py): against the oracle's base
+    step with the same correction added by hand."""
+    from oracle import erk_oracle as eo
+    from torchdyn_b200.numerics.solvers import HyperEuler, HyperMidpoint, HyperRungeKutta4
+    from torchdyn_b200.numerics import odeint
+    torch.manual_seed(5)
+    f_net = nn.Sequential(nn.Linear(3, 8), nn.Tanh(), nn.Linear(8, 3))
+    g_net = nn.Sequential(nn.Linear(3, 8), nn.Tanh(), nn.Linear(8, 3))
+    f = lambda t, x: f_net(x)       # noqa: E731
+    g = lambda t, x: g_net(x)       # noqa: E731
+    x0 = torch.randn(6, 3)
+    t_span = torch.linspace(0, 1, 6)
+    for cls, name, order in ((HyperEuler, "euler", 1), (HyperMidpoint, "midpoint", 2), (HyperRungeKutta4, "rk4", 4)):
+        with torch.no_grad():
+            _, sol = odeint(f, x0, t_span, cls(g))
+            tab = eo.Tableau(name)
+            x, t, dt = x0, t_span[0], t_span[1] - t_span[0]
+            for i in range(1, len(t_span)):
+                _, xn, _, _ = eo.rk_step(tab, f, x, t, dt)
+                x = xn + dt ** (order + 1) * g(t, x)
+                t = t + dt
+                if i < len(t_span) - 1:
+                    dt = t_span[i + 1] - t
+        assert torch.allclose(sol[-1], x, rtol=1e-6, atol=1e-7), name
+
+
 def test_neuralode_api_surface():
     net = nn.Sequential(nn.Linear(2, 8), nn.Tanh(), nn.Linear(8, 2))
     model = torchdyn_b200.NeuralODE(net, solver="dopri5", sensitivity="adjoint", return_t_eval=False)
