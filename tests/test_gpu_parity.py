@@ -478,3 +478,54 @@ def test_persistent_adjoints_match_host_loop(sens):
     assert_close(gxa, gxb, "dL/dx0", rtol=2e-3, atol_scale=5e-4)
     for i, (a, b) in enumerate(zip(gpa, gpb)):
         assert_close(a, b, f"dL/dtheta[{i}]", rtol=2e-3, atol_scale=5e-4)
+
+
+# ------------------------------------------------------------------------------ size-independent properties at BASELINE sizes
+
+def test_cfg5_size_conv_state_known_answer():
+    """cfg-5-sized 4-D state (4096 x 11 x 28 x 28 = 35.3 M elements) through the generic adaptive kernels on the linear
+    field dx/dt = -x: every element must reach x0*exp(-1) to the solver tolerance, and the controller must accept."""
+    x0 = torch.randn(4096, 11, 28, 28, device=DEV)
+    with torch.no_grad():
+        t_eval, sol = odeint(lambda t, x: -x, x0, torch.linspace(0, 1, 2), "dopri5", atol=1e-6, rtol=1e-6)
+    assert sol.shape == (2, 4096, 11, 28, 28) and torch.equal(t_eval.cpu(), torch.tensor([0.0, 1.0]))
+    assert torch.allclose(sol[-1], x0 * float(np.exp(-1.0)), rtol=1e-5, atol=1e-6)
+
+
+def test_cfg3_size_tsit5_linearity_and_reversibility():
+    """cfg-3-sized state (262144 x 128): (i) linearity -- for f(x) = A x the batch [x0; 2 x0] must give exactly twice the
+    solution on the second half (one global controller, power-of-two scaling is exact in fp32); (ii) integrating forward
+    and then back over the reversed span returns to x0 within the tolerance."""
+    torch.manual_seed(1)
+    A = (torch.randn(128, 128, device=DEV) / 128 ** 0.5) * 0.5
+    x0 = torch.randn(131072, 128, device=DEV)
+    xx = torch.cat([x0, 2 * x0])
+    f = lambda t, x: x @ A.T       # noqa: E731
+    with torch.no_grad():
+        _, fwd = odeint(f, xx, torch.tensor([0.0, 1.0]), "tsit5", atol=1e-6, rtol=1e-6)
+        assert torch.equal(fwd[-1][131072:], 2 * fwd[-1][:131072])
+        t_b, back = odeint(f, fwd[-1], torch.tensor([1.0, 0.0]), "tsit5", atol=1e-6, rtol=1e-6)
+    assert torch.allclose(t_b.cpu(), torch.tensor([-1.0, 0.0]))
+    assert torch.allclose(back[-1], xx, rtol=2e-4, atol=2e-4)
+
+
+def test_cfg2_size_fused_rk4_checksum_matches_generic():
+    """cfg 2 at full size for the full 100 steps on the fused tensor-core path; the generic path on a 4096-row sample of
+    the same rows must agree (rows are independent: a row's trajectory does not depend on the batch it is in)."""
+    from torchdyn_b200 import fused
+    net = _c2_net(0).to(DEV)
+    model = torchdyn_b200.NeuralODE(net, solver="rk4")
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(1 << 20, 32, generator=g).to(DEV)
+    t_span = torch.linspace(0, 1, 101)
+    idx = torch.arange(0, 1 << 20, 256, device=DEV)
+    with torch.no_grad():
+        _, full = model(x, t_span, save_at=t_span[-1:])
+        assert fused.last_used() is not None and model.vf.nfe == 400
+        fused.DISABLED = True
+        try:
+            _, part = model(x[idx].contiguous(), t_span, save_at=t_span[-1:])
+        finally:
+            fused.DISABLED = False
+    assert torch.isfinite(full).all()
+    assert_close(full[0][idx], part[0], "fused (full batch) vs generic (row sample) after 100 rk4 steps", rtol=1e-5, atol_scale=2e-6)
