@@ -529,3 +529,28 @@ def test_cfg2_size_fused_rk4_checksum_matches_generic():
             fused.DISABLED = False
     assert torch.isfinite(full).all()
     assert_close(full[0][idx], part[0], "fused (full batch) vs generic (row sample) after 100 rk4 steps", rtol=1e-5, atol_scale=2e-6)
+
+
+@pytest.mark.parametrize("solver,kw", [("dopri5", dict(atol=1e-4, rtol=1e-4)), ("rk4", {}), ("tsit5", dict(atol=1e-4, rtol=1e-4))])
+def test_sensitivity_autograd_on_gpu_matches_oracle(solver, kw):
+    """sensitivity='autograd' (NeuralODE's default) on the GPU: back-propagation through the differentiable stage
+    combinations against the oracle's autograd on CPU."""
+    torch.manual_seed(7)
+    net_c = build_mlp([3, 16, 3], "tanh")
+    net_g = build_mlp([3, 16, 3], "tanh", [p.detach() for p in net_c.parameters()], DEV)
+    x0 = torch.randn(12, 3)
+    t_span = torch.linspace(0, 1, 4)
+    ora = eo.OracleNeuralODE(net_c, solver=solver, sensitivity="autograd", **kw)
+    xc = x0.clone().requires_grad_(True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, sol_c = ora(xc, t_span)
+        sol_c[-1].pow(2).sum().backward()
+        model = torchdyn_b200.NeuralODE(net_g, solver=solver, sensitivity="autograd", **kw)
+        xg = x0.clone().to(DEV).requires_grad_(True)
+        _, sol_g = model(xg, t_span)
+        sol_g[-1].pow(2).sum().backward()
+    assert_close(sol_g, sol_c, "solution", rtol=1e-5, atol_scale=2e-6)
+    assert_close(xg.grad, xc.grad, "dL/dx0", rtol=2e-3, atol_scale=1e-4)        # dt0's (tiny) gradient is dropped by design
+    for pg, pc in zip(net_g.parameters(), net_c.parameters()):
+        assert_close(pg.grad, pc.grad, "dL/dtheta", rtol=2e-3, atol_scale=1e-4)
