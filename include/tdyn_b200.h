@@ -35,7 +35,7 @@ extern "C" {
 #define TDYN_API
 #endif
 
-#define TDYN_ABI_VERSION 7
+#define TDYN_ABI_VERSION 8
 #define TDYN_MAX_STAGES 7
 #define TDYN_MAX_PEERS 8
 
@@ -114,6 +114,18 @@ TDYN_API int64_t tdyn_mlp_ffma_workspace_bytes(const tdyn_mlp_t* mlp);
 TDYN_API int tdyn_mlp_ffma_forward(const tdyn_mlp_t* mlp, const float* y, float* out, int64_t rows, float sign, void* stream);
 TDYN_API int tdyn_mlp_ffma_adjoint(const tdyn_mlp_t* mlp, const float* x, const float* lam, float* dx, float* dlam,
                                    float* dmu, void* workspace, int64_t rows, float sign, void* stream);
+
+/* Fused CNF vector field with Hutchinson's trace estimator (models/cnf.py:26-31, :55-65) for a narrow MLP `mlp`:
+ * state s = [logp, x] ([rows, D+1]), eps [rows, D] the noise sampled once per forward (core/neuralde.py:112-116).
+ *   forward : out = sign * [ -eps^T (df/dx) eps , f(x) ]                       (MLP forward + one in-kernel VJP)
+ *   adjoint : ds as above, dlam = sign * (-lam^T dF/ds), dmu = sign * (-sum_batch lam^T dF/dtheta) -- the body of
+ *             adjoint_dynamics (numerics/sensitivity.py:57-75) including the SECOND-ORDER terms the reference gets from
+ *             autograd's create_graph=True, written out analytically.  workspace as for tdyn_mlp_ffma_adjoint. */
+TDYN_API int tdyn_cnf_ffma_supported(const tdyn_mlp_t* mlp);
+TDYN_API int tdyn_cnf_ffma_forward(const tdyn_mlp_t* mlp, const float* s, const float* eps, float* out, int64_t rows, float sign,
+                                   void* stream);
+TDYN_API int tdyn_cnf_ffma_adjoint(const tdyn_mlp_t* mlp, const float* s, const float* lam, const float* eps, float* ds,
+                                   float* dlam, float* dmu, void* workspace, int64_t rows, float sign, void* stream);
 
 /* K1/K3 (persistent form). A whole `odeint` call (numerics/odeint.py:29-91 + :326-408: k1, init_step, the adaptive loop
  * with checkpoint handling, FSAL, the step controller) for a narrow MLP vector field in ONE cooperative kernel; one

@@ -554,3 +554,53 @@ def test_sensitivity_autograd_on_gpu_matches_oracle(solver, kw):
     assert_close(xg.grad, xc.grad, "dL/dx0", rtol=2e-3, atol_scale=1e-4)        # dt0's (tiny) gradient is dropped by design
     for pg, pc in zip(net_g.parameters(), net_c.parameters()):
         assert_close(pg.grad, pc.grad, "dL/dtheta", rtol=2e-3, atol_scale=1e-4)
+
+
+# ------------------------------------------------------------------------------ fused CNF / Hutchinson kernels
+
+@pytest.mark.parametrize("dims,act", [([2, 64, 64, 64, 2], "softplus"), ([2, 32, 2], "tanh"), ([3, 16, 16, 3], "tanh"),
+                                      ([4, 24, 4], "relu")])
+@pytest.mark.parametrize("rows", [5, 64, 4099])
+def test_cnf_kernels_match_double_backward_autograd(dims, act, rows):
+    """tdyn_cnf_ffma_forward / _adjoint against fp64 autograd of the reference formulation (models/cnf.py): the field
+    [-eps^T J eps, f(x)] and its VJPs w.r.t. state and parameters (second-order autograd, create_graph=True)."""
+    from torchdyn_b200 import fused
+    torch.manual_seed(rows + sum(dims))
+    D = dims[0]
+    net = build_mlp(dims, act).to(DEV)
+    fm = fused.FusedMLP(net)
+    kern = _kernels.get(torch.empty(1, device=DEV))
+    assert fm.ready_ffma(kern) and kern.cnf_ffma_supported(fm._desc)
+    s = torch.randn(rows, D + 1, device=DEV)
+    lam = torch.randn(rows, D + 1, device=DEV)
+    eps = torch.randn(rows, D, device=DEV)
+    net64 = build_mlp(dims, act, [p.detach() for p in net.parameters()], DEV).double()
+    x64 = s[:, 1:].double().requires_grad_(True)
+    f64 = net64(x64)
+    vjp = torch.autograd.grad(f64, x64, eps.double(), create_graph=True)[0]
+    tr = (vjp * eps.double()).sum(1)
+    F = torch.cat([-tr[:, None], f64], 1)
+    grads = torch.autograd.grad(F, (x64,) + tuple(net64.parameters()), -lam.double(), allow_unused=True)
+    want_dlam = torch.cat([torch.zeros(rows, 1, device=DEV, dtype=torch.float64), grads[0]], 1)
+    want_dmu = torch.cat([(g if g is not None else torch.zeros_like(p)).flatten() for g, p in zip(grads[1:], net64.parameters())])
+    out = kern.cnf_ffma_forward(fm._desc, s, eps, torch.empty_like(s), 1.0, fm.flops_per_row)
+    assert_close(out, F.detach(), "CNF field", rtol=1e-5, atol_scale=4e-6)
+    ds, dlam, dmu = torch.empty_like(s), torch.empty_like(s), torch.empty(fm.n_params, device=DEV)
+    for sign in (1.0, -1.0):
+        kern.cnf_ffma_adjoint(fm._desc, s, lam, eps, ds, dlam, dmu, fm.workspace(kern), rows, sign, fm.flops_per_row)
+        assert_close(ds, sign * F.detach(), "ds", rtol=1e-5, atol_scale=4e-6)
+        assert_close(dlam, sign * want_dlam, "dlam", rtol=2e-5, atol_scale=1e-5)
+        assert_close(dmu, sign * want_dmu, "dmu", rtol=5e-5, atol_scale=2e-5)
+
+
+def test_cnf_fixture_runs_on_the_fused_kernels():
+    """cfg 4 (reduced) end to end: the fused CNF kernels must be the ones evaluating the field (few launches) and the
+    result must match the executed reference."""
+    from torchdyn_b200 import fused
+    fx = load_golden("c4r_cnf_hutch")
+    n0 = _kernels.launches()
+    out = run_cnf_case(fx, DEV)
+    used = _kernels.launches() - n0
+    check_neuralode_case(fx, out)
+    assert "CNF" in (fused.last_used() or ""), fused.last_used()
+    assert used < 200, used

@@ -272,6 +272,28 @@ class CudaKernels:
         _lib.check(rc, "tdyn_mlp_solve_interp")
         _launches += 1
 
+    def cnf_ffma_supported(self, desc) -> bool:
+        return bool(self.lib.tdyn_cnf_ffma_supported(C.byref(desc)))
+
+    def cnf_ffma_forward(self, desc, s: Tensor, eps: Tensor, out: Tensor, sign: float, flops_per_row: float):
+        global _launches
+        with _Timed("cnf_ffma_forward", 2.0 * flops_per_row * s.shape[0]):
+            rc = self.lib.tdyn_cnf_ffma_forward(C.byref(desc), s.data_ptr(), eps.data_ptr(), out.data_ptr(), s.shape[0],
+                                                float(sign), self._stream())
+        _lib.check(rc, "tdyn_cnf_ffma_forward")
+        _launches += 1
+        return out
+
+    def cnf_ffma_adjoint(self, desc, s: Tensor, lam: Tensor, eps: Tensor, ds: Tensor, dlam: Tensor, dmu: Tensor, ws: Tensor,
+                         rows: int, sign: float, flops_per_row: float):
+        global _launches
+        with _Timed("cnf_ffma_adjoint", 6.0 * flops_per_row * rows):
+            rc = self.lib.tdyn_cnf_ffma_adjoint(C.byref(desc), s.data_ptr(), lam.data_ptr(), eps.data_ptr(), ds.data_ptr(),
+                                                dlam.data_ptr(), dmu.data_ptr(), ws.data_ptr(), int(rows), float(sign),
+                                                self._stream())
+        _lib.check(rc, "tdyn_cnf_ffma_adjoint")
+        _launches += 1
+
     def read_reduction(self, n: int = 1):
         """Device -> pinned host read of the first ``n`` reduction results (the step's ONE host sync)."""
         self.red_host[:n].copy_(self.red[:n], non_blocking=True)

@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdyn_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_STAGES = 7
 MAX_LAYERS = 4
 MODE_CHAIN, MODE_INNER = 0, 1
@@ -67,6 +67,10 @@ SIGNATURES = {
     "tdyn_mlp_ffma_forward": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "tdyn_mlp_ffma_adjoint": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
+    "tdyn_cnf_ffma_supported": (C.c_int, [C.POINTER(MlpDesc)]),
+    "tdyn_cnf_ffma_forward": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
+    "tdyn_cnf_ffma_adjoint": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "tdyn_mlp_solve_supported": (C.c_int, [C.POINTER(MlpDesc), C.c_int]),
     "tdyn_mlp_solve_workspace_bytes": (C.c_int64, [C.POINTER(MlpDesc)]),
     "tdyn_mlp_solve": (C.c_int, [C.POINTER(MlpDesc), C.POINTER(RkPlan), C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p,

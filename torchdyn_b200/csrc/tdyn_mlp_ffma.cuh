@@ -41,6 +41,14 @@ __device__ __forceinline__ float act_bwd(float h) {
     return 1.f - h * h;
 }
 
+// second derivative of the activation through its output h
+template <int ACT>
+__device__ __forceinline__ float act_bwd2(float h) {
+    if (ACT == TDYN_ACT_RELU) return 0.f;
+    if (ACT == TDYN_ACT_SOFTPLUS) { const float s = 1.f - expf(-h); return s * (1.f - s); }
+    return -2.f * h * (1.f - h * h);
+}
+
 __device__ __forceinline__ void load_weights(const Net& net, float* w_s) {
     for (int l = 0; l < net.L; ++l) {
         const int K = net.dims[l], N = net.dims[l + 1];
@@ -95,45 +103,55 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float s)
     s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); return fmaf(a.w, b.w, s);
 }
 
+// gacc(base + n*K + k, sum_r A[n][r] * B[k][r]) for an [N][kLd] tile A and a [K][kLd] tile B (rows beyond the batch are 0).
+// A thread owns 4 consecutive n x 1 k, lanes run over k: the B loads are conflict-free (stride kLd), the A loads are
+// warp broadcasts -- 5 LDS.128 per 16 FFMA per row group.
+template <class GAcc>
+__device__ __forceinline__ void outer_tile(int N, int K, const float* A, const float* B, int base, GAcc&& gacc) {
+    if ((N & 3) == 0) {
+        for (int i = threadIdx.x; i < (N >> 2) * K; i += kThreads) {
+            const int nb = i / K, k = i - nb * K;
+            const float* a0 = A + (4 * nb) * kLd;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int q = 0; q < kRG; ++q) {
+                const float4 bv = *reinterpret_cast<const float4*>(B + k * kLd + 4 * q);
+                s0 = dot4(*reinterpret_cast<const float4*>(a0 + 4 * q), bv, s0);
+                s1 = dot4(*reinterpret_cast<const float4*>(a0 + kLd + 4 * q), bv, s1);
+                s2 = dot4(*reinterpret_cast<const float4*>(a0 + 2 * kLd + 4 * q), bv, s2);
+                s3 = dot4(*reinterpret_cast<const float4*>(a0 + 3 * kLd + 4 * q), bv, s3);
+            }
+            const int o = base + (4 * nb) * K + k;
+            gacc(o, s0); gacc(o + K, s1); gacc(o + 2 * K, s2); gacc(o + 3 * K, s3);
+        }
+    } else {
+        for (int i = threadIdx.x; i < N * K; i += kThreads) {
+            const int nn = i / K, k = i - nn * K;
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < kRG; ++q)
+                s = dot4(*reinterpret_cast<const float4*>(A + nn * kLd + 4 * q), *reinterpret_cast<const float4*>(B + k * kLd + 4 * q), s);
+            gacc(base + i, s);
+        }
+    }
+}
+
 // VJP of the tile whose activations h_l are in h_s and whose output cotangent delta_L is in dcur ([dims[L]][kLd]):
 // for every layer, the tile's parameter-gradient contribution (weight [N][K] then bias [N], flat index p_off[l] + ...)
 // is handed to `gacc(flat_index, value)` (each index is produced by exactly one thread), and delta is pulled back
 // through W_l and the activation derivative.  Returns the buffer holding delta_0 = (delta_L)^T df/dx.
 // wgrad mapping: a thread owns 4 consecutive neurons x 1 input feature, lanes run over the input feature -- the
 // h loads are conflict-free (stride kLd), the delta loads are warp broadcasts: 5 LDS.128 per 16 FFMA per row group.
+// `zbar` (optional, activation-area layout): extra cotangent added to the pre-activation of hidden layer l
+// (zbar + h_off[l]) -- the second-order terms of a CNF's trace (tdyn_cnf_ffma.cu); nullptr for a plain MLP.
 template <int ACT, class GAcc>
 __device__ __forceinline__ float* backward_tile(const Net& net, const float* w_s, const float* h_s, float* dcur, float* dnxt,
-                                                GAcc&& gacc) {
+                                                GAcc&& gacc, const float* zbar = nullptr) {
     for (int l = net.L - 1; l >= 0; --l) {
         const int K = net.dims[l], N = net.dims[l + 1];
         const float* hin = h_s + net.h_off[l];
         const int po = net.p_off[l];
-        if ((N & 3) == 0) {
-            for (int i = threadIdx.x; i < (N >> 2) * K; i += kThreads) {
-                const int nb = i / K, k = i - nb * K;
-                const float* d0 = dcur + (4 * nb) * kLd;
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                for (int q = 0; q < kRG; ++q) {
-                    const float4 hv = *reinterpret_cast<const float4*>(hin + k * kLd + 4 * q);
-                    s0 = dot4(*reinterpret_cast<const float4*>(d0 + 4 * q), hv, s0);
-                    s1 = dot4(*reinterpret_cast<const float4*>(d0 + kLd + 4 * q), hv, s1);
-                    s2 = dot4(*reinterpret_cast<const float4*>(d0 + 2 * kLd + 4 * q), hv, s2);
-                    s3 = dot4(*reinterpret_cast<const float4*>(d0 + 3 * kLd + 4 * q), hv, s3);
-                }
-                const int base = po + (4 * nb) * K + k;
-                gacc(base, s0); gacc(base + K, s1); gacc(base + 2 * K, s2); gacc(base + 3 * K, s3);
-            }
-        } else {
-            for (int i = threadIdx.x; i < N * K; i += kThreads) {
-                const int nn = i / K, k = i - nn * K;
-                float s = 0.f;
-#pragma unroll
-                for (int q = 0; q < kRG; ++q)
-                    s = dot4(*reinterpret_cast<const float4*>(dcur + nn * kLd + 4 * q), *reinterpret_cast<const float4*>(hin + k * kLd + 4 * q), s);
-                gacc(po + i, s);
-            }
-        }
+        outer_tile(N, K, dcur, hin, po, gacc);
         for (int nn = threadIdx.x; nn < N; nn += kThreads) {
             float s = 0.f;
 #pragma unroll
@@ -154,6 +172,10 @@ __device__ __forceinline__ float* backward_tile(const Net& net, const float* w_s
             if (l > 0) {
                 const float4 hv = *reinterpret_cast<const float4*>(hin + k * kLd + 4 * g);
                 acc.x *= act_bwd<ACT>(hv.x); acc.y *= act_bwd<ACT>(hv.y); acc.z *= act_bwd<ACT>(hv.z); acc.w *= act_bwd<ACT>(hv.w);
+                if (zbar) {
+                    const float4 zb = *reinterpret_cast<const float4*>(zbar + net.h_off[l] + k * kLd + 4 * g);
+                    acc.x += zb.x; acc.y += zb.y; acc.z += zb.z; acc.w += zb.w;
+                }
             }
             *reinterpret_cast<float4*>(dnxt + k * kLd + 4 * g) = acc;
         }

@@ -68,6 +68,32 @@ def _unwrap(f):
     return (cur, counters) if isinstance(cur, nn.Sequential) and counters else (None, [])
 
 
+def _unwrap_cnf(f):
+    """-> (CNF module | None, [objects whose .nfe must advance]) for DEFunc -> DEFuncBase -> CNF(net, hutch_trace)."""
+    from .core.defunc import DEFunc, DEFuncBase
+    from .models.cnf import CNF, hutch_trace
+    counters = []
+    cur = f
+    for _ in range(3):
+        if isinstance(cur, DEFunc):
+            if cur.order > 1 or (cur.integral_loss is not None and cur.sensitivity == "autograd"):
+                return None, []
+            counters.append(cur)
+            cur = cur.vf
+            continue
+        if isinstance(cur, DEFuncBase):
+            if cur.has_time_arg:
+                return None, []
+            counters.append(cur)
+            cur = cur.vf
+            continue
+        break
+    if isinstance(cur, CNF) and counters and cur.trace_estimator is hutch_trace and cur.order == 1 \
+            and isinstance(cur.net, nn.Sequential):
+        return cur, counters
+    return None, []
+
+
 _cache = weakref.WeakKeyDictionary()      # nn.Sequential -> FusedMLP | False (kept off the module: it must stay picklable)
 _ACTS = {nn.Tanh: ACT_TANH, nn.Softplus: ACT_SOFTPLUS, nn.ReLU: ACT_RELU}
 
@@ -205,10 +231,75 @@ class FusedField:
         return out
 
 
+class FusedCNFField:
+    """CNF(net, hutch_trace) evaluated by ``tdyn_cnf_ffma_forward``: MLP forward + the eps^T J VJP + the trace dot
+    product in one launch (the reference builds an autograd graph per evaluation)."""
+
+    def __init__(self, f, cnf, fm: FusedMLP, counters, kern):
+        self.f, self.cnf, self.fm, self.counters, self.kern = f, cnf, fm, counters, kern
+
+    def __call__(self, t, x, *a, **k):
+        return self.f(t, x, *a, **k)
+
+    def parameters(self):
+        return self.f.parameters()
+
+    def tdyn_eval(self, t_host, s, sign: float = 1.0):
+        fm, kern, eps = self.fm, self.kern, self.cnf.noise
+        D = fm.dims[0]
+        if not (s.dim() == 2 and s.shape[1] == D + 1 and s.is_contiguous() and isinstance(eps, torch.Tensor) and eps.is_cuda
+                and eps.dtype == torch.float32 and tuple(eps.shape) == (s.shape[0], D) and eps.is_contiguous()
+                and fm.ready_ffma(kern)):
+            out = self.f(kern.time_tensor(t_host, s), s)
+            return out if sign == 1.0 else -out
+        out = kern.cnf_ffma_forward(fm._desc, s, eps, torch.empty_like(s), sign, fm.flops_per_row)
+        for c in self.counters:
+            c.nfe += 1
+        return out
+
+
+class FusedCNFAdjoint:
+    """Body of the adjoint dynamics of a CNF (forward, VJP, and the second-order terms) in one launch
+    (``tdyn_cnf_ffma_adjoint``); same call signature as FusedAdjoint."""
+
+    def __init__(self, cnf, fm: FusedMLP, counters, kern):
+        self.cnf, self.fm, self.counters, self.kern = cnf, fm, counters, kern
+
+    def __call__(self, s_flat, lam_flat, ds_out, dlam_out, dmu_out, rows, sign):
+        fm = self.fm
+        self.kern.cnf_ffma_adjoint(fm._desc, s_flat, lam_flat, self.cnf.noise, ds_out, dlam_out, dmu_out, fm.workspace(self.kern),
+                                   rows, sign, fm.flops_per_row)
+        for c in self.counters:
+            c.nfe += 1
+
+
+def _get_fused_cnf(f):
+    cnf, counters = _unwrap_cnf(f)
+    if cnf is None:
+        return None
+    fm = _cache.get(cnf.net)
+    if fm is None:
+        try:
+            fm = FusedMLP(cnf.net)
+        except ValueError:
+            fm = False
+        _cache[cnf.net] = fm
+    return (cnf, fm, counters) if fm else None
+
+
 def wrap(f, x):
     """Return a FusedField for ``f`` when it is a fusable MLP on this device, else ``f`` unchanged."""
     global _last
-    if DISABLED or isinstance(f, FusedField) or not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32):
+    if DISABLED or isinstance(f, (FusedField, FusedCNFField)) or not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32):
+        return f
+    gc = _get_fused_cnf(f)
+    if gc is not None:
+        cnf, fm, counters = gc
+        kern = _kernels.get(x)
+        if getattr(kern, "is_cuda", False) and x.dim() == 2 and x.shape[1] == fm.dims[0] + 1 and fm.ready_ffma(kern) \
+                and kern.cnf_ffma_supported(fm._desc):
+            _last = "fused CNF / Hutchinson vector field (tdyn_cnf_ffma_forward)"
+            return FusedCNFField(f, cnf, fm, counters, kern)
         return f
     got = _get_fused(f)
     if got is None:
@@ -259,6 +350,16 @@ def adjoint_for(vf, x_shape, device) -> Optional[FusedAdjoint]:
     """FusedAdjoint for ``vf`` (as held by ODEProblem: DEFunc / DEFuncBase wrapped nn.Sequential) or None."""
     if DISABLED or len(x_shape) != 2 or device.type != "cuda":
         return None
+    gc = _get_fused_cnf(vf)
+    if gc is not None:
+        cnf, fm, counters = gc
+        kern = _kernels.get(torch.empty(0, device=device))
+        eps = cnf.noise
+        ok = (getattr(kern, "is_cuda", False) and x_shape[1] == fm.dims[0] + 1 and fm.ready_ffma(kern)
+              and kern.cnf_ffma_supported(fm._desc) and isinstance(eps, torch.Tensor) and eps.is_cuda
+              and eps.dtype == torch.float32 and eps.is_contiguous() and tuple(eps.shape) == (x_shape[0], fm.dims[0])
+              and sum(p.numel() for p in vf.parameters()) == fm.n_params)
+        return FusedCNFAdjoint(cnf, fm, counters, kern) if ok else None
     got = _get_fused(vf)
     if got is None:
         return None
@@ -375,7 +476,7 @@ def try_adjoint_interval(dyn, A, t_from, t_to, solver, atol, rtol):
     ``A`` = flat [x, lam, mu, lam_t]; integrates from ``t_from`` down to ``t_to``.  Returns the new flat A or None."""
     from . import distributed as _dist
     fa = getattr(dyn, "fused", None)
-    if DISABLED or not PERSISTENT or fa is None or not _solver_ok(solver) or not A.is_contiguous():
+    if DISABLED or not PERSISTENT or not isinstance(fa, FusedAdjoint) or not _solver_ok(solver) or not A.is_contiguous():
         return None
     fm, kern = fa.fm, fa.kern
     if not kern.mlp_solve_supported(fm._desc, True):
@@ -412,7 +513,7 @@ def try_interp_interval(dyn, A, t_from, t_to, solver, atol, rtol):
     from . import distributed as _dist
     fa = getattr(dyn, "fused", None)
     sp = getattr(dyn, "spline", None)
-    if DISABLED or not PERSISTENT or fa is None or _dist.is_enabled() or not _solver_ok(solver) or not A.is_contiguous():
+    if DISABLED or not PERSISTENT or not isinstance(fa, FusedAdjoint) or _dist.is_enabled() or not _solver_ok(solver) or not A.is_contiguous():
         return None
     if not all(hasattr(sp, a) for a in ("sol", "kd", "two_c", "three_d", "t")):
         return None
