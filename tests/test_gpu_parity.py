@@ -248,12 +248,14 @@ def _c2_net(seed=8):
     return build_mlp([32, 256, 256, 32], "tanh")
 
 
-def test_mlp_tc_single_stage_matches_fp64_reference():
+@pytest.mark.parametrize("act", ["tanh", "softplus", "relu"])
+def test_mlp_tc_single_stage_matches_fp64_reference(act):
     """One tdyn_mlp_tc_stage launch (prologue combine + MLP + x_new epilogue) against an fp64 evaluation:
     3xTF32 must keep fp32-level accuracy (max error ~1e-6 relative to the output scale)."""
     from torchdyn_b200 import fused
-    net = _c2_net()
-    netg = build_mlp([32, 256, 256, 32], "tanh", [p.detach() for p in net.parameters()], DEV)
+    torch.manual_seed(8)
+    net = build_mlp([32, 256, 256, 32], act)
+    netg = build_mlp([32, 256, 256, 32], act, [p.detach() for p in net.parameters()], DEV)
     fm = fused.FusedMLP(netg)
     kern = _kernels.get(torch.empty(1, device=DEV))
     assert fm.ready(kern), "32-256-256-32 must be supported by the tensor-core kernel"
@@ -604,3 +606,29 @@ def test_cnf_fixture_runs_on_the_fused_kernels():
     check_neuralode_case(fx, out)
     assert "CNF" in (fused.last_used() or ""), fused.last_used()
     assert used < 200, used
+
+
+def test_edge_shapes_and_views():
+    """Awkward inputs through the public API: a single row, a batch that is not a multiple of any tile, a
+    non-contiguous state, a state given as a view into a larger buffer, t_span on the GPU."""
+    torch.manual_seed(2)
+    net = build_mlp([3, 16, 3], "tanh").to(DEV)
+    f = lambda t, x: net(x)        # noqa: E731
+    fc = lambda t, x: net.cpu()(x)  # noqa: E731,F841
+    t_span = torch.linspace(0, 1, 3)
+    with torch.no_grad():
+        for rows in (1, 33, 1025):
+            x = torch.randn(rows, 3, device=DEV)
+            _, a = odeint(f, x, t_span, "dopri5", atol=1e-5, rtol=1e-5)
+            _, b = odeint(f, x, t_span.to(DEV), "dopri5", atol=1e-5, rtol=1e-5)        # t_span on the device
+            assert torch.equal(a, b) and a.shape == (3, rows, 3)
+        big = torch.randn(64, 7, device=DEV)
+        view = big[:, 2:5]                                   # non-contiguous view
+        _, c = odeint(f, view, t_span, "tsit5", atol=1e-5, rtol=1e-5)
+        _, d = odeint(f, view.contiguous(), t_span, "tsit5", atol=1e-5, rtol=1e-5)
+        assert torch.equal(c, d)
+        flat = torch.randn(1 + 40 * 3, device=DEV)
+        off = flat[1:].view(40, 3)                           # 4-byte-aligned (not 16-byte-aligned) storage offset
+        _, e = odeint(f, off, t_span, "rk4")
+        _, g = odeint(f, off.clone(), t_span, "rk4")
+        assert torch.equal(e, g)
