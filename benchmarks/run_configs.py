@@ -114,6 +114,11 @@ def run_gpu(cfg, iters, scale):
     for _ in range(3):
         it()
     torch.cuda.synchronize()
+    timer = _kernels.KernelTimer()
+    _kernels.set_timer(timer)
+    it()
+    _kernels.set_timer(None)
+    per_kernel = {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in timer.summary().items()}
     n0, l0 = model.vf.nfe, _kernels.launches()
     t0 = time.perf_counter()
     for _ in range(iters):
@@ -122,7 +127,8 @@ def run_gpu(cfg, iters, scale):
     dt = (time.perf_counter() - t0) / iters
     nfe = (model.vf.nfe - n0) / iters
     return dict(config=name, impl="b200", batch=x.shape[0], nfe_per_iter=nfe, ms_per_iter=1e3 * dt,
-                sample_nfe_per_s=x.shape[0] * nfe / dt, own_kernel_launches_per_iter=(_kernels.launches() - l0) / iters)
+                sample_nfe_per_s=x.shape[0] * nfe / dt, own_kernel_launches_per_iter=(_kernels.launches() - l0) / iters,
+                own_kernel_ms_per_iter=per_kernel)
 
 
 def run_cpu(cfg, iters, scale):

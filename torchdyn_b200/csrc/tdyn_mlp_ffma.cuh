@@ -5,7 +5,7 @@
 namespace tdyn {
 namespace ffma {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kRows = 32;            // rows per tile
 constexpr int kRG = kRows / 4;       // row groups of 4
 constexpr int kLd = kRows + 4;       // row stride of the feature-major tiles: 36 floats = 9 x 16 B (odd), so that 8 lanes

@@ -122,7 +122,7 @@ __device__ __forceinline__ float combine_at(const float* y, float* const* K, con
 }
 
 template <int ACT>
-__global__ void __launch_bounds__(kThreads) ode_solve_kernel(const Args A) {
+__global__ void __launch_bounds__(kThreads, 1) ode_solve_kernel(const Args A) {
     extern __shared__ __align__(16) float sm[];
     const Net& net = A.net;
     const Plan& pl = A.plan;
@@ -563,7 +563,7 @@ struct InterpArgs {
 };
 
 template <int ACT>
-__global__ void __launch_bounds__(kThreads) interp_adjoint_kernel(const InterpArgs A) {
+__global__ void __launch_bounds__(kThreads, 1) interp_adjoint_kernel(const InterpArgs A) {
     extern __shared__ __align__(16) float sm[];
     const Net& net = A.net;
     const Plan& pl = A.plan;
