@@ -35,7 +35,7 @@ extern "C" {
 #define TDYN_API
 #endif
 
-#define TDYN_ABI_VERSION 8
+#define TDYN_ABI_VERSION 9
 #define TDYN_MAX_STAGES 7
 #define TDYN_MAX_PEERS 8
 
@@ -192,6 +192,27 @@ TDYN_API int tdyn_mlp_tc_prepare(const tdyn_mlp_t* mlp, void* wsplit, void* stre
 TDYN_API int tdyn_mlp_tc_stage(const tdyn_mlp_t* mlp, const void* wsplit, float* k_out, float* y_out,
                       const float* x, const float* const* k, const float* coef, int n_k, int mode, float dt,
                       float* x_new, const float* bsol, int n_sol, int64_t rows, void* stream);
+
+/* ---- Layer-wise tensor-core kernels for wide MLP vector fields (any widths that are multiples of 32; output widths
+ * <= 128 or multiples of 128, <= 2048): BASELINE configs[2] (128-1024-128) and the adjoint of the 32-256-256-32 class.
+ * Replaces, per layer, the nn.Linear / activation calls of the vector field (reference core/defunc.py:30-35) and the
+ * autograd VJP `grad(dx, (x, t) + params, -lambda)` of the adjoint dynamics (numerics/sensitivity.py:62-66, 134-138).
+ *
+ * tdyn_lin_tc_prepare: image of the B operand of one layer (3xTF32 hi/lo, swizzled), `transpose` = 0 for the forward
+ *   (B = W [w_rows = out, w_cols = in]) and 1 for the input gradient (B = W^T).  Rebuild after a parameter update.
+ * tdyn_lin_tc_apply:  out[r, n] = scale * epi(sum_k in[r, k] B[n, k] + bias[n]);  mode 0: epi = identity,
+ *   1: epi = act, 2: epi(v) = v * act'(z) with act' evaluated from the saved activation OUTPUT saved[r, n].
+ *   in [rows, k_in], out / saved [rows, n_out], contiguous fp32, 16-byte aligned; bias may be NULL.
+ * tdyn_wgrad_tc: dw[n, k] = scale * sum_r g[r, n] in[r, k], db[n] = scale * sum_r g[r, n]  (g [rows, n_out],
+ *   in [rows, k_in]); deterministic (fixed-order reduction of per-CTA partials held in `ws`). */
+TDYN_API int tdyn_lin_tc_supported(int n_out, int k_in);
+TDYN_API int64_t tdyn_lin_tc_image_bytes(int n_out, int k_in);
+TDYN_API int tdyn_lin_tc_prepare(const float* w, int w_rows, int w_cols, int transpose, void* img, void* stream);
+TDYN_API int tdyn_lin_tc_apply(const void* img, int n_out, int k_in, const float* in, const float* bias, const float* saved,
+                      float* out, int act, int mode, float scale, int64_t rows, void* stream);
+TDYN_API int64_t tdyn_wgrad_tc_workspace_bytes(int n_out, int k_in, int64_t rows);
+TDYN_API int tdyn_wgrad_tc(const float* g, int n_out, const float* in, int k_in, float* dw, float* db, float scale,
+                  void* ws, int64_t ws_bytes, int64_t rows, void* stream);
 
 #ifdef __cplusplus
 }

@@ -213,6 +213,44 @@ class CudaKernels:
         _lib.check(rc, "tdyn_mlp_tc_stage")
         _launches += 1
 
+    # ---- layer-wise tensor-core kernels for wide MLPs (tdyn_lin_tc_*, tdyn_wgrad_tc)
+    def lin_tc_supported(self, n_out: int, k_in: int) -> bool:
+        return bool(self.lib.tdyn_lin_tc_supported(int(n_out), int(k_in)))
+
+    def lin_tc_prepare(self, w: Tensor, transpose: bool) -> Tensor:
+        """Weight image of one layer: B = W (forward) or B = W^T (input gradient)."""
+        global _launches
+        rows, cols = w.shape
+        n, k = (cols, rows) if transpose else (rows, cols)
+        img = torch.empty(int(self.lib.tdyn_lin_tc_image_bytes(n, k)), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.tdyn_lin_tc_prepare(w.data_ptr(), rows, cols, int(transpose), img.data_ptr(), self._stream()),
+                   "tdyn_lin_tc_prepare")
+        _launches += 1
+        return img
+
+    def lin_tc_apply(self, img: Tensor, n_out: int, k_in: int, inp: Tensor, bias: Optional[Tensor], saved: Optional[Tensor],
+                     out: Tensor, act: int, mode: int, scale: float, rows: int):
+        """out[r, n] = scale * epi(in[r, :] . B[n, :] + bias[n]); mode 0 linear, 1 activation, 2 times act'(saved)."""
+        global _launches
+        with _Timed("lin_tc", 2.0 * n_out * k_in * rows):
+            rc = self.lib.tdyn_lin_tc_apply(img.data_ptr(), int(n_out), int(k_in), inp.data_ptr(), _ptr(bias), _ptr(saved),
+                                            out.data_ptr(), int(act), int(mode), float(scale), int(rows), self._stream())
+        _lib.check(rc, "tdyn_lin_tc_apply")
+        _launches += 1
+
+    def wgrad_tc_workspace(self, n_out: int, k_in: int, rows: int) -> Tensor:
+        return torch.empty(int(self.lib.tdyn_wgrad_tc_workspace_bytes(int(n_out), int(k_in), int(rows))), dtype=torch.uint8,
+                           device=self.device)
+
+    def wgrad_tc(self, g: Tensor, n_out: int, inp: Tensor, k_in: int, dw: Tensor, db: Tensor, scale: float, ws: Tensor, rows: int):
+        """dw[n, k] = scale * sum_r g[r, n] in[r, k]; db[n] = scale * sum_r g[r, n] (two launches: partials + reduce)."""
+        global _launches
+        with _Timed("wgrad_tc", 2.0 * n_out * k_in * rows):
+            rc = self.lib.tdyn_wgrad_tc(g.data_ptr(), int(n_out), inp.data_ptr(), int(k_in), dw.data_ptr(), db.data_ptr(),
+                                        float(scale), ws.data_ptr(), ws.numel(), int(rows), self._stream())
+        _lib.check(rc, "tdyn_wgrad_tc")
+        _launches += 2
+
     def mlp_ffma_supported(self, desc) -> bool:
         return bool(self.lib.tdyn_mlp_ffma_supported(C.byref(desc)))
 

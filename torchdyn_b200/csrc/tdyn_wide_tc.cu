@@ -1,0 +1,751 @@
+// K10/K11: layer-wise tensor-core (tcgen05 / TMEM, 3xTF32) kernels for WIDE MLP vector fields of any shape whose layer
+// widths are multiples of 32 (BASELINE.json configs[2]: 128-1024-128) and for the adjoint of the 32-256-256-32 class.
+//
+//   K10 tdyn_lin_tc_apply : OUT[r, n] = scale * epi( sum_k IN[r, k] * B[n, k] (+ bias[n]) )
+//        forward layer  : B = W            epi = act(.)            (hidden)   or identity (last layer)
+//        dgrad          : B = W^T          epi = (.) * act'(a[r,n]) (hidden)  or identity (first layer)
+//        = the Linear / activation calls of the vector field and the input half of its VJP
+//          (reference core/defunc.py:30-35, numerics/sensitivity.py:62-66, 134-138).
+//   K11 tdyn_wgrad_tc     : dW[n, k] = scale * sum_r G[r, n] * IN[r, k],  db[n] = scale * sum_r G[r, n]
+//        = the parameter half of the VJP, -lambda^T df/dtheta, contracted over the batch (sensitivity.py:66, 138).
+//
+// Both keep the 3xTF32 split (hi = rna_tf32(a), lo = a - hi; lo*hi + hi*lo + hi*hi with fp32 accumulation in TMEM).
+// K10: M = 128 batch rows per tile, the A operand (activations) is split by producer warps straight from global memory
+// into a TMEM ring (both halves: every MMA is the A-from-TMEM form, shared memory only carries B), the pre-split /
+// pre-swizzled weight image is streamed from L2 with bulk copies, accumulators are double-buffered [128 x <=128] TMEM
+// tiles drained by separate epilogue warps.  K11: M = 128 output features (TMEM lanes), N = <=128 input features,
+// K = batch rows; G^T goes to TMEM as it is loaded (lane = feature: no transposition), IN^T is transposed into the
+// K-major swizzled layout by the store pattern; the accumulator is flushed into fp32 registers every 256 rows so the
+// tensor core's truncating accumulation never runs over more than 96 partial sums; per-CTA partials are reduced in a
+// fixed order by a second kernel (deterministic).
+#include "tdyn_tc_ptx.cuh"
+
+namespace tdyn {
+namespace wtc {
+
+using namespace tcx;
+
+constexpr int kKB = 32;                 // K-block: 32 fp32 = 128 B = one swizzle row
+constexpr int kNcMax = 128;             // accumulator tile width
+constexpr int kThreads = 576;           // warp 0 weight producer, warp 1 MMA, warps 2..17 workers
+constexpr int kASlots = 3;              // TMEM ring of A K-blocks: slot = 32 hi + 32 lo columns
+constexpr uint32_t kColAcc0 = 0, kColAcc1 = 128, kColA = 256;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kMaxWidth = 2048;
+
+// ---------------------------------------------------------------------------------------------------- K10
+constexpr int kBStages = 4;
+constexpr int kSegKB = 8;                                       // accumulators are flushed every 8 K-blocks (K = 256): the tensor
+                                                                // core adds with truncation, 96 partial sums keep it at ~3e-6
+constexpr uint32_t kBStage = kNcMax * 256;                      // [Nc x 32] hi | lo  (32 KB at Nc = 128)
+constexpr uint32_t kLSmemB = 0;
+constexpr uint32_t kLSmemPart = kLSmemB + kBStages * kBStage;   // fp32 partial sums [warp][col][lane] when K > 256
+constexpr uint32_t kLSmemStage = kLSmemPart + kNcMax * kTileM * 4;  // 8 epilogue warps x [32 rows][16 cols] output staging
+constexpr uint32_t kLSmemBias = kLSmemStage + 8 * 2048;             // up to kMaxWidth floats
+constexpr uint32_t kLSmemBars = kLSmemBias + kMaxWidth * 4;
+constexpr uint32_t kLSmemTotal = kLSmemBars + 256 + 1024;
+enum { MODE_LIN = 0, MODE_ACT = 1, MODE_DACT = 2 };
+enum LBar { LB_FULL0 = 0, LB_EMPTY0 = LB_FULL0 + kBStages, LA_FULL0 = LB_EMPTY0 + kBStages, LA_EMPTY0 = LA_FULL0 + kASlots,
+            LACC_FULL0 = LA_EMPTY0 + kASlots, LACC_EMPTY0 = LACC_FULL0 + 2, L_NUM_BARS = LACC_EMPTY0 + 2 };
+
+struct LinParams {
+    const uint8_t* img;        // slabs (chunk c, K-block kb): [Nc x 32] hi then lo, 128B-swizzled
+    const float* in;           // [rows][K]
+    const float* bias;         // [N] or null
+    const float* saved;        // [rows][N] activation outputs (MODE_DACT) or null
+    float* out;                // [rows][N]
+    int N, K, Nc;
+    float scale;
+    int64_t rows;
+    int num_tiles;
+};
+
+// derivative of the activation expressed through its OUTPUT a = act(z)
+template <int ACT>
+__device__ __forceinline__ float dact_from_out(float a) {
+    if (ACT == TDYN_ACT_RELU) return a > 0.f ? 1.f : 0.f;
+    if (ACT == TDYN_ACT_SOFTPLUS) return -expm1f(-a);       // sigmoid(z) = 1 - exp(-softplus(z))
+    return fmaf(-a, a, 1.f);                                  // 1 - tanh^2
+}
+
+__device__ __forceinline__ void split8_to_tmem(uint32_t t_hi, uint32_t t_lo, const float (&a)[8]) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float h = tf32_rna(a[i]);
+        hi[i] = __float_as_uint(h);
+        lo[i] = __float_as_uint(a[i] - h);
+    }
+    tmem_st8(t_hi, hi);
+    tmem_st8(t_lo, lo);
+}
+
+// 3xTF32 K-block with both A halves in TMEM: D (+)= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi
+__device__ __forceinline__ void issue_kblock_tt(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                uint32_t idesc, bool first) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d_tmem, a_lo + k * 8, umma_desc(b_hi + k * 32), idesc, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d_tmem, a_hi + k * 8, umma_desc(b_lo + k * 32), idesc, 1u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d_tmem, a_hi + k * 8, umma_desc(b_hi + k * 32), idesc, 1u);
+}
+
+template <int ACT, int MODE>
+__global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t tmem_base_slot;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bars = sbase + kLSmemBars;
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < L_NUM_BARS; ++i) {
+            uint32_t cnt = 1;
+            if (i >= LA_FULL0 && i < LA_FULL0 + kASlots) cnt = 256;
+            if (i >= LACC_EMPTY0 && i < LACC_EMPTY0 + 2) cnt = 256;
+            mbar_init(bar(i), cnt);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (P.bias) {
+        float* sb = reinterpret_cast<float*>(smem + kLSmemBias);
+        for (int i = threadIdx.x; i < P.N; i += kThreads) sb[i] = __ldg(P.bias + i);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+    const int my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int nchunks = P.N / P.Nc;
+    const int nkb = P.K / kKB;
+    const int items = my_tiles * nchunks;           // item = (row tile, output chunk); chunk is the fast index
+    const uint32_t slab = (uint32_t)P.Nc * 256u;
+
+    if (warp == 0) {
+        // ================= weight producer =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int item = 0; item < items; ++item) {
+                const int c = item % nchunks;
+                const uint8_t* src = P.img + (size_t)c * nkb * slab;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t slot = it % kBStages, use = it / kBStages;
+                    mbar_wait(bar(LB_EMPTY0 + slot), (use & 1) ^ 1);
+                    mbar_expect_tx(bar(LB_FULL0 + slot), slab);
+                    bulk_g2s(sbase + kLSmemB + slot * kBStage, src + (size_t)kb * slab, slab, bar(LB_FULL0 + slot));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t ait = 0, bit = 0, sc = 0;
+            const uint32_t idesc = umma_idesc(P.Nc);
+            for (int item = 0; item < items; ++item) {
+                for (int kb0 = 0; kb0 < nkb; kb0 += kSegKB, ++sc) {           // one accumulator buffer per K segment
+                    const uint32_t buf = sc & 1, u = sc >> 1;
+                    mbar_wait(bar(LACC_EMPTY0 + buf), (u & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem + (buf ? kColAcc1 : kColAcc0);
+                    const int kb1 = kb0 + kSegKB < nkb ? kb0 + kSegKB : nkb;
+                    for (int kb = kb0; kb < kb1; ++kb, ++ait, ++bit) {
+                        const uint32_t as = ait % kASlots, au = ait / kASlots, bs = bit % kBStages, bu = bit / kBStages;
+                        mbar_wait(bar(LA_FULL0 + as), au & 1);
+                        mbar_wait(bar(LB_FULL0 + bs), bu & 1);
+                        tc_fence_after();
+                        const uint32_t a_hi = tmem + kColA + as * 64u;
+                        const uint32_t b_hi = sbase + kLSmemB + bs * kBStage;
+                        issue_kblock_tt(d, a_hi, a_hi + 32u, b_hi, b_hi + slab / 2, idesc, kb == kb0);
+                        tc_commit(bar(LA_EMPTY0 + as));
+                        tc_commit(bar(LB_EMPTY0 + bs));
+                    }
+                    tc_commit(bar(LACC_FULL0 + buf));
+                }
+            }
+        }
+    } else if (warp < 10) {
+        // ================= A producers: IN rows -> TF32 hi/lo -> TMEM ring =================
+        const int quarter = warp & 3;
+        const int cg = (warp - 2) >> 2;                           // which 16 of the 32 K values
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + kColA + (uint32_t)(cg * 16);
+        const int total = items * nkb;
+        auto load = [&](float4 (&r)[4], int n) {
+            const int item = n / nkb, kb = n - item * nkb;
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)(item / nchunks) * gridDim.x;
+            const int64_t grow = tile * kTileM + row;
+            if (grow < P.rows) {
+                const float4* p = reinterpret_cast<const float4*>(P.in + (size_t)grow * P.K + kb * kKB + cg * 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r[i] = __ldg(p + i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto emit = [&](const float4 (&r)[4], int n) {
+            const uint32_t as = (uint32_t)n % kASlots, au = (uint32_t)n / kASlots;
+            mbar_wait(bar(LA_EMPTY0 + as), (au & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t t_hi = lane_addr + as * 64u;
+            const float a0[8] = {r[0].x, r[0].y, r[0].z, r[0].w, r[1].x, r[1].y, r[1].z, r[1].w};
+            const float a1[8] = {r[2].x, r[2].y, r[2].z, r[2].w, r[3].x, r[3].y, r[3].z, r[3].w};
+            split8_to_tmem(t_hi, t_hi + 32u, a0);
+            split8_to_tmem(t_hi + 8u, t_hi + 40u, a1);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar(LA_FULL0 + as));
+        };
+        float4 b0[4], b1[4], b2[4], b3[4];
+        if (total > 0) load(b0, 0);
+        if (total > 1) load(b1, 1);
+        if (total > 2) load(b2, 2);
+        int n = 0;
+        while (n < total) {                                       // four register buffers in rotation: three loads in flight
+            if (n + 3 < total) load(b3, n + 3);
+            emit(b0, n); if (++n >= total) break;
+            if (n + 3 < total) load(b0, n + 3);
+            emit(b1, n); if (++n >= total) break;
+            if (n + 3 < total) load(b1, n + 3);
+            emit(b2, n); if (++n >= total) break;
+            if (n + 3 < total) load(b2, n + 3);
+            emit(b3, n); ++n;
+        }
+    } else {
+        // ================= epilogue: TMEM -> (+bias, activation | * act'(saved)) * scale -> OUT =================
+        // Each thread owns one row (TMEM lane) and ncol columns of the chunk.  Results go 16 columns at a time through a
+        // per-warp shared-memory tile ([32 rows][16 cols], 16-byte chunks XOR-swizzled by row) so that global stores
+        // (and the loads of the saved activations, prefetched one pass ahead) are 64-byte row segments, 8 rows per
+        // instruction, instead of 16 bytes per row.
+        const int quarter = warp & 3;
+        const int ew = warp - 10;
+        const int half = ew >> 2;
+        const int ncol = P.Nc >> 1;                               // columns of the chunk this thread drains: 16, 32 or 64
+        const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * ncol);
+        const float* sb = reinterpret_cast<const float*>(smem + kLSmemBias);
+        float* part = reinterpret_cast<float*>(smem + kLSmemPart) + (size_t)ew * 64 * 32 + lane;       // [col][lane]
+        uint8_t* stage = smem + kLSmemStage + (size_t)ew * 2048;
+        const int lr = lane >> 2, lch = lane & 3;                 // coalesced phase: row inside a group of 8, chunk
+        auto st_off = [](int r, int ch) { return (uint32_t)(r * 64 + ((ch ^ ((r >> 1) & 3)) << 4)); };
+        const int nseg = (nkb + kSegKB - 1) / kSegKB;
+        const int npass = ncol >> 4;
+        uint32_t sc = 0;
+        float4 sv[4];                                             // saved activations of the NEXT pass (MODE_DACT)
+        auto fetch_saved = [&](int item, int pass) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)(item / nchunks) * gridDim.x;
+            const int64_t row0 = tile * kTileM + quarter * 32;
+            const int n0 = (item % nchunks) * P.Nc + half * ncol + pass * 16;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t r = row0 + i * 8 + lr;
+                sv[i] = r < P.rows ? __ldg(reinterpret_cast<const float4*>(P.saved + (size_t)r * P.N + n0 + lch * 4))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        if (MODE == MODE_DACT && items > 0) fetch_saved(0, 0);
+        for (int item = 0; item < items; ++item) {
+            const int c = item % nchunks;
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)(item / nchunks) * gridDim.x;
+            const int64_t row0 = tile * kTileM + quarter * 32;    // first row of this warp
+            const int n0 = c * P.Nc + half * ncol;
+            for (int seg = 0; seg < nseg; ++seg, ++sc) {
+                const uint32_t buf = sc & 1, u = sc >> 1;
+                const bool first = seg == 0, last = seg == nseg - 1;
+                mbar_wait(bar(LACC_FULL0 + buf), u & 1);
+                tc_fence_after();
+                const uint32_t src = lane_addr + (buf ? kColAcc1 : kColAcc0);
+                uint32_t ra[8], rb8[8];
+                tmem_ld8(src, ra);
+                for (int pass = 0; pass < npass; ++pass) {
+                    const int p0 = pass * 16;
+                    tmem_ld8(src + (uint32_t)(p0 + 8), rb8);
+                    if (MODE == MODE_DACT && last) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stage + st_off(i * 8 + lr, lch)) = sv[i];
+                        __syncwarp();
+                        if (pass + 1 < npass) fetch_saved(item, pass + 1);
+                        else if (item + 1 < items) fetch_saved(item + 1, 0);
+                    }
+                    auto proc = [&](const uint32_t (&acc)[8], int g) {      // 8 columns starting at p0 + g (g = 0 or 8)
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[i]);
+                        if (!first) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] += part[(p0 + g + i) * 32];
+                        }
+                        if (!last) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) part[(p0 + g + i) * 32] = v[i];
+                            return;
+                        }
+                        if (P.bias) {
+                            const float4 q0 = *reinterpret_cast<const float4*>(sb + n0 + p0 + g);
+                            const float4 q1 = *reinterpret_cast<const float4*>(sb + n0 + p0 + g + 4);
+                            v[0] += q0.x; v[1] += q0.y; v[2] += q0.z; v[3] += q0.w;
+                            v[4] += q1.x; v[5] += q1.y; v[6] += q1.z; v[7] += q1.w;
+                        }
+                        float4* st0 = reinterpret_cast<float4*>(stage + st_off(lane, g >> 2));
+                        float4* st1 = reinterpret_cast<float4*>(stage + st_off(lane, (g >> 2) + 1));
+                        if (MODE == MODE_ACT) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = activate<ACT>(v[i]);
+                        } else if (MODE == MODE_DACT) {
+                            const float4 s0 = *st0, s1 = *st1;
+                            const float a[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] *= dact_from_out<ACT>(a[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] *= P.scale;
+                        *st0 = make_float4(v[0], v[1], v[2], v[3]);
+                        *st1 = make_float4(v[4], v[5], v[6], v[7]);
+                    };
+                    tmem_wait8(ra);                                   // (also completes rb8: the wait covers all loads)
+                    tmem_wait8(rb8);
+                    uint32_t ca[8], cb[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { ca[i] = ra[i]; cb[i] = rb8[i]; }
+                    if (pass + 1 < npass) tmem_ld8(src + (uint32_t)(p0 + 16), ra);    // next pass in flight
+                    proc(ca, 0);
+                    proc(cb, 8);
+                    if (last) {
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = i * 8 + lr;
+                            if (row0 + r < P.rows)
+                                *reinterpret_cast<float4*>(P.out + (size_t)(row0 + r) * P.N + n0 + p0 + lch * 4) =
+                                    *reinterpret_cast<const float4*>(stage + st_off(r, lch));
+                        }
+                        __syncwarp();
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(bar(LACC_EMPTY0 + buf));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+    }
+}
+
+// image of operand B[n'][k']: transpose = 0: B = W ([n_out x k_in] row-major); transpose = 1: B[n'][k'] = W[k'][n']
+__global__ void lin_prepare_kernel(const float* __restrict__ w, int w_rows, int w_cols, int transpose, int Nc,
+                                   uint8_t* __restrict__ img) {
+    const int Np = transpose ? w_cols : w_rows, Kp = transpose ? w_rows : w_cols;
+    const int nkb = Kp / kKB;
+    const size_t slab = (size_t)Nc * 256;
+    const int total = w_rows * w_cols;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int r = idx / w_cols, cidx = idx - r * w_cols;
+        const int n = transpose ? cidx : r, k = transpose ? r : cidx;
+        const int c = n / Nc, nl = n - c * Nc, kb = k / kKB, kk = k - kb * kKB;
+        const size_t off = ((size_t)c * nkb + kb) * slab + swz((uint32_t)nl, (uint32_t)(kk >> 2)) + (kk & 3) * 4;
+        const float v = w[idx];
+        const float hi = tf32_rna(v);
+        *reinterpret_cast<float*>(img + off) = hi;
+        *reinterpret_cast<float*>(img + off + slab / 2) = tf32_rna(v - hi);
+    }
+    (void)Np;
+}
+
+// ---------------------------------------------------------------------------------------------------- K11
+constexpr int kWStages = 3;                         // ring index shared by the raw tiles, the A TMEM slot and the B operand stage
+constexpr int kDrainLag = 2;                        // segment s is drained after K-block 8(s+1)+2 has been produced
+constexpr uint32_t kRawTile = kKB * kNcMax * 4;     // 16 KB: [32 rows][128 features] fp32 as it lies in global memory
+constexpr uint32_t kWSmemOp = 0;                                     // B operand stages (hi | lo), kBStage each
+constexpr uint32_t kWSmemRawG = kWSmemOp + kWStages * kBStage;       // raw G tiles
+constexpr uint32_t kWSmemRawI = kWSmemRawG + kWStages * kRawTile;    // raw IN tiles
+constexpr uint32_t kWSmemBias = kWSmemRawI + kWStages * kRawTile;    // double[4][128]
+constexpr uint32_t kWSmemBars = kWSmemBias + 4 * 128 * 8;
+constexpr uint32_t kWSmemTotal = kWSmemBars + 256 + 1024;
+enum WBar { RAW_FULL0 = 0, RAW_EMPTY0 = RAW_FULL0 + kWStages, W_FULL0 = RAW_EMPTY0 + kWStages, W_EMPTY0 = W_FULL0 + kWStages,
+            WACC_FULL0 = W_EMPTY0 + kWStages, WACC_EMPTY0 = WACC_FULL0 + 2, W_NUM_BARS = WACC_EMPTY0 + 2 };
+
+struct WgradParams {
+    const float* g;            // [rows][No]
+    const float* in;           // [rows][Ki]
+    float* part_w;             // [splits][No][Ki]
+    double* part_b;            // [splits][No]
+    int No, Ki, Nk;            // Nk = min(128, Ki): output-tile width
+    int n_tiles, k_tiles, splits;
+    int64_t rows, rows_per_split;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t tmem_base_slot;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bars = sbase + kWSmemBars;
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < W_NUM_BARS; ++i) {
+            uint32_t cnt = 1;
+            if (i >= RAW_FULL0 && i < RAW_FULL0 + kWStages) cnt = 512;      // one cp.async arrive-on per worker thread
+            if (i >= RAW_EMPTY0 && i < RAW_EMPTY0 + kWStages) cnt = 512;
+            if (i >= W_FULL0 && i < W_FULL0 + kWStages) cnt = 512;
+            if (i >= WACC_EMPTY0 && i < WACC_EMPTY0 + 2) cnt = 512;
+            mbar_init(bar(i), cnt);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+
+    const int split = (int)blockIdx.x / (P.n_tiles * P.k_tiles);
+    const int tile = (int)blockIdx.x - split * (P.n_tiles * P.k_tiles);
+    const int nt = tile / P.k_tiles, kt = tile - nt * P.k_tiles;
+    const int n0 = nt * kTileM, k0 = kt * P.Nk;
+    const int gw = P.No - n0 < kTileM ? P.No - n0 : kTileM;          // valid output features of this tile
+    const int64_t r_begin = (int64_t)split * P.rows_per_split;
+    const int64_t r_end = r_begin + P.rows_per_split < P.rows ? r_begin + P.rows_per_split : P.rows;
+    const int nkb = r_end > r_begin ? (int)((r_end - r_begin + kKB - 1) / kKB) : 0;
+    const int nseg = (nkb + kSegKB - 1) / kSegKB;
+    const uint32_t bhalf = (uint32_t)P.Nk * 128u;
+
+    if (warp == 0) {
+        // idle: the raw tiles are fetched by the worker threads themselves with cp.async (16 bytes per request,
+        // coalesced along the rows, completion counted on an mbarrier; many small bulk copies were 4x slower)
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(P.Nk);
+            for (int j = 0; j < nkb; ++j) {
+                const int seg = j / kSegKB;
+                const uint32_t buf = seg & 1;
+                if (j % kSegKB == 0) {
+                    mbar_wait(bar(WACC_EMPTY0 + buf), (((uint32_t)seg >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                }
+                const uint32_t s = (uint32_t)j % kWStages, use = (uint32_t)j / kWStages;
+                mbar_wait(bar(W_FULL0 + s), use & 1);
+                tc_fence_after();
+                const uint32_t a_hi = tmem + kColA + s * 64u;
+                const uint32_t b_hi = sbase + kWSmemOp + s * kBStage;
+                issue_kblock_tt(tmem + (buf ? kColAcc1 : kColAcc0), a_hi, a_hi + 32u, b_hi, b_hi + bhalf, idesc, j % kSegKB == 0);
+                tc_commit(bar(W_EMPTY0 + s));
+                if (j % kSegKB == kSegKB - 1 || j == nkb - 1) tc_commit(bar(WACC_FULL0 + buf));
+            }
+        }
+    } else {
+        // ================= transform (raw tiles -> G^T in TMEM, IN^T in shared memory) + accumulator drains =================
+        const int quarter = warp & 3;
+        const int rg = (warp - 2) >> 2;                           // 0..3
+        const int tid_w = (warp - 2) * 32 + lane;                 // 0..511
+        const int nl = quarter * 32 + lane;                       // output feature inside the tile = TMEM lane
+        const bool n_ok = nl < gw;
+        const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+        const int units = P.Nk * 8;                               // (k, 4-row chunk) units of the B tile
+        const int u0 = tid_w, u1 = tid_w + 512;
+        const int kl0 = u0 % P.Nk, ch0 = u0 / P.Nk, kl1 = u1 % P.Nk, ch1 = u1 / P.Nk;
+        const bool has0 = u0 < units, has1 = u1 < units;
+        const int cols_per = P.Nk >> 2;                           // accumulator columns this thread drains (multiple of 8)
+        const int nld = cols_per >> 3;
+        float acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+        double bsum = 0.0;
+
+        auto drain = [&](int seg) {
+            const uint32_t buf = seg & 1;
+            mbar_wait(bar(WACC_FULL0 + buf), ((uint32_t)seg >> 1) & 1);
+            tc_fence_after();
+            const uint32_t src = lane_base + (buf ? kColAcc1 : kColAcc0) + (uint32_t)(rg * cols_per);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < nld) {
+                    uint32_t r[8];
+                    tmem_ld8(src + (uint32_t)(q * 8), r);
+                    tmem_wait8(r);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[q * 8 + i] += __uint_as_float(r[i]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar(WACC_EMPTY0 + buf));
+        };
+        auto split4 = [&](const float (&v)[4], uint8_t* dst) {
+            float4 hi, lo;
+            hi.x = tf32_rna_fast(v[0]); lo.x = v[0] - hi.x; hi.y = tf32_rna_fast(v[1]); lo.y = v[1] - hi.y;
+            hi.z = tf32_rna_fast(v[2]); lo.z = v[2] - hi.z; hi.w = tf32_rna_fast(v[3]); lo.w = v[3] - hi.w;
+            *reinterpret_cast<float4*>(dst) = hi;
+            *reinterpret_cast<float4*>(dst + bhalf) = lo;
+        };
+        // ---- per-thread constants of the raw-tile fetch (two 16-byte chunks of each operand per K-block)
+        const int gcpr = gw >> 2, icpr = P.Nk >> 2;               // 16-byte chunks per raw row
+        const int64_t r_last = r_end - 1;
+        // chunk ids tid_w and tid_w + 512: same 16-byte column, 512 / (chunks per row) rows further down
+        const int frg = tid_w / gcpr, fri = tid_w / icpr;         // row inside the K-block of the first chunk
+        const int stepg = 512 / gcpr, stepi = 512 / icpr;
+        const bool fg0 = frg < kKB, fg1 = frg + stepg < kKB, fi0 = fri < kKB, fi1 = fri + stepi < kKB;
+        const float* fsg = P.g + (size_t)(r_begin + frg) * P.No + n0 + (tid_w - frg * gcpr) * 4;
+        const float* fsi = P.in + (size_t)(r_begin + fri) * P.Ki + k0 + (tid_w - fri * icpr) * 4;
+        const uint32_t fdg = (uint32_t)(frg * (kNcMax * 4) + (tid_w - frg * gcpr) * 16);
+        const uint32_t fdi = (uint32_t)(fri * (P.Nk * 4) + (tid_w - fri * icpr) * 16);
+        auto fetch = [&](int j) {                                 // raw tiles of K-block j -> ring stage j % kWStages
+            const uint32_t s = (uint32_t)j % kWStages, use = (uint32_t)j / kWStages;
+            const int64_t r0 = r_begin + (int64_t)j * kKB;
+            mbar_wait(bar(RAW_EMPTY0 + s), (use & 1) ^ 1);
+            const uint32_t dg = sbase + kWSmemRawG + s * kRawTile + fdg, di = sbase + kWSmemRawI + s * kRawTile + fdi;
+            const float* sg = fsg + (size_t)j * kKB * P.No;
+            const float* si = fsi + (size_t)j * kKB * P.Ki;
+            if (r0 + kKB <= r_end) {
+                if (fg0) cp_async16(dg, sg);
+                if (fg1) cp_async16(dg + (uint32_t)(stepg * kNcMax * 4), sg + (size_t)stepg * P.No);
+                if (fi0) cp_async16(di, si);
+                if (fi1) cp_async16(di + (uint32_t)(stepi * P.Nk * 4), si + (size_t)stepi * P.Ki);
+            } else {                                              // tail K-block: rows past the end are clamped (masked when read)
+                auto back = [&](int rr) { return (size_t)(r0 + rr > r_last ? r0 + rr - r_last : 0); };
+                if (fg0) cp_async16(dg, sg - back(frg) * P.No);
+                if (fg1) cp_async16(dg + (uint32_t)(stepg * kNcMax * 4), sg + ((size_t)stepg - back(frg + stepg)) * P.No);
+                if (fi0) cp_async16(di, si - back(fri) * P.Ki);
+                if (fi1) cp_async16(di + (uint32_t)(stepi * P.Nk * 4), si + ((size_t)stepi - back(fri + stepi)) * P.Ki);
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar(RAW_FULL0 + s)) : "memory");
+        };
+        // ---- per-thread constants of the transform
+        const uint32_t a_rd = (uint32_t)((rg * 8) * kNcMax + nl) * 4u;                     // raw G: rows rg*8.., column nl
+        const uint32_t b_rd0 = (uint32_t)((ch0 * 4) * P.Nk + kl0) * 4u, b_rd1 = (uint32_t)((ch1 * 4) * P.Nk + kl1) * 4u;
+        const uint32_t b_wr0 = swz((uint32_t)kl0, (uint32_t)ch0), b_wr1 = swz((uint32_t)kl1, (uint32_t)ch1);
+        const bool want_bias = kt == 0;
+        for (int j = 0; j < kWStages && j < nkb; ++j) fetch(j);
+        for (int j = 0; j < nkb; ++j) {
+            const uint32_t s = (uint32_t)j % kWStages, use = (uint32_t)j / kWStages;
+            const int nvalid = (int)(r_end - r_begin - (int64_t)j * kKB);       // rows of this K-block that exist (>= 1)
+            const uint8_t* rawg = smem + kWSmemRawG + s * kRawTile;
+            const uint8_t* rawi = smem + kWSmemRawI + s * kRawTile;
+            mbar_wait(bar(RAW_FULL0 + s), use & 1);
+            float a[8], b0[4], b1[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float*>(rawg + a_rd + i * (kNcMax * 4));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                b0[i] = *reinterpret_cast<const float*>(rawi + b_rd0 + i * (P.Nk * 4));
+                b1[i] = has1 ? *reinterpret_cast<const float*>(rawi + b_rd1 + i * (P.Nk * 4)) : 0.f;
+            }
+            if (nvalid < kKB || !n_ok || !has0) {                 // tail K-block / padded tile: mask what does not exist
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (!n_ok || rg * 8 + i >= nvalid) a[i] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (!has0 || ch0 * 4 + i >= nvalid) b0[i] = 0.f;
+                    if (!has1 || ch1 * 4 + i >= nvalid) b1[i] = 0.f;
+                }
+            }
+            mbar_arrive(bar(RAW_EMPTY0 + s));
+            mbar_wait(bar(W_EMPTY0 + s), (use & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t t_hi = lane_base + kColA + s * 64u + (uint32_t)(rg * 8);
+            {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float h = tf32_rna_fast(a[i]);
+                    hi[i] = __float_as_uint(h);
+                    lo[i] = __float_as_uint(a[i] - h);
+                }
+                tmem_st8(t_hi, hi);
+                tmem_st8(t_hi + 32u, lo);
+            }
+            if (want_bias) bsum += (double)(((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])));
+            uint8_t* bst = smem + kWSmemOp + s * kBStage;
+            if (has0) split4(b0, bst + b_wr0);
+            if (has1) split4(b1, bst + b_wr1);
+            tmem_wait_st();
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar(W_FULL0 + s));
+            if (j + kWStages < nkb) fetch(j + kWStages);
+            // flush the previous segment's accumulator once its MMAs have had time to retire
+            if (j % kSegKB == kDrainLag && j >= kSegKB) drain(j / kSegKB - 1);
+        }
+        // segments whose drain point lies beyond the last K-block
+        for (int seg = 0; seg < nseg; ++seg)
+            if ((seg + 1) * kSegKB + kDrainLag >= nkb) drain(seg);
+
+        // ---- partial results: part_w[split][n][k0 + rg*cols_per ...], part_b[split][n] (k-tile 0 only)
+        if (n_ok) {
+            float* dst = P.part_w + ((size_t)split * P.No + n0 + nl) * P.Ki + k0 + rg * cols_per;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < nld) {
+                    reinterpret_cast<float4*>(dst + q * 8)[0] = make_float4(acc[q * 8], acc[q * 8 + 1], acc[q * 8 + 2], acc[q * 8 + 3]);
+                    reinterpret_cast<float4*>(dst + q * 8)[1] = make_float4(acc[q * 8 + 4], acc[q * 8 + 5], acc[q * 8 + 6], acc[q * 8 + 7]);
+                }
+            }
+        }
+        double* sbias = reinterpret_cast<double*>(smem + kWSmemBias);
+        sbias[rg * 128 + nl] = bsum;
+        asm volatile("bar.sync 1, 512;" ::: "memory");             // the 16 worker warps only
+        if (kt == 0 && rg == 0 && n_ok)
+            P.part_b[(size_t)split * P.No + n0 + nl] = ((sbias[nl] + sbias[128 + nl]) + sbias[256 + nl]) + sbias[384 + nl];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+    }
+}
+
+// dW[i] = scale * sum_s part_w[s][i] (fp64, fixed order), db[n] likewise
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part_w, const double* __restrict__ part_b, float* __restrict__ dw,
+                                    float* __restrict__ db, int n_w, int n_b, int splits, float scale) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_w + n_b; i += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        if (i < n_w) {
+            for (int k = 0; k < splits; ++k) s += (double)part_w[(size_t)k * n_w + i];
+            dw[i] = scale * (float)s;
+        } else {
+            const int n = i - n_w;
+            for (int k = 0; k < splits; ++k) s += part_b[(size_t)k * n_b + n];
+            db[n] = scale * (float)s;
+        }
+    }
+}
+
+static bool width_ok(int n) { return n <= kMaxWidth && (n == 32 || n == 64 || (n >= kNcMax && n % kNcMax == 0)); }
+static int chunk_of(int n) { return n < kNcMax ? n : kNcMax; }
+
+struct WgradPlan { int n_tiles, k_tiles, splits, Nk; int64_t rows_per_split; size_t part_w_bytes, part_b_bytes; };
+static WgradPlan wgrad_plan(int No, int Ki, int64_t rows) {
+    WgradPlan p;
+    p.Nk = chunk_of(Ki);
+    p.n_tiles = (No + kTileM - 1) / kTileM;
+    p.k_tiles = Ki / p.Nk;
+    const int tiles = p.n_tiles * p.k_tiles;
+    int splits = kNumSMs / tiles;
+    if (splits < 1) splits = 1;
+    const int64_t seg_rows = (int64_t)kSegKB * kKB;
+    const int64_t max_splits = (rows + seg_rows - 1) / seg_rows;
+    if (splits > max_splits) splits = (int)(max_splits > 0 ? max_splits : 1);
+    int64_t rps = (rows + splits - 1) / splits;
+    rps = (rps + kKB - 1) / kKB * kKB;
+    p.rows_per_split = rps;
+    p.splits = (int)((rows + rps - 1) / rps);
+    if (p.splits < 1) p.splits = 1;
+    p.part_w_bytes = (size_t)p.splits * No * Ki * sizeof(float);
+    p.part_b_bytes = (size_t)p.splits * No * sizeof(double);
+    return p;
+}
+
+}  // namespace wtc
+}  // namespace tdyn
+
+using namespace tdyn;
+
+template <int ACT, int MODE>
+static int launch_lin(const wtc::LinParams& P, int grid, cudaStream_t st) {
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        TDYN_CHECK_CUDA(cudaFuncSetAttribute(wtc::lin_tc_kernel<ACT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, wtc::kLSmemTotal));
+        attr_set = true;
+    }
+    wtc::lin_tc_kernel<ACT, MODE><<<grid, wtc::kThreads, wtc::kLSmemTotal, st>>>(P);
+    TDYN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int tdyn_lin_tc_supported(int n_out, int k_in) {
+    return wtc::width_ok(n_out) && k_in >= 32 && k_in <= wtc::kMaxWidth && k_in % 32 == 0;
+}
+
+int64_t tdyn_lin_tc_image_bytes(int n_out, int k_in) {
+    return tdyn_lin_tc_supported(n_out, k_in) ? (int64_t)n_out * k_in * 8 : 0;
+}
+
+int tdyn_lin_tc_prepare(const float* w, int w_rows, int w_cols, int transpose, void* img, void* stream) {
+    const int n = transpose ? w_cols : w_rows, k = transpose ? w_rows : w_cols;
+    TDYN_REQUIRE(w && img, "tdyn_lin_tc_prepare: null argument");
+    TDYN_REQUIRE(tdyn_lin_tc_supported(n, k), "tdyn_lin_tc_prepare: unsupported layer shape %d x %d", n, k);
+    TDYN_REQUIRE(((uintptr_t)img & 15) == 0, "tdyn_lin_tc_prepare: image must be 16-byte aligned");
+    wtc::lin_prepare_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(w, w_rows, w_cols, transpose, wtc::chunk_of(n), (uint8_t*)img);
+    TDYN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tdyn_lin_tc_apply(const void* img, int n_out, int k_in, const float* in, const float* bias, const float* saved,
+                      float* out, int act, int mode, float scale, int64_t rows, void* stream) {
+    TDYN_REQUIRE(tdyn_lin_tc_supported(n_out, k_in), "tdyn_lin_tc_apply: unsupported layer shape %d x %d", n_out, k_in);
+    TDYN_REQUIRE(img && in && out, "tdyn_lin_tc_apply: null argument");
+    TDYN_REQUIRE(mode >= 0 && mode <= 2, "tdyn_lin_tc_apply: mode must be 0 (linear), 1 (activation) or 2 (times act')");
+    TDYN_REQUIRE(mode == wtc::MODE_LIN || act == TDYN_ACT_TANH || act == TDYN_ACT_SOFTPLUS || act == TDYN_ACT_RELU,
+                 "tdyn_lin_tc_apply: unknown activation");
+    TDYN_REQUIRE(mode != wtc::MODE_DACT || saved, "tdyn_lin_tc_apply: mode 2 needs the saved activations");
+    TDYN_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)img & 15) == 0 &&
+                 (!saved || ((uintptr_t)saved & 15) == 0), "tdyn_lin_tc_apply: pointers must be 16-byte aligned");
+    if (rows <= 0) return 0;
+    wtc::LinParams P{};
+    P.img = (const uint8_t*)img; P.in = in; P.bias = bias; P.saved = saved; P.out = out;
+    P.N = n_out; P.K = k_in; P.Nc = wtc::chunk_of(n_out); P.scale = scale; P.rows = rows;
+    P.num_tiles = (int)((rows + tcx::kTileM - 1) / tcx::kTileM);
+    const int grid = P.num_tiles < kNumSMs ? P.num_tiles : kNumSMs;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == wtc::MODE_LIN) return launch_lin<TDYN_ACT_TANH, wtc::MODE_LIN>(P, grid, st);
+    if (mode == wtc::MODE_ACT) {
+        if (act == TDYN_ACT_TANH) return launch_lin<TDYN_ACT_TANH, wtc::MODE_ACT>(P, grid, st);
+        if (act == TDYN_ACT_SOFTPLUS) return launch_lin<TDYN_ACT_SOFTPLUS, wtc::MODE_ACT>(P, grid, st);
+        return launch_lin<TDYN_ACT_RELU, wtc::MODE_ACT>(P, grid, st);
+    }
+    if (act == TDYN_ACT_TANH) return launch_lin<TDYN_ACT_TANH, wtc::MODE_DACT>(P, grid, st);
+    if (act == TDYN_ACT_SOFTPLUS) return launch_lin<TDYN_ACT_SOFTPLUS, wtc::MODE_DACT>(P, grid, st);
+    return launch_lin<TDYN_ACT_RELU, wtc::MODE_DACT>(P, grid, st);
+}
+
+int64_t tdyn_wgrad_tc_workspace_bytes(int n_out, int k_in, int64_t rows) {
+    if (!(n_out >= 32 && n_out % 32 == 0 && n_out <= wtc::kMaxWidth && wtc::width_ok(k_in)) || rows <= 0) return 0;
+    const wtc::WgradPlan p = wtc::wgrad_plan(n_out, k_in, rows);
+    return (int64_t)(p.part_w_bytes + p.part_b_bytes + 256);
+}
+
+int tdyn_wgrad_tc(const float* g, int n_out, const float* in, int k_in, float* dw, float* db, float scale, void* ws,
+                  int64_t ws_bytes, int64_t rows, void* stream) {
+    TDYN_REQUIRE(n_out >= 32 && n_out % 32 == 0 && n_out <= wtc::kMaxWidth && wtc::width_ok(k_in),
+                 "tdyn_wgrad_tc: unsupported layer shape %d x %d", n_out, k_in);
+    TDYN_REQUIRE(g && in && dw && db && ws, "tdyn_wgrad_tc: null argument");
+    TDYN_REQUIRE(rows > 0, "tdyn_wgrad_tc: rows must be positive");
+    TDYN_REQUIRE(((uintptr_t)ws & 255) == 0, "tdyn_wgrad_tc: workspace must be 256-byte aligned");
+    TDYN_REQUIRE(ws_bytes >= tdyn_wgrad_tc_workspace_bytes(n_out, k_in, rows), "tdyn_wgrad_tc: workspace too small");
+    const wtc::WgradPlan p = wtc::wgrad_plan(n_out, k_in, rows);
+    wtc::WgradParams P{};
+    P.g = g; P.in = in;
+    P.part_w = (float*)ws;
+    P.part_b = (double*)((uint8_t*)ws + ((p.part_w_bytes + 255) & ~(size_t)255));
+    P.No = n_out; P.Ki = k_in; P.Nk = p.Nk; P.n_tiles = p.n_tiles; P.k_tiles = p.k_tiles; P.splits = p.splits;
+    P.rows = rows; P.rows_per_split = p.rows_per_split;
+    cudaStream_t st = (cudaStream_t)stream;
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        TDYN_CHECK_CUDA(cudaFuncSetAttribute(wtc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wtc::kWSmemTotal));
+        attr_set = true;
+    }
+    wtc::wgrad_tc_kernel<<<p.n_tiles * p.k_tiles * p.splits, wtc::kThreads, wtc::kWSmemTotal, st>>>(P);
+    TDYN_CHECK_CUDA(cudaGetLastError());
+    const int n_w = n_out * k_in;
+    wtc::wgrad_reduce_kernel<<<(n_w + n_out + 255) / 256, 256, 0, st>>>(P.part_w, P.part_b, dw, db, n_w, n_out, p.splits, scale);
+    TDYN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

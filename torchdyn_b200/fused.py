@@ -132,6 +132,8 @@ class FusedMLP:
         self._tc_ok = False
         self._ffma_ok = False
         self._ffma_ws = None
+        self._wide_ok = False
+        self._wide_imgs = None
 
     def _params_key(self):
         return tuple((p.data_ptr(), p._version) for m in self.linears for p in (m.weight, m.bias))
@@ -143,6 +145,16 @@ class FusedMLP:
     def ready_ffma(self, kern) -> bool:
         """True if the narrow-net FFMA kernels can run this net."""
         return self._refresh(kern) and self._ffma_ok
+
+    def ready_wide(self, kern) -> bool:
+        """True if the layer-wise tensor-core kernels (tdyn_lin_tc_apply / tdyn_wgrad_tc) can run this net."""
+        return self._refresh(kern) and self._wide_ok
+
+    def wide_images(self, kern):
+        """[(forward image, input-gradient image)] per layer, rebuilt after a parameter update."""
+        if self._wide_imgs is None:
+            self._wide_imgs = [(kern.lin_tc_prepare(m.weight, False), kern.lin_tc_prepare(m.weight, True)) for m in self.linears]
+        return self._wide_imgs
 
     def scratch(self, key, make):
         """Per-network cache of solver scratch buffers (stage storage, ping-pong state, status, trace): they are
@@ -180,9 +192,11 @@ class FusedMLP:
         for i, m in enumerate(self.linears):
             d.w[i] = m.weight.data_ptr()
             d.b[i] = m.bias.data_ptr()
-        self._key, self._desc, self._img = key, d, None
+        self._key, self._desc, self._img, self._wide_imgs = key, d, None, None
         self._tc_ok = kern.mlp_tc_supported(d)
         self._ffma_ok = kern.mlp_ffma_supported(d)
+        self._wide_ok = not self._ffma_ok and all(kern.lin_tc_supported(o, i) and kern.lin_tc_supported(i, o)
+                                                  for i, o in zip(self.dims[:-1], self.dims[1:]))
         if self._tc_ok:
             self._img = kern.mlp_tc_prepare(d)
         return True
@@ -204,7 +218,8 @@ def _get_fused(f) -> Optional[tuple]:
 
 class FusedField:
     """``f`` with a kernel-backed ``tdyn_eval``: the integration loops evaluate the MLP inside this library (FFMA
-    kernel for narrow nets, the tensor-core stage kernel for the 32-256-256-32 class) instead of calling torch.
+    kernel for narrow nets, the tensor-core stage kernel for the 32-256-256-32 class, the layer-wise tensor-core
+    kernels for other wide nets) instead of calling torch.
     ``__call__`` still forwards to the original callable (user code may call it directly)."""
 
     def __init__(self, f, fm: FusedMLP, counters, kern):
@@ -224,11 +239,81 @@ class FusedField:
         out = torch.empty_like(y)
         if fm.ready(kern) and sign == 1.0:
             kern.mlp_tc_stage(fm._desc, fm._img, out, y, [], (), MODE_INNER, 0.0, None, (), fm.flops_per_row)
-        else:
+        elif fm.ready_ffma(kern):
             kern.mlp_ffma_forward(fm._desc, y, out, sign, fm.flops_per_row)
+        else:
+            wide_forward(fm, kern, y, out, sign)
         for c in self.counters:
             c.nfe += 1
         return out
+
+
+LIN_MODE_LINEAR, LIN_MODE_ACT, LIN_MODE_DACT = 0, 1, 2
+
+
+def _aligned(t):
+    """The tensor-core kernels use 128-bit accesses: views at odd offsets of a flat vector are copied."""
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
+def wide_forward(fm: "FusedMLP", kern, y, out, sign: float = 1.0):
+    """Layer-by-layer forward of a wide MLP on the tensor cores (``tdyn_lin_tc_apply``, 3xTF32): hidden layers write
+    their activation outputs (returned: the adjoint reuses them), the last layer writes ``sign * f`` into ``out``
+    (skipped when ``out`` is None: the interpolated adjoint does not need f itself)."""
+    imgs, dims, rows = fm.wide_images(kern), fm.dims, y.numel() // fm.dims[0]
+    L = len(fm.linears)
+    h, saved = _aligned(y), []
+    for l, lin in enumerate(fm.linears):
+        last = l == L - 1
+        if last and out is None:
+            break
+        o = torch.empty(rows, dims[l + 1], dtype=torch.float32, device=y.device) if not last or out.data_ptr() % 16 else out
+        kern.lin_tc_apply(imgs[l][0], dims[l + 1], dims[l], h, lin.bias, None, o, fm.act,
+                          LIN_MODE_LINEAR if last else LIN_MODE_ACT, sign if last else 1.0, rows)
+        if not last:
+            saved.append(o)
+        elif o is not out:
+            out.view(-1).copy_(o.view(-1))
+        h = o
+    return saved
+
+
+class FusedWideAdjoint:
+    """Body of the adjoint dynamics for a wide MLP on the tensor cores: forward (activations kept), then per layer,
+    last to first, the parameter gradient ``-lam^T df/dtheta`` contracted over the batch (``tdyn_wgrad_tc``) and the
+    input gradient (``tdyn_lin_tc_apply`` with the transposed weight image, times act' of the saved activations).
+    Same call signature as FusedAdjoint; ``dx_out`` may be None (interpolated adjoint)."""
+    f_optional = True
+
+    def __init__(self, fm: "FusedMLP", counters, kern):
+        self.fm, self.counters, self.kern = fm, counters, kern
+
+    def __call__(self, x_flat, lam_flat, dx_out, dlam_out, dmu_out, rows, sign):
+        fm, kern = self.fm, self.kern
+        dims, imgs = fm.dims, fm.wide_images(kern)
+        x_flat, lam_flat = _aligned(x_flat), _aligned(lam_flat)
+        saved = wide_forward(fm, kern, x_flat, dx_out, sign)
+        offs, o_ = [], 0
+        for i, o in zip(dims[:-1], dims[1:]):
+            offs.append(o_)
+            o_ += o * i + o
+        g = lam_flat
+        for l in range(len(fm.linears) - 1, -1, -1):
+            i, o = dims[l], dims[l + 1]
+            inp = saved[l - 1] if l > 0 else x_flat
+            ws = fm.scratch(("wgrad", l, rows, x_flat.device.index), lambda: kern.wgrad_tc_workspace(o, i, rows))
+            kern.wgrad_tc(g, o, inp, i, dmu_out[offs[l]:offs[l] + o * i], dmu_out[offs[l] + o * i:offs[l] + o * i + o], -sign, ws, rows)
+            if l > 0:
+                gp = torch.empty(rows, i, dtype=torch.float32, device=x_flat.device)
+                kern.lin_tc_apply(imgs[l][1], i, o, g, None, saved[l - 1], gp, fm.act, LIN_MODE_DACT, 1.0, rows)
+                g = gp
+            else:
+                dl = dlam_out if dlam_out.data_ptr() % 16 == 0 else torch.empty(rows, i, dtype=torch.float32, device=g.device)
+                kern.lin_tc_apply(imgs[0][1], i, o, g, None, None, dl, fm.act, LIN_MODE_LINEAR, -sign, rows)
+                if dl is not dlam_out:
+                    dlam_out.view(-1).copy_(dl.view(-1))
+        for c in self.counters:
+            c.nfe += 1
 
 
 class FusedCNFField:
@@ -308,9 +393,11 @@ def wrap(f, x):
     kern = _kernels.get(x)
     if not getattr(kern, "is_cuda", False) or x.dim() != 2 or x.shape[1] != fm.dims[0]:
         return f
-    if not (fm.ready(kern) or fm.ready_ffma(kern)):
+    if not (fm.ready(kern) or fm.ready_ffma(kern) or fm.ready_wide(kern)):
         return f
-    _last = "fused MLP vector field (tdyn_mlp_tc_stage)" if fm.ready(kern) else "fused MLP vector field (tdyn_mlp_ffma_forward)"
+    _last = ("fused MLP vector field (tdyn_mlp_tc_stage)" if fm.ready(kern) else
+             "fused MLP vector field (tdyn_mlp_ffma_forward)" if fm.ready_ffma(kern) else
+             "wide MLP vector field, layer-wise tcgen05 3xTF32 (tdyn_lin_tc_apply)")
     return FusedField(f, fm, counters, kern)
 
 
@@ -323,8 +410,12 @@ def eval_field(vf, t, x):
         if got is not None:
             fm, counters = got
             kern = _kernels.get(x)
-            if getattr(kern, "is_cuda", False) and x.shape[1] == fm.dims[0] and fm.ready_ffma(kern):
-                out = kern.mlp_ffma_forward(fm._desc, x, torch.empty_like(x), 1.0, fm.flops_per_row)
+            if getattr(kern, "is_cuda", False) and x.shape[1] == fm.dims[0] and (fm.ready_ffma(kern) or fm.ready_wide(kern)):
+                out = torch.empty_like(x)
+                if fm.ready_ffma(kern):
+                    kern.mlp_ffma_forward(fm._desc, x, out, 1.0, fm.flops_per_row)
+                else:
+                    wide_forward(fm, kern, x, out, 1.0)
                 for c in counters:
                     c.nfe += 1
                 return out
@@ -367,12 +458,12 @@ def adjoint_for(vf, x_shape, device) -> Optional[FusedAdjoint]:
     if x_shape[1] != fm.dims[0]:
         return None
     kern = _kernels.get(torch.empty(0, device=device))
-    if not getattr(kern, "is_cuda", False) or not fm.ready_ffma(kern):
+    if not getattr(kern, "is_cuda", False) or not (fm.ready_ffma(kern) or fm.ready_wide(kern)):
         return None
     # the flat parameter vector of the problem must be exactly this net's parameters, in order
     if sum(p.numel() for p in vf.parameters()) != fm.n_params:
         return None
-    return FusedAdjoint(fm, counters, kern)
+    return FusedAdjoint(fm, counters, kern) if fm.ready_ffma(kern) else FusedWideAdjoint(fm, counters, kern)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -107,7 +107,8 @@ class InterpDynamics:
         if self.fused is not None and A.is_contiguous() and x.is_contiguous():
             n, P = self.n, self.P
             out = torch.empty_like(A)
-            scratch = torch.empty_like(x)                     # f(x) itself is not part of [dlam, dmu]
+            # f(x) itself is not part of [dlam, dmu]: kernels that can skip it take None
+            scratch = None if getattr(self.fused, "f_optional", False) else torch.empty_like(x)
             self.fused(x, A[:n], scratch, out[:n], out[n:n + P], self.lam_shape[0], sign)
             return out
         out = self._eval_torch(t_host, A, x)
