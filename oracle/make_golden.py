@@ -150,6 +150,16 @@ def neuralode_cases():
     cases["act_tsit5_interp"] = dict(
         dims=[4, 64, 4], act="tanh", seed=5, gain=4.0, x=xa, y=None, t_span=torch.tensor([0.0, 4.0]), loss="sqmean",
         kw=dict(solver="tsit5", atol=1e-4, rtol=1e-4, sensitivity="interpolated_adjoint"))
+    # wide nets (widths multiples of 32, hidden 256): the layer-wise tensor-core kernels (tdyn_lin_tc_apply / tdyn_wgrad_tc)
+    torch.manual_seed(9)
+    cases["w256_tsit5_interp"] = dict(
+        dims=[32, 256, 32], act="tanh", seed=9, x=torch.randn(256, 32), y=None, t_span=torch.linspace(0, 1, 2),
+        loss="sqmean", kw=dict(solver="tsit5", atol=1e-4, rtol=1e-4, sensitivity="interpolated_adjoint"))
+    torch.manual_seed(10)
+    cases["w256_dopri5_adjoint"] = dict(
+        dims=[64, 256, 64], act="softplus", seed=10, x=torch.randn(128, 64), y=None, t_span=torch.linspace(0, 1, 2),
+        loss="sqmean", kw=dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="adjoint", atol_adjoint=1e-4,
+                               rtol_adjoint=1e-4))
     return cases
 
 
@@ -192,13 +202,17 @@ def functional_cases():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated fixture names (default: all)")
     args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
     from torchdyn.numerics import odeint as ref_odeint
     torch.set_num_threads(1)  # reduction order of torch CPU kernels is thread-count independent for these sizes, but pin it
 
     for name, c in neuralode_cases().items():
+        if only and name not in only:
+            continue
         net = mlp(c["dims"], c["act"], c["seed"], c.get("gain", 1.0))
         loss_fn = (lambda sol, c=c: LOSSES[c["loss"]](sol, c["y"]))
         out = run_ref_neuralode(net, c["x"], c["t_span"], loss_fn, **c["kw"])
@@ -211,6 +225,8 @@ def main():
         print(f"{name}: nfe={out['nfe_total']:.0f} attempts per odeint call={ntr} len(t_eval)={len(out['t_eval'])}")
 
     for name, c in functional_cases().items():
+        if only and name not in only:
+            continue
         net = mlp(c["dims"], c["act"], c["seed"], c.get("gain", 1.0))
         kw = dict(c["kw"])
         if c.get("save_last"):
@@ -233,6 +249,8 @@ def main():
         torch.save(fix, os.path.join(OUT, name + ".pt"))
         print(f"{name}: sol {tuple(sol.shape)} attempts={[len(r['t']) for r in tr.records]}")
 
+    if only:
+        return
     # Van der Pol adjoint (reduced test/test_sensitivity.py:40-76): gradient wrt x0, t_span of 20 points
     for sens in ("adjoint", "interpolated_adjoint"):
         for solver in ("dopri5", "tsit5"):

@@ -63,7 +63,8 @@ LOSSES = {
 }
 
 NEURALODE_CASES = ["c1_moons_dopri5_adjoint", "c1_moons_tsit5_interp", "mlp3_tsit5_adjoint_tspan5",
-                   "mlp_relu_dopri5_interp_tspan4", "c3r_tsit5_interp", "act_dopri5_adjoint", "act_tsit5_interp"]
+                   "mlp_relu_dopri5_interp_tspan4", "c3r_tsit5_interp", "act_dopri5_adjoint", "act_tsit5_interp",
+                   "w256_tsit5_interp", "w256_dopri5_adjoint"]
 FUNCTIONAL_CASES = ["fn_euler_tspan10", "fn_midpoint_tspan10", "fn_rk4_tspan10", "fn_dopri5_tspan10", "fn_tsit5_tspan10",
                     "fn_dopri5_4th_tspan10", "fn_dopri5_reversed", "fn_tsit5_all_eval", "fn_rk4_save_at", "c2r_rk4_100",
                     "act_tsit5_fn", "act_dopri5_4th_fn"]

@@ -182,3 +182,24 @@ def test_wide_neuralode_training_step_matches_generic_path(sens, solver, dims):
     assert res[False][2] == res[True][2], "NFE (step sequence) differs between the fused and the generic path"
     assert_close(res[False][0], res[True][0], "final state", rtol=2e-5, atol_scale=1e-5)
     assert_close(res[False][1], res[True][1], "gradients", rtol=2e-4, atol_scale=2e-5)
+
+
+@pytest.mark.parametrize("name", ["w256_tsit5_interp", "w256_dopri5_adjoint"])
+def test_wide_fixture_runs_on_the_tensor_core_kernels(name):
+    """The executed-reference fixtures with 256-wide nets (test_gpu_parity checks their values) really take the
+    layer-wise tensor-core path: forward and both halves of the VJP are launches of this library."""
+    from conftest import load_golden
+    from parity_helpers import check_neuralode_case, run_neuralode_case
+    fx = load_golden(name)
+    timer = _kernels.KernelTimer()
+    _kernels.set_timer(timer)
+    try:
+        out = run_neuralode_case(fx, DEV)
+    finally:
+        _kernels.set_timer(None)
+    check_neuralode_case(fx, out)
+    names = {r[0] for r in timer.records}
+    assert "lin_tc" in names and "wgrad_tc" in names, names
+    nfe_adj = out["model"].vf.nfe - out["nfe_fwd"]
+    n_layers = len(fx["dims"]) - 1
+    assert sum(r[0] == "wgrad_tc" for r in timer.records) == n_layers * nfe_adj or fx["kw"]["sensitivity"] == "adjoint"
