@@ -396,7 +396,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradParams
         for (int i = 0; i < W_NUM_BARS; ++i) {
             uint32_t cnt = 1;
             if (i >= RAW_FULL0 && i < RAW_FULL0 + kWStages) cnt = 512;      // one cp.async arrive-on per worker thread
-            if (i >= RAW_EMPTY0 && i < RAW_EMPTY0 + kWStages) cnt = 512;
             if (i >= W_FULL0 && i < W_FULL0 + kWStages) cnt = 512;
             if (i >= WACC_EMPTY0 && i < WACC_EMPTY0 + 2) cnt = 512;
             mbar_init(bar(i), cnt);
@@ -448,23 +447,27 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradParams
             }
         }
     } else {
-        // ================= transform (raw tiles -> G^T in TMEM, IN^T in shared memory) + accumulator drains =================
+        // ================= transform (raw sub-tiles -> G^T in TMEM, IN^T in shared memory) + accumulator drains =================
+        // Every warp fetches exactly the raw data it transforms (cp.async into a warp-private 2 KB slice of each raw
+        // stage, two K-blocks ahead, completion by cp.async.wait_group + __syncwarp): no CTA-wide barrier on the raw
+        // tiles, the only cross-warp synchronisation left is the operand ring towards the MMA warp.
         const int quarter = warp & 3;
-        const int rg = (warp - 2) >> 2;                           // 0..3
-        const int tid_w = (warp - 2) * 32 + lane;                 // 0..511
+        const int w = warp - 2;                                   // 0..15
+        const int rg = w >> 2;                                    // 0..3: which 8 of the 32 rows go to TMEM from this warp
         const int nl = quarter * 32 + lane;                       // output feature inside the tile = TMEM lane
-        const bool n_ok = nl < gw;
+        const bool n_ok = quarter * 32 < gw;                      // warp-uniform (gw is a multiple of 32)
         const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
-        const int units = P.Nk * 8;                               // (k, 4-row chunk) units of the B tile
-        const int u0 = tid_w, u1 = tid_w + 512;
-        const int kl0 = u0 % P.Nk, ch0 = u0 / P.Nk, kl1 = u1 % P.Nk, ch1 = u1 / P.Nk;
-        const bool has0 = u0 < units, has1 = u1 < units;
+        const int colb = (w * 32) % P.Nk;                         // B units of this warp: columns colb..colb+31,
+        const int ch0 = (w * 32) / P.Nk, ch1 = ch0 + 4;           // rows 4*ch0..+3 (unit 0) and 4*ch1..+3 (unit 1)
+        const bool has0 = w * 32 < P.Nk * 8, has1 = P.Nk == kNcMax;
         const int cols_per = P.Nk >> 2;                           // accumulator columns this thread drains (multiple of 8)
         const int nld = cols_per >> 3;
+        const bool want_bias = kt == 0;
         float acc[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = 0.f;
         double bsum = 0.0;
+        float bs32 = 0.f;                                         // bias partial of the current segment (<= 64 values)
 
         auto drain = [&](int seg) {
             const uint32_t buf = seg & 1;
@@ -483,7 +486,42 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradParams
             }
             tc_fence_before();
             mbar_arrive(bar(WACC_EMPTY0 + buf));
+            bsum += (double)bs32;
+            bs32 = 0.f;
         };
+
+        // ---- warp-private raw slices: [stage][warp][A: 8 rows x 32 | B0: 4 rows x 32 | B1: 4 rows x 32] fp32
+        const int crow = lane >> 3, cc = lane & 7;                // this lane's 16-byte chunk: row, column chunk
+        const float* gsrc = P.g + (size_t)(r_begin + rg * 8 + crow) * P.No + n0 + quarter * 32 + cc * 4;     // rows crow, crow+4
+        const float* isrc = P.in + (size_t)(r_begin + ch0 * 4 + crow) * P.Ki + k0 + colb + cc * 4;          // unit 0; unit 1: +16 rows
+        const uint32_t raw_w = sbase + kWSmemRawG + (uint32_t)w * 2048u;
+        const uint32_t cdst = raw_w + (uint32_t)(crow * 128 + cc * 16);
+        const int nfull = (int)((r_end - r_begin) / kKB);         // K-blocks whose 32 rows all exist
+        auto issue = [&](int jf, uint32_t stg) {                  // raw data of K-block jf -> stage stg (then one commit group)
+            const uint32_t d = cdst + stg * (2u * kRawTile);
+            if (jf < nfull) {
+                if (n_ok) { cp_async16(d, gsrc); cp_async16(d + 512u, gsrc + (size_t)4 * P.No); }
+                if (has0) cp_async16(d + 1024u, isrc);
+                if (has1) cp_async16(d + 1536u, isrc + (size_t)16 * P.Ki);
+            } else if (jf < nkb) {                                // tail K-block: rows past the end are clamped (masked when read)
+                const int nv = (int)(r_end - r_begin) - jf * kKB;
+                auto back = [&](int rr) { return (size_t)(rr >= nv ? rr - nv + 1 : 0); };
+                if (n_ok) {
+                    cp_async16(d, gsrc - back(rg * 8 + crow) * P.No);
+                    cp_async16(d + 512u, gsrc + ((size_t)4 - back(rg * 8 + crow + 4)) * P.No);
+                }
+                if (has0) cp_async16(d + 1024u, isrc - back(ch0 * 4 + crow) * P.Ki);
+                if (has1) cp_async16(d + 1536u, isrc + ((size_t)16 - back(ch1 * 4 + crow)) * P.Ki);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            gsrc += (size_t)kKB * P.No;
+            isrc += (size_t)kKB * P.Ki;
+        };
+        const float* rd = reinterpret_cast<const float*>(smem + kWSmemRawG) + w * 512 + lane;       // + stage * 2 * kRawTile / 4
+        uint8_t* b_wr0 = smem + kWSmemOp + swz((uint32_t)(colb + lane), (uint32_t)ch0);
+        uint8_t* b_wr1 = smem + kWSmemOp + swz((uint32_t)(colb + lane), (uint32_t)ch1);
+        const uint32_t t_a = lane_base + kColA + (uint32_t)(rg * 8);
+        const uint32_t bar0 = bar(0);
         auto split4 = [&](const float (&v)[4], uint8_t* dst) {
             float4 hi, lo;
             hi.x = tf32_rna_fast(v[0]); lo.x = v[0] - hi.x; hi.y = tf32_rna_fast(v[1]); lo.y = v[1] - hi.y;
@@ -491,71 +529,37 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradParams
             *reinterpret_cast<float4*>(dst) = hi;
             *reinterpret_cast<float4*>(dst + bhalf) = lo;
         };
-        // ---- per-thread constants of the raw-tile fetch (two 16-byte chunks of each operand per K-block)
-        const int gcpr = gw >> 2, icpr = P.Nk >> 2;               // 16-byte chunks per raw row
-        const int64_t r_last = r_end - 1;
-        // chunk ids tid_w and tid_w + 512: same 16-byte column, 512 / (chunks per row) rows further down
-        const int frg = tid_w / gcpr, fri = tid_w / icpr;         // row inside the K-block of the first chunk
-        const int stepg = 512 / gcpr, stepi = 512 / icpr;
-        const bool fg0 = frg < kKB, fg1 = frg + stepg < kKB, fi0 = fri < kKB, fi1 = fri + stepi < kKB;
-        const float* fsg = P.g + (size_t)(r_begin + frg) * P.No + n0 + (tid_w - frg * gcpr) * 4;
-        const float* fsi = P.in + (size_t)(r_begin + fri) * P.Ki + k0 + (tid_w - fri * icpr) * 4;
-        const uint32_t fdg = (uint32_t)(frg * (kNcMax * 4) + (tid_w - frg * gcpr) * 16);
-        const uint32_t fdi = (uint32_t)(fri * (P.Nk * 4) + (tid_w - fri * icpr) * 16);
-        auto fetch = [&](int j) {                                 // raw tiles of K-block j -> ring stage j % kWStages
-            const uint32_t s = (uint32_t)j % kWStages, use = (uint32_t)j / kWStages;
-            const int64_t r0 = r_begin + (int64_t)j * kKB;
-            mbar_wait(bar(RAW_EMPTY0 + s), (use & 1) ^ 1);
-            const uint32_t dg = sbase + kWSmemRawG + s * kRawTile + fdg, di = sbase + kWSmemRawI + s * kRawTile + fdi;
-            const float* sg = fsg + (size_t)j * kKB * P.No;
-            const float* si = fsi + (size_t)j * kKB * P.Ki;
-            if (r0 + kKB <= r_end) {
-                if (fg0) cp_async16(dg, sg);
-                if (fg1) cp_async16(dg + (uint32_t)(stepg * kNcMax * 4), sg + (size_t)stepg * P.No);
-                if (fi0) cp_async16(di, si);
-                if (fi1) cp_async16(di + (uint32_t)(stepi * P.Nk * 4), si + (size_t)stepi * P.Ki);
-            } else {                                              // tail K-block: rows past the end are clamped (masked when read)
-                auto back = [&](int rr) { return (size_t)(r0 + rr > r_last ? r0 + rr - r_last : 0); };
-                if (fg0) cp_async16(dg, sg - back(frg) * P.No);
-                if (fg1) cp_async16(dg + (uint32_t)(stepg * kNcMax * 4), sg + ((size_t)stepg - back(frg + stepg)) * P.No);
-                if (fi0) cp_async16(di, si - back(fri) * P.Ki);
-                if (fi1) cp_async16(di + (uint32_t)(stepi * P.Nk * 4), si + ((size_t)stepi - back(fri + stepi)) * P.Ki);
-            }
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar(RAW_FULL0 + s)) : "memory");
-        };
-        // ---- per-thread constants of the transform
-        const uint32_t a_rd = (uint32_t)((rg * 8) * kNcMax + nl) * 4u;                     // raw G: rows rg*8.., column nl
-        const uint32_t b_rd0 = (uint32_t)((ch0 * 4) * P.Nk + kl0) * 4u, b_rd1 = (uint32_t)((ch1 * 4) * P.Nk + kl1) * 4u;
-        const uint32_t b_wr0 = swz((uint32_t)kl0, (uint32_t)ch0), b_wr1 = swz((uint32_t)kl1, (uint32_t)ch1);
-        const bool want_bias = kt == 0;
-        for (int j = 0; j < kWStages && j < nkb; ++j) fetch(j);
+
+        issue(0, 0);
+        issue(1, 1);
+        uint32_t st = 0, ph = 0, st2 = 2;                         // ring stage / phase parity of K-block j; stage of K-block j + 2
+        int seg_pos = 0;                                          // j % kSegKB
         for (int j = 0; j < nkb; ++j) {
-            const uint32_t s = (uint32_t)j % kWStages, use = (uint32_t)j / kWStages;
-            const int nvalid = (int)(r_end - r_begin - (int64_t)j * kKB);       // rows of this K-block that exist (>= 1)
-            const uint8_t* rawg = smem + kWSmemRawG + s * kRawTile;
-            const uint8_t* rawi = smem + kWSmemRawI + s * kRawTile;
-            mbar_wait(bar(RAW_FULL0 + s), use & 1);
+            issue(j + 2, st2);                                    // (stage st2 was read in the previous iteration)
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
+            __syncwarp();
+            const float* r = rd + st * (2 * kRawTile / 4);
             float a[8], b0[4], b1[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float*>(rawg + a_rd + i * (kNcMax * 4));
+            for (int i = 0; i < 8; ++i) a[i] = n_ok ? r[i * 32] : 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                b0[i] = *reinterpret_cast<const float*>(rawi + b_rd0 + i * (P.Nk * 4));
-                b1[i] = has1 ? *reinterpret_cast<const float*>(rawi + b_rd1 + i * (P.Nk * 4)) : 0.f;
+                b0[i] = has0 ? r[256 + i * 32] : 0.f;
+                b1[i] = has1 ? r[384 + i * 32] : 0.f;
             }
-            if (nvalid < kKB || !n_ok || !has0) {                 // tail K-block / padded tile: mask what does not exist
+            if (j >= nfull) {                                     // tail K-block: mask the rows that do not exist
+                const int nvalid = (int)(r_end - r_begin) - j * kKB;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) if (!n_ok || rg * 8 + i >= nvalid) a[i] = 0.f;
+                for (int i = 0; i < 8; ++i) if (rg * 8 + i >= nvalid) a[i] = 0.f;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    if (!has0 || ch0 * 4 + i >= nvalid) b0[i] = 0.f;
-                    if (!has1 || ch1 * 4 + i >= nvalid) b1[i] = 0.f;
+                    if (ch0 * 4 + i >= nvalid) b0[i] = 0.f;
+                    if (ch1 * 4 + i >= nvalid) b1[i] = 0.f;
                 }
             }
-            mbar_arrive(bar(RAW_EMPTY0 + s));
-            mbar_wait(bar(W_EMPTY0 + s), (use & 1) ^ 1);
+            __syncwarp();                                         // all lanes have read this stage before it is refilled
+            mbar_wait(bar0 + 8u * (W_EMPTY0 + st), ph ^ 1);
             tc_fence_after();
-            const uint32_t t_hi = lane_base + kColA + s * 64u + (uint32_t)(rg * 8);
             {
                 uint32_t hi[8], lo[8];
 #pragma unroll
@@ -564,24 +568,27 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradParams
                     hi[i] = __float_as_uint(h);
                     lo[i] = __float_as_uint(a[i] - h);
                 }
-                tmem_st8(t_hi, hi);
-                tmem_st8(t_hi + 32u, lo);
+                tmem_st8(t_a + st * 64u, hi);
+                tmem_st8(t_a + st * 64u + 32u, lo);
             }
-            if (want_bias) bsum += (double)(((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])));
-            uint8_t* bst = smem + kWSmemOp + s * kBStage;
-            if (has0) split4(b0, bst + b_wr0);
-            if (has1) split4(b1, bst + b_wr1);
+            if (want_bias) bs32 += ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+            if (has0) split4(b0, b_wr0 + st * kBStage);
+            if (has1) split4(b1, b_wr1 + st * kBStage);
             tmem_wait_st();
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bar(W_FULL0 + s));
-            if (j + kWStages < nkb) fetch(j + kWStages);
+            mbar_arrive(bar0 + 8u * (W_FULL0 + st));
             // flush the previous segment's accumulator once its MMAs have had time to retire
-            if (j % kSegKB == kDrainLag && j >= kSegKB) drain(j / kSegKB - 1);
+            if (seg_pos == kDrainLag && j >= kSegKB) drain(j / kSegKB - 1);
+            if (++seg_pos == kSegKB) seg_pos = 0;
+            st2 = st;
+            if (++st == kWStages) { st = 0; ph ^= 1; }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         // segments whose drain point lies beyond the last K-block
         for (int seg = 0; seg < nseg; ++seg)
             if ((seg + 1) * kSegKB + kDrainLag >= nkb) drain(seg);
+        bsum += (double)bs32;
 
         // ---- partial results: part_w[split][n][k0 + rg*cols_per ...], part_b[split][n] (k-tile 0 only)
         if (n_ok) {
