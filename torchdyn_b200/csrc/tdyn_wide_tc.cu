@@ -28,7 +28,8 @@ using namespace tcx;
 constexpr int kKB = 32;                 // K-block: 32 fp32 = 128 B = one swizzle row
 constexpr int kNcMax = 128;             // accumulator tile width
 constexpr int kThreads = 576;           // warp 0 weight producer, warp 1 MMA, warps 2..17 workers
-constexpr int kASlots = 3;              // TMEM ring of A K-blocks: slot = 32 hi + 32 lo columns
+constexpr int kASlots = 4;              // TMEM ring of A K-blocks: slot = 32 hi + 32 lo columns (K10; K <= 128: the whole
+                                        // row tile stays resident and is reused by every output chunk)
 constexpr uint32_t kColAcc0 = 0, kColAcc1 = 128, kColA = 256;
 constexpr uint32_t kTmemCols = 512;
 constexpr int kMaxWidth = 2048;
@@ -126,6 +127,8 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
     const int nchunks = P.N / P.Nc;
     const int nkb = P.K / kKB;
     const int items = my_tiles * nchunks;           // item = (row tile, output chunk); chunk is the fast index
+    const bool resident = nkb <= kASlots;           // A of a row tile fits the TMEM ring: produced once per tile
+    const uint32_t aring = resident ? (uint32_t)nkb : (uint32_t)kASlots;
     const uint32_t slab = (uint32_t)P.Nc * 256u;
 
     if (warp == 0) {
@@ -155,17 +158,21 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
                     tc_fence_after();
                     const uint32_t d = tmem + (buf ? kColAcc1 : kColAcc0);
                     const int kb1 = kb0 + kSegKB < nkb ? kb0 + kSegKB : nkb;
-                    for (int kb = kb0; kb < kb1; ++kb, ++ait, ++bit) {
-                        const uint32_t as = ait % kASlots, au = ait / kASlots, bs = bit % kBStages, bu = bit / kBStages;
-                        mbar_wait(bar(LA_FULL0 + as), au & 1);
+                    const int c = item % nchunks;
+                    for (int kb = kb0; kb < kb1; ++kb, ++bit) {
+                        const uint32_t as = ait % aring, au = ait / aring, bs = bit % kBStages, bu = bit / kBStages;
+                        if (!resident || c == 0) mbar_wait(bar(LA_FULL0 + as), au & 1);
                         mbar_wait(bar(LB_FULL0 + bs), bu & 1);
                         tc_fence_after();
                         const uint32_t a_hi = tmem + kColA + as * 64u;
                         const uint32_t b_hi = sbase + kLSmemB + bs * kBStage;
                         issue_kblock_tt(d, a_hi, a_hi + 32u, b_hi, b_hi + slab / 2, idesc, kb == kb0);
-                        tc_commit(bar(LA_EMPTY0 + as));
+                        if (!resident || c == nchunks - 1) tc_commit(bar(LA_EMPTY0 + as));
                         tc_commit(bar(LB_EMPTY0 + bs));
+                        // resident: the ring position runs over (tile, kb) only and is rewound for every further chunk
+                        ++ait;
                     }
+                    if (resident && kb1 == nkb && c != nchunks - 1) ait -= (uint32_t)nkb;
                     tc_commit(bar(LACC_FULL0 + buf));
                 }
             }
@@ -176,10 +183,11 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
         const int cg = (warp - 2) >> 2;                           // which 16 of the 32 K values
         const int row = quarter * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + kColA + (uint32_t)(cg * 16);
-        const int total = items * nkb;
+        const int total = (resident ? my_tiles : items) * nkb;
+        const int per_tile = resident ? 1 : nchunks;
         auto load = [&](float4 (&r)[4], int n) {
             const int item = n / nkb, kb = n - item * nkb;
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)(item / nchunks) * gridDim.x;
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)(item / per_tile) * gridDim.x;
             const int64_t grow = tile * kTileM + row;
             if (grow < P.rows) {
                 const float4* p = reinterpret_cast<const float4*>(P.in + (size_t)grow * P.K + kb * kKB + cg * 16);
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
             }
         };
         auto emit = [&](const float4 (&r)[4], int n) {
-            const uint32_t as = (uint32_t)n % kASlots, au = (uint32_t)n / kASlots;
+            const uint32_t as = (uint32_t)n % aring, au = (uint32_t)n / aring;
             mbar_wait(bar(LA_EMPTY0 + as), (au & 1) ^ 1);
             tc_fence_after();
             const uint32_t t_hi = lane_addr + as * 64u;
@@ -303,8 +311,10 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] *= dact_from_out<ACT>(a[i]);
                         }
+                        if (P.scale != 1.f) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] *= P.scale;
+                            for (int i = 0; i < 8; ++i) v[i] *= P.scale;
+                        }
                         *st0 = make_float4(v[0], v[1], v[2], v[3]);
                         *st1 = make_float4(v[4], v[5], v[6], v[7]);
                     };
