@@ -18,7 +18,7 @@ from typing import Iterable, List, Optional, Tuple
 
 import torch
 
-_state = {"enabled": False, "group": None, "symm": None, "epoch": 0, "symm_failed": False}
+_state = {"enabled": False, "group": None, "symm": None, "epoch": 0, "symm_failed": False, "replicated_from": None}
 
 
 def enable(group=None):
@@ -78,6 +78,49 @@ def world_size() -> int:
         return 1
     import torch.distributed as dist
     return dist.get_world_size(_state["group"])
+
+
+def rank() -> int:
+    if not _state["enabled"]:
+        return 0
+    import torch.distributed as dist
+    return dist.get_rank(_state["group"])
+
+
+class replicated_tail:
+    """``with replicated_tail(n):`` -- inside, the flat state integrated by ``odeint`` is ``[sharded (n elements of
+    this rank), replicated]``: the tail is identical on every rank (the interpolated adjoint's mu block once its stage
+    derivatives are all-reduced, reference sensitivity.py:124,152 puts mu INSIDE the error norm), so only rank 0
+    contributes it to the global sums of squares and element counts."""
+
+    def __init__(self, n_sharded: int):
+        self.n = int(n_sharded)
+
+    def __enter__(self):
+        self.prev = _state["replicated_from"]
+        if _state["enabled"]:
+            _state["replicated_from"] = self.n
+        return self
+
+    def __exit__(self, *exc):
+        _state["replicated_from"] = self.prev
+        return False
+
+
+def local_norm_count(count: int) -> int:
+    """Of the first ``count`` elements of this rank's flat state, how many this rank contributes to a global norm."""
+    rf = _state["replicated_from"]
+    if not _state["enabled"] or rf is None or rank() == 0:
+        return int(count)
+    return min(int(count), rf)
+
+
+def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    """In-place sum over ranks (no-op when sharding is off)."""
+    if _state["enabled"]:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_state["group"])
+    return t
 
 
 def reduce_sums(kern, n_sums: int, local_count: int) -> Tuple[List[float], int]:

@@ -136,7 +136,7 @@ class _KernelAttempt:
         self.solver, self.atol, self.rtol = solver, atol, rtol
         self.kern = _kernels.get(x)
         self.plan = solver.plan()
-        self.norm_n = _seminorm_count(x, seminorm)
+        self.norm_n = _dist.local_norm_count(_seminorm_count(x, seminorm))
         self.interp = interpolator
         self._bmid = None
 

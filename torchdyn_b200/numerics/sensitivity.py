@@ -17,6 +17,7 @@ import numpy as np
 import torch
 from torch.autograd import Function, grad
 
+from .. import distributed as _dist
 from .odeint import odeint
 from .spline import NaturalCubicSpline
 
@@ -110,9 +111,14 @@ class InterpDynamics:
             # f(x) itself is not part of [dlam, dmu]: kernels that can skip it take None
             scratch = None if getattr(self.fused, "f_optional", False) else torch.empty_like(x)
             self.fused(x, A[:n], scratch, out[:n], out[n:n + P], self.lam_shape[0], sign)
-            return out
-        out = self._eval_torch(t_host, A, x)
-        return out if sign == 1.0 else -out
+        else:
+            out = self._eval_torch(t_host, A, x)
+            out = out if sign == 1.0 else -out
+        if _dist.is_enabled():
+            # batch sharded over ranks: d(mu)/dt is a sum over the batch -> add the per-rank partials so that mu (which
+            # sits INSIDE the error norm here, sensitivity.py:152) is the same global vector on every rank
+            _dist.allreduce_sum_(out[self.n:self.n + self.P])
+        return out
 
     def _eval_torch(self, t_host, A, x):
         lam = A[:self.n].reshape(self.lam_shape)
@@ -197,16 +203,20 @@ def _gather_odefunc_interp_adjoint(vf, vf_params, solver, atol, rtol, interpolat
             dyn = InterpDynamics(vf, spline, lamT.shape, P, integral_loss, device=lamT.device)
             from .. import fused
             solver_obj = solver if not isinstance(solver, str) else None
-            for i in range(len(span) - 1, 0, -1):
-                # forward solver and tolerances, no seminorm (sensitivity.py:152)
-                last = None
-                if solver_obj is not None:
-                    last = fused.try_interp_interval(dyn, A, span[i], span[i - 1], solver_obj, atol, rtol)
-                if last is None:
-                    _, As = odeint(dyn, A, np.array([span[i], span[i - 1]], dtype=np.float32), solver, atol=atol, rtol=rtol)
-                    last = As[-1]
-                A = torch.cat([last[:n] + g_sol[i - 1].flatten(), last[-P:]])
+            with _dist.replicated_tail(n):          # sharded batch: lam is per-rank, mu is replicated (counted once)
+                for i in range(len(span) - 1, 0, -1):
+                    # forward solver and tolerances, no seminorm (sensitivity.py:152)
+                    last = None
+                    if solver_obj is not None:
+                        last = fused.try_interp_interval(dyn, A, span[i], span[i - 1], solver_obj, atol, rtol)
+                    if last is None:
+                        _, As = odeint(dyn, A, np.array([span[i], span[i - 1]], dtype=np.float32), solver, atol=atol, rtol=rtol)
+                        last = As[-1]
+                    A = torch.cat([last[:n] + g_sol[i - 1].flatten(), last[-P:]])
             lam, mu = A[:n].reshape(lamT.shape), A[-P:]
+            if _dist.is_enabled() and _dist.rank() != 0:
+                mu = torch.zeros_like(mu)           # mu is already the global sum: hand it out once, so that the
+                                                    # caller's allreduce_gradients (sum over ranks) stays correct
             return (mu, lam, None, None, None)
 
     return _ODEProblemFunc

@@ -41,8 +41,10 @@ def init_step(f, f0, x0, t0, order, atol, rtol):
     kern = _kernels.get(x0)
     t0 = f32(t0.item() if isinstance(t0, torch.Tensor) else t0)
     x0, f0 = x0.detach(), f0.detach()       # step sizes are constants of the autograd graph
-    kern.init_norms(x0, f0, None, atol, rtol)
-    (s0, s1), count = _dist.reduce_sums(kern, 2, x0.numel())
+    cn = _dist.local_norm_count(x0.numel())     # < numel only for a sharded state with a replicated tail (rank != 0)
+    nv = (lambda v: v) if cn == x0.numel() else (lambda v: v.reshape(-1)[:cn])
+    kern.init_norms(nv(x0), nv(f0), None, atol, rtol)
+    (s0, s1), count = _dist.reduce_sums(kern, 2, cn)
     d0, d1 = rms_from_sumsq(s0, count), rms_from_sumsq(s1, count)
     if d0 < 1e-5 or d1 < 1e-5:
         h0 = f32(1e-6)
@@ -51,8 +53,8 @@ def init_step(f, f0, x0, t0, order, atol, rtol):
     x_new = kern.combine(kern.empty_like(x0), x0, [f0], (1.0,), MODE_CHAIN, h0)     # x0 + h0*f0
     with torch.no_grad():
         f_new = call_vf(kern, f, f32(t0 + h0), x_new)
-    kern.init_norms(x0, f0, f_new, atol, rtol)
-    s2 = _dist.reduce_sums(kern, 3, x0.numel())[0][2]
+    kern.init_norms(nv(x0), nv(f0), nv(f_new), atol, rtol)
+    s2 = _dist.reduce_sums(kern, 3, cn)[0][2]
     d2 = f32(rms_from_sumsq(s2, count) / h0)
     if d1 <= 1e-15 and d2 <= 1e-15:
         h1 = max(f32(1e-6), f32(h0 * f32(1e-3)))
