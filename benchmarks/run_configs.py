@@ -63,6 +63,15 @@ def build(cfg, device, scale=1.0):
         kw = dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="adjoint")
         loss = lambda sol, y=y.to(device): nn.CrossEntropyLoss()(sol[-1], y)   # noqa: E731
         return net, X, torch.linspace(0, 1, 2), kw, loss, "c1 moons 1024x2, MLP 2-64-2, dopri5 1e-4, backsolve adjoint"
+    if cfg == 2:
+        # the north-star headline on the config-2 network: dopri5 forward + backsolve adjoint (not a BASELINE config by
+        # itself: configs[1] is rk4 forward only = bench.py); batch 2^18 so that the adjoint state fits comfortably
+        B = int(262144 * scale)
+        net = mlp([32, 256, 256, 32])
+        X = torch.randn(B, 32)
+        kw = dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="adjoint", atol_adjoint=1e-4, rtol_adjoint=1e-4)
+        return net, X, torch.linspace(0, 1, 2), kw, (lambda sol: sol[-1].pow(2).mean()), \
+            f"c2a dopri5 1e-4 forward + backsolve adjoint, MLP 32-256-256-32, batch {B}"
     if cfg == 3:
         B = int(262144 * scale)
         net = mlp([128, 1024, 128])

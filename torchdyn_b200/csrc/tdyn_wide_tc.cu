@@ -375,13 +375,12 @@ constexpr int kWStages = 3;                         // ring index shared by the 
 constexpr int kDrainLag = 2;                        // segment s is drained after K-block 8(s+1)+2 has been produced
 constexpr uint32_t kRawTile = kKB * kNcMax * 4;     // 16 KB: [32 rows][128 features] fp32 as it lies in global memory
 constexpr uint32_t kWSmemOp = 0;                                     // B operand stages (hi | lo), kBStage each
-constexpr uint32_t kWSmemRawG = kWSmemOp + kWStages * kBStage;       // raw G tiles
-constexpr uint32_t kWSmemRawI = kWSmemRawG + kWStages * kRawTile;    // raw IN tiles
-constexpr uint32_t kWSmemBias = kWSmemRawI + kWStages * kRawTile;    // double[4][128]
+constexpr uint32_t kWSmemRawG = kWSmemOp + kWStages * kBStage;       // raw fp32 data: [stage][16 warps][2 KB] (G rows | IN rows)
+constexpr uint32_t kWSmemBias = kWSmemRawG + kWStages * 2 * kRawTile;    // double[4][128]
 constexpr uint32_t kWSmemBars = kWSmemBias + 4 * 128 * 8;
 constexpr uint32_t kWSmemTotal = kWSmemBars + 256 + 1024;
-enum WBar { RAW_FULL0 = 0, RAW_EMPTY0 = RAW_FULL0 + kWStages, W_FULL0 = RAW_EMPTY0 + kWStages, W_EMPTY0 = W_FULL0 + kWStages,
-            WACC_FULL0 = W_EMPTY0 + kWStages, WACC_EMPTY0 = WACC_FULL0 + 2, W_NUM_BARS = WACC_EMPTY0 + 2 };
+enum WBar { W_FULL0 = 0, W_EMPTY0 = W_FULL0 + kWStages, WACC_FULL0 = W_EMPTY0 + kWStages, WACC_EMPTY0 = WACC_FULL0 + 2,
+            W_NUM_BARS = WACC_EMPTY0 + 2 };
 
 struct WgradParams {
     const float* g;            // [rows][No]
@@ -405,7 +404,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradParams
     if (threadIdx.x == 0) {
         for (int i = 0; i < W_NUM_BARS; ++i) {
             uint32_t cnt = 1;
-            if (i >= RAW_FULL0 && i < RAW_FULL0 + kWStages) cnt = 512;      // one cp.async arrive-on per worker thread
             if (i >= W_FULL0 && i < W_FULL0 + kWStages) cnt = 512;
             if (i >= WACC_EMPTY0 && i < WACC_EMPTY0 + 2) cnt = 512;
             mbar_init(bar(i), cnt);
@@ -433,8 +431,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradParams
     const uint32_t bhalf = (uint32_t)P.Nk * 128u;
 
     if (warp == 0) {
-        // idle: the raw tiles are fetched by the worker threads themselves with cp.async (16 bytes per request,
-        // coalesced along the rows, completion counted on an mbarrier; many small bulk copies were 4x slower)
+        // idle: every worker warp fetches its own raw sub-tiles with cp.async (64 bulk copies of 512 B per K-block
+        // issued from here were 4x slower than the tensor pipe; a CTA-wide cp.async stage still 2x slower)
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
