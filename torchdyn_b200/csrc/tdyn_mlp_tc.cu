@@ -69,10 +69,10 @@ __device__ __forceinline__ void store_split8(uint8_t* stage, int row, int sub, c
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         float4 hi, lo;
-        hi.x = tf32_rna(a[4 * i + 0]); lo.x = a[4 * i + 0] - hi.x;
-        hi.y = tf32_rna(a[4 * i + 1]); lo.y = a[4 * i + 1] - hi.y;
-        hi.z = tf32_rna(a[4 * i + 2]); lo.z = a[4 * i + 2] - hi.z;
-        hi.w = tf32_rna(a[4 * i + 3]); lo.w = a[4 * i + 3] - hi.w;
+        hi.x = tf32_rna_fast(a[4 * i + 0]); lo.x = a[4 * i + 0] - hi.x;
+        hi.y = tf32_rna_fast(a[4 * i + 1]); lo.y = a[4 * i + 1] - hi.y;
+        hi.z = tf32_rna_fast(a[4 * i + 2]); lo.z = a[4 * i + 2] - hi.z;
+        hi.w = tf32_rna_fast(a[4 * i + 3]); lo.w = a[4 * i + 3] - hi.w;
         const uint32_t off = swz((uint32_t)row, (uint32_t)(sub * 2 + i));
         *reinterpret_cast<float4*>(stage + off) = hi;
         *reinterpret_cast<float4*>(stage + kATile + off) = lo;
@@ -85,7 +85,7 @@ __device__ __forceinline__ void store_split8_tmem(uint32_t taddr, uint8_t* lo_ti
     float lo[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float h = tf32_rna(a[i]);
+        const float h = tf32_rna_fast(a[i]);
         hi[i] = __float_as_uint(h);
         lo[i] = a[i] - h;
     }

@@ -73,7 +73,7 @@ __device__ __forceinline__ void split8_to_tmem(uint32_t t_hi, uint32_t t_lo, con
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float h = tf32_rna(a[i]);
+        const float h = tf32_rna_fast(a[i]);
         hi[i] = __float_as_uint(h);
         lo[i] = __float_as_uint(a[i] - h);
     }
