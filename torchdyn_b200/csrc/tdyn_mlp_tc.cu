@@ -62,6 +62,16 @@ struct Params {
 };
 
 
+// act(acc + bias); for tanh `bias` is the pre-scaled value (see the bias staging in the kernel)
+template <int ACT>
+__device__ __forceinline__ float activate_biased(float acc, float bias) {
+    if (ACT != TDYN_ACT_TANH) return activate<ACT>(acc + bias);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(acc, kTanhScale, bias)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return fmaf(-2.f, r, 1.f);
+}
+
 // hi = rna_tf32(a) (exactly representable: the tensor core's truncation is a no-op); lo = a - hi is exact in fp32 and
 // is truncated to TF32 by the tensor core (error 2^-22 |a|).
 // layer-1 operand: both parts to shared memory (K-major, 128B swizzle)
@@ -202,8 +212,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
     }
     {   // biases -> shared memory (the L1 is almost entirely carved out as shared memory: global re-reads would go to L2)
         float* sb = reinterpret_cast<float*>(smem + kSmemBias);
+        // tanh: the hidden-layer biases are stored pre-multiplied by 2*log2(e) so that bias add and argument scaling of
+        // tanh(z) = 1 - 2/(1 + 2^(2z*log2e)) are one FMA in the epilogue
+        const float bscale = ACT == TDYN_ACT_TANH ? kTanhScale : 1.f;
         for (int i = threadIdx.x; i < 2 * kH + kD; i += kThreads)
-            sb[i] = i < kH ? __ldg(P.b1 + i) : (i < 2 * kH ? __ldg(P.b2 + i - kH) : __ldg(P.b3 + i - 2 * kH));
+            sb[i] = i < kH ? bscale * __ldg(P.b1 + i) : (i < 2 * kH ? bscale * __ldg(P.b2 + i - kH) : __ldg(P.b3 + i - 2 * kH));
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols));
@@ -351,10 +364,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                     const float4 b0 = *reinterpret_cast<const float4*>(bias + j * kKB);
                     const float4 b1 = *reinterpret_cast<const float4*>(bias + j * kKB + 4);
                     float v[8];
-                    v[0] = activate<ACT>(__uint_as_float(cur[0]) + b0.x); v[1] = activate<ACT>(__uint_as_float(cur[1]) + b0.y);
-                    v[2] = activate<ACT>(__uint_as_float(cur[2]) + b0.z); v[3] = activate<ACT>(__uint_as_float(cur[3]) + b0.w);
-                    v[4] = activate<ACT>(__uint_as_float(cur[4]) + b1.x); v[5] = activate<ACT>(__uint_as_float(cur[5]) + b1.y);
-                    v[6] = activate<ACT>(__uint_as_float(cur[6]) + b1.z); v[7] = activate<ACT>(__uint_as_float(cur[7]) + b1.w);
+                    v[0] = activate_biased<ACT>(__uint_as_float(cur[0]), b0.x); v[1] = activate_biased<ACT>(__uint_as_float(cur[1]), b0.y);
+                    v[2] = activate_biased<ACT>(__uint_as_float(cur[2]), b0.z); v[3] = activate_biased<ACT>(__uint_as_float(cur[3]), b0.w);
+                    v[4] = activate_biased<ACT>(__uint_as_float(cur[4]), b1.x); v[5] = activate_biased<ACT>(__uint_as_float(cur[5]), b1.y);
+                    v[6] = activate_biased<ACT>(__uint_as_float(cur[6]), b1.z); v[7] = activate_biased<ACT>(__uint_as_float(cur[7]), b1.w);
                     const uint32_t as = ait % kLoStages, au = ait / kLoStages;
                     mbar_wait(bar(A_EMPTY0 + as), (au & 1) ^ 1);
                     store_split8_tmem(src + (uint32_t)(j * kKB), smem + kSmemLoRing + as * kATile, w.row, w.sub, v);
