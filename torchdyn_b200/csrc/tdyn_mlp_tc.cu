@@ -21,6 +21,7 @@
 // The next tile's stage input is produced during layer 2; its layer 1 is issued once this tile's output left TMEM.
 // Algorithmic work: 163 840 FLOP per sample-NFE (x3 issued as TF32).  HBM traffic is negligible (128-256 B per
 // sample-NFE), the bound is the tensor pipe with the activation epilogue (512 tanh per sample-NFE) next.
+#include <cuda_bf16.h>
 #include "tdyn_tc_ptx.cuh"
 
 namespace tdyn {
@@ -72,64 +73,69 @@ __device__ __forceinline__ float activate_biased(float acc, float bias) {
     return fmaf(-2.f, r, 1.f);
 }
 
-// hi = rna_tf32(a) (exactly representable: the tensor core's truncation is a no-op); lo = a - hi is exact in fp32 and
-// is truncated to TF32 by the tensor core (error 2^-22 |a|).
-// layer-1 operand: both parts to shared memory (K-major, 128B swizzle)
-__device__ __forceinline__ void store_split8(uint8_t* stage, int row, int sub, const float (&a)[8]) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        float4 hi, lo;
-        hi.x = tf32_rna_fast(a[4 * i + 0]); lo.x = a[4 * i + 0] - hi.x;
-        hi.y = tf32_rna_fast(a[4 * i + 1]); lo.y = a[4 * i + 1] - hi.y;
-        hi.z = tf32_rna_fast(a[4 * i + 2]); lo.z = a[4 * i + 2] - hi.z;
-        hi.w = tf32_rna_fast(a[4 * i + 3]); lo.w = a[4 * i + 3] - hi.w;
-        const uint32_t off = swz((uint32_t)row, (uint32_t)(sub * 2 + i));
-        *reinterpret_cast<float4*>(stage + off) = hi;
-        *reinterpret_cast<float4*>(stage + kATile + off) = lo;
-    }
+// Split precision: a = hi + lo with hi = rna_tf32(a) (exactly representable in TF32) and lo = a - hi (exact in fp32,
+// |lo| <= 2^-12 |a|).  D = A_hi*W_hi runs as kind::tf32; the two correction terms A_hi*W_lo + A_lo*W_hi are 2^-11 of
+// the result and only need ~10 significant bits, so they run as ONE kind::f16 (bf16) chain over a concatenated K:
+// A' = [bf16(a_hi) | bf16(a_lo)] (one 128-byte row per batch row = 64 bf16), W' = [bf16(w_lo) ; bf16(w_hi)].  A bf16 MMA
+// covers K = 16 in the cycles a TF32 MMA needs for K = 8: a K-block of 32 costs 4 TF32 + 4 BF16 MMAs instead of the 12
+// TF32 MMAs of plain 3xTF32 (2/3 of the tensor-pipe time; the kernel is power-limited on the tensor pipe).  The bf16
+// rounding of the correction operands adds ~2^-21 relative per product, below the accumulator's truncation noise.
+__device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(lo_elem, hi_elem);     // .x (low 16 bits) = element at the lower address
+    return *reinterpret_cast<const uint32_t*>(&p);
 }
-// hidden-layer operand: hi back into TMEM IN PLACE of the accumulator columns it came from (A-from-TMEM MMAs read it
-// without touching shared memory), lo into the shared-memory ring
-__device__ __forceinline__ void store_split8_tmem(uint32_t taddr, uint8_t* lo_tile, int row, int sub, const float (&a)[8]) {
-    uint32_t hi[8];
-    float lo[8];
+// the correction tile row: 16-byte chunk `sub` holds bf16(hi) of k = 8*sub..8*sub+7, chunk 4+sub holds bf16(lo)
+__device__ __forceinline__ void store_corr8(uint8_t* tile, int row, int sub, const float (&hi)[8], const float (&lo)[8]) {
+    *reinterpret_cast<uint4*>(tile + swz((uint32_t)row, (uint32_t)sub)) =
+        make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
+    *reinterpret_cast<uint4*>(tile + swz((uint32_t)row, (uint32_t)(4 + sub))) =
+        make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+}
+// layer-1 operand: TF32 hi tile + bf16 correction tile, both in shared memory (K-major, 128B swizzle)
+__device__ __forceinline__ void store_split8(uint8_t* stage, int row, int sub, const float (&a)[8]) {
+    float hi[8], lo[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float h = tf32_rna_fast(a[i]);
-        hi[i] = __float_as_uint(h);
-        lo[i] = a[i] - h;
-    }
-    tmem_st8(taddr, hi);
+    for (int i = 0; i < 8; ++i) { hi[i] = tf32_rna_fast(a[i]); lo[i] = a[i] - hi[i]; }
 #pragma unroll
     for (int i = 0; i < 2; ++i)
-        *reinterpret_cast<float4*>(lo_tile + swz((uint32_t)row, (uint32_t)(sub * 2 + i))) =
-            make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+        *reinterpret_cast<float4*>(stage + swz((uint32_t)row, (uint32_t)(sub * 2 + i))) =
+            make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+    store_corr8(stage + kATile, row, sub, hi, lo);
+}
+// hidden-layer operand: TF32 hi back into TMEM IN PLACE of the accumulator columns it came from (A-from-TMEM MMAs read
+// it without touching shared memory), the bf16 correction tile into the shared-memory ring
+__device__ __forceinline__ void store_split8_tmem(uint32_t taddr, uint8_t* corr_tile, int row, int sub, const float (&a)[8]) {
+    uint32_t hiu[8];
+    float hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        hi[i] = tf32_rna_fast(a[i]);
+        hiu[i] = __float_as_uint(hi[i]);
+        lo[i] = a[i] - hi[i];
+    }
+    tmem_st8(taddr, hiu);
+    store_corr8(corr_tile, row, sub, hi, lo);
     tmem_wait_st();
 }
 
-// one 3xTF32 K-block (32 wide): D (+)= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, 4 MMAs of K = 8 per term
-__device__ __forceinline__ void issue_kblock(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                             uint32_t idesc, bool first) {
-    const uint32_t A[3] = {a_lo, a_hi, a_hi};
-    const uint32_t B[3] = {b_hi, b_lo, b_hi};
+// one K-block (32 wide) with all operands in shared memory: D (+)= A'*W' (4 bf16 MMAs, K = 16) + A_hi*W_hi (4 TF32 MMAs)
+__device__ __forceinline__ void issue_kblock(uint32_t d_tmem, uint32_t a_hi, uint32_t a_corr, uint32_t b_hi, uint32_t b_corr,
+                                             int n, bool first) {
+    const uint32_t id32 = umma_idesc(n), id16 = umma_idesc_bf16(n);
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
+    for (int k = 0; k < 4; ++k) tc_mma_bf16(d_tmem, umma_desc(a_corr + k * 32), umma_desc(b_corr + k * 32), id16, (first && k == 0) ? 0u : 1u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            tc_mma_tf32(d_tmem, umma_desc(A[t] + k * 32), umma_desc(B[t] + k * 32), idesc, (first && t == 0 && k == 0) ? 0u : 1u);
-        }
-    }
+    for (int k = 0; k < 4; ++k) tc_mma_tf32(d_tmem, umma_desc(a_hi + k * 32), umma_desc(b_hi + k * 32), id32, 1u);
 }
 
-// hidden-layer K-block: A_hi in TMEM (32 columns at a_hi_tmem), A_lo in shared memory
-__device__ __forceinline__ void issue_kblock_ts(uint32_t d_tmem, uint32_t a_hi_tmem, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                                uint32_t idesc, bool first) {
+// hidden-layer K-block: A_hi in TMEM (32 columns at a_hi_tmem), the correction tile in shared memory
+__device__ __forceinline__ void issue_kblock_ts(uint32_t d_tmem, uint32_t a_hi_tmem, uint32_t a_corr, uint32_t b_hi, uint32_t b_corr,
+                                                int n, bool first) {
+    const uint32_t id32 = umma_idesc(n), id16 = umma_idesc_bf16(n);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) tc_mma_tf32(d_tmem, umma_desc(a_lo + k * 32), umma_desc(b_hi + k * 32), idesc, (first && k == 0) ? 0u : 1u);
+    for (int k = 0; k < 4; ++k) tc_mma_bf16(d_tmem, umma_desc(a_corr + k * 32), umma_desc(b_corr + k * 32), id16, (first && k == 0) ? 0u : 1u);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d_tmem, a_hi_tmem + k * 8, umma_desc(b_lo + k * 32), idesc, 1u);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d_tmem, a_hi_tmem + k * 8, umma_desc(b_hi + k * 32), idesc, 1u);
+    for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d_tmem, a_hi_tmem + k * 8, umma_desc(b_hi + k * 32), id32, 1u);
 }
 
 struct WorkerCtx {
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                 mbar_wait(bar(W_FULL0 + slot), use & 1);
                 tc_fence_after();
                 const uint32_t w = sbase + kSmemWRing + slot * kWStage;
-                issue_kblock(tmem + kColD1, a1, a1 + kATile, w, w + kWStage / 2, umma_idesc(kNSplit), true);
+                issue_kblock(tmem + kColD1, a1, a1 + kATile, w, w + kWStage / 2, kNSplit, true);
                 tc_commit(bar(W_EMPTY0 + slot));
                 tc_commit(bar(D1_FULL));
                 ++wit;
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                 mbar_wait(bar(W1B_FULL), t & 1);
                 tc_fence_after();
                 const uint32_t w = sbase + kSmemW1B;
-                issue_kblock(tmem + kColD1 + kNSplit, a1, a1 + kATile, w, w + 4096u, umma_idesc(kH - kNSplit), true);
+                issue_kblock(tmem + kColD1 + kNSplit, a1, a1 + kATile, w, w + 4096u, kH - kNSplit, true);
                 tc_commit(bar(W1B_EMPTY));
                 tc_commit(bar(D1B_FULL));
             };
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                     tc_fence_after();
                     const uint32_t w = sbase + kSmemWRing + ws * kWStage;
                     issue_kblock_ts(tmem + kColD2, tmem + kColD1 + (uint32_t)(j * kKB), sbase + kSmemLoRing + as * kATile,
-                                    w, w + kWStage / 2, umma_idesc(kH), j == 0);
+                                    w, w + kWStage / 2, kH, j == 0);
                     tc_commit(bar(W_EMPTY0 + ws));
                     tc_commit(bar(A_EMPTY0 + as));
                 }
@@ -311,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                         tc_fence_after();
                         const uint32_t wj = w + (uint32_t)j * 8192u;
                         issue_kblock_ts(tmem + kColD3, tmem + kColD2 + (uint32_t)(j * kKB), sbase + kSmemLoRing + as * kATile,
-                                        wj, wj + 4096u, umma_idesc(kD), j == 0);
+                                        wj, wj + 4096u, kD, j == 0);
                         tc_commit(bar(A_EMPTY0 + as));
                     }
                     tc_commit(bar(W_EMPTY0 + ws));
@@ -442,34 +448,31 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
 __global__ void prepare_weights_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
                                        const float* __restrict__ w3, uint8_t* __restrict__ img) {
     const int total = kD * kH + kH * kH + kH * kD;
+    // per K-block slab: TF32 part [n][32 k] fp32 (row = 128 B) at `hi`, correction part W' [n][64 k'] bf16 (row = 128 B) at
+    // `corr`: k' = kk holds bf16(w_lo) (pairs with bf16(a_hi)), k' = 32 + kk holds bf16(w_hi) (pairs with bf16(a_lo))
+    auto put = [&](size_t hi, size_t corr, int n, int kk, float w) {
+        const float h = tf32_rna(w);
+        *reinterpret_cast<float*>(img + hi + swz(n, kk >> 2) + (kk & 3) * 4) = h;
+        *reinterpret_cast<__nv_bfloat16*>(img + corr + swz(n, kk >> 3) + (kk & 7) * 2) = __float2bfloat16_rn(w - h);
+        *reinterpret_cast<__nv_bfloat16*>(img + corr + swz(n, 4 + (kk >> 3)) + (kk & 7) * 2) = __float2bfloat16_rn(h);
+    };
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        float w;
-        size_t hi_off, lo_off;
         if (idx < kD * kH) {                       // W1[n][k], n < 256, k < 32
             const int n = idx / kD, k = idx % kD;
-            w = w1[idx];
-            hi_off = swz(n, k >> 2) + (k & 3) * 4;
-            lo_off = hi_off + kWStage / 2;
+            put(0, kWStage / 2, n, k, w1[idx]);
             if (n >= kNSplit) {                    // duplicate rows 224..255 into the W1B slab (stage index 10)
-                const size_t o = (size_t)kWStagesPerTile * kWStage + swz(n - kNSplit, k >> 2) + (k & 3) * 4;
-                const float h = tf32_rna(w);
-                *reinterpret_cast<float*>(img + o) = h;
-                *reinterpret_cast<float*>(img + o + 4096) = tf32_rna(w - h);
+                const size_t o = (size_t)kWStagesPerTile * kWStage;
+                put(o, o + 4096, n - kNSplit, k, w1[idx]);
             }
         } else if (idx < kD * kH + kH * kH) {      // W2[n][k]
             const int e = idx - kD * kH, n = e / kH, k = e % kH, kb = k / kKB, kk = k % kKB;
-            w = w2[e];
-            hi_off = (size_t)(1 + kb) * kWStage + swz(n, kk >> 2) + (kk & 3) * 4;
-            lo_off = hi_off + kWStage / 2;
+            const size_t o = (size_t)(1 + kb) * kWStage;
+            put(o, o + kWStage / 2, n, kk, w2[e]);
         } else {                                   // W3[n][k], n < 32, k < 256
             const int e = idx - kD * kH - kH * kH, n = e / kH, k = e % kH, kb = k / kKB, kk = k % kKB;
-            w = w3[e];
-            hi_off = (size_t)9 * kWStage + (size_t)kb * 8192 + swz(n, kk >> 2) + (kk & 3) * 4;
-            lo_off = hi_off + 4096;
+            const size_t o = (size_t)9 * kWStage + (size_t)kb * 8192;
+            put(o, o + 4096, n, kk, w3[e]);
         }
-        const float hi = tf32_rna(w);
-        *reinterpret_cast<float*>(img + hi_off) = hi;
-        *reinterpret_cast<float*>(img + lo_off) = tf32_rna(w - hi);
     }
 }
 
