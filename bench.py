@@ -252,18 +252,22 @@ def main():
         name, a = max(agg.items(), key=lambda kv: kv[1]["ms"])
         per_launch_ms = a["ms"] / a["launches"]
         if name.startswith("mlp_tc"):
-            # tensor bound: algorithmic FLOP/s against the 3xTF32 ceiling = measured bf16 peak / 6
+            # tensor bound.  Per algorithmic FLOP the kernel issues one TF32 MMA FLOP (= 2 bf16-equivalents: TF32 dense
+            # runs at half the bf16 rate) plus a bf16 correction chain over a concatenated K of twice the length
+            # (a_hi*w_lo + a_lo*w_hi = 2 bf16 FLOPs): 4 bf16-equivalent FLOPs, so the ceiling is measured bf16 peak / 4.
+            # (plain 3xTF32 would issue 6: its ceiling, bf16/6, is reported next to it for comparison with earlier lines)
             achieved = a["work"] / (a["ms"] * 1e-3) / 1e12
-            peak = pk["bf16_sustained"] / 6.0
+            peak = pk["bf16_sustained"] / 4.0
             traffic = None
             tp = os.path.join(ROOT, "profiles", "k2_traffic.json")
             if os.path.exists(tp):
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")     # from the committed ncu --set full capture
             roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic,
+                    "frac_of_plain_3xtf32_ceiling": achieved / (pk["bf16_sustained"] / 6.0),
                     "note": "achieved = algorithmic fp32-equivalent FLOP/s (2*sum(in*out) per sample-NFE); each is issued "
-                            "as 3 TF32 MMAs (hi*hi + lo*hi + hi*lo); TF32 dense = 1/2 of bf16 dense, so the ceiling is "
-                            f"bf16_sustained/6 of {pk['src']}; issued-TF32 TFLOP/s = 3x achieved"}
+                            "as 1 TF32 MMA (hi*hi) + a bf16 MMA chain of double K (hi*lo + lo*hi) = 4 bf16-equivalent "
+                            f"tensor FLOPs, so the ceiling is bf16_sustained/4 of {pk['src']}"}
         else:
             achieved = a["work"] / (a["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s",

@@ -1,4 +1,4 @@
-// K2: tensor-core (tcgen05 / TMEM, 3xTF32) stage kernel for wide MLP vector fields on sm_100a.
+// K2: tensor-core (tcgen05 / TMEM, split precision: TF32 + bf16 corrections) stage kernel for wide MLP vector fields on sm_100a.
 //
 //   y     = combine(x, k[], coef, mode, dt)                  (reference numerics/solvers/ode.py:100-103,148-153)
 //   k_out = W3 act(W2 act(W1 y + b1) + b2) + b3              (the nn.Sequential vector field, f(t, y))
@@ -6,20 +6,22 @@
 //
 // Shape class (BASELINE.json configs[1]): state dim D = 32, two hidden layers of width 256, three Linear layers.
 // One persistent CTA per SM walks 128-row tiles of the batch.  Per tile:
-//   workers (16 warps) : load x/k rows, combine in the reference's rounding order, split y into TF32 hi/lo and
-//                        store it K-major / 128B-swizzled in shared memory (the UMMA canonical layout);
-//   MMA warp (1 thread): layer 1 as tcgen05.mma kind::tf32  D1[128x256] (TMEM cols 0..255 = X)
-//                        = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (3xTF32: fp32-accurate products, fp32 accumulate);
+//   workers (16 warps) : load x/k rows, combine in the reference's rounding order, split y = hi + lo (hi = TF32) and
+//                        store the TF32 tile and the bf16 correction tile [bf16(hi) | bf16(lo)] K-major / 128B-swizzled in
+//                        shared memory (the UMMA canonical layout);
+//   MMA warp (1 thread): layer 1 D1[128x256] (TMEM cols 0..255 = X) = A_hi*W_hi as tcgen05.mma kind::tf32 plus
+//                        A_hi*W_lo + A_lo*W_hi as ONE kind::f16 (bf16) chain over the concatenated K (see store_corr8):
+//                        fp32-accurate products, fp32 accumulate, 2/3 of the tensor time of plain 3xTF32;
 //   workers            : X -> registers (tcgen05.ld, next chunk prefetched), +bias (shared memory), activation, split:
-//                        hi goes back into the SAME TMEM columns (tcgen05.st) and is consumed by A-from-TMEM MMAs,
-//                        lo goes through a 3-stage shared-memory ring; one 32-wide K-block at a time, so layer 2's MMAs
+//                        hi goes back into the SAME TMEM columns (tcgen05.st) and is consumed by A-from-TMEM MMAs, the
+//                        correction tile goes through a 3-stage shared-memory ring; one 32-wide K-block at a time, so layer 2's MMAs
 //                        (TMEM cols 256..511 = Y) start while later K-blocks are still being produced; same again for
 //                        layer 3 (N = 32, A_hi = Y in place, accumulator X[0,32));
 //   producer (1 thread): streams the pre-split, pre-swizzled weight images (tdyn_mlp_tc_prepare) from L2 into a
 //                        2 x 64 KB ring with cp.async.bulk + mbarrier complete_tx (weights total 640 KB per tile pass:
 //                        they cannot stay resident in 227 KB of shared memory).
 // The next tile's stage input is produced during layer 2; its layer 1 is issued once this tile's output left TMEM.
-// Algorithmic work: 163 840 FLOP per sample-NFE (x3 issued as TF32).  HBM traffic is negligible (128-256 B per
+// Algorithmic work: 163 840 FLOP per sample-NFE (issued as 1 TF32 + 2 bf16 FLOPs = 4 bf16-equivalents).  HBM traffic is negligible (128-256 B per
 // sample-NFE), the bound is the tensor pipe with the activation epilogue (512 tanh per sample-NFE) next.
 #include <cuda_bf16.h>
 #include "tdyn_tc_ptx.cuh"

@@ -678,5 +678,5 @@ def try_fixed(f, x, ts, sv, solver) -> Optional[List[torch.Tensor]]:
                 dt = f32(ts[step + 1] - t)
     for c in counters:
         c.nfe += n_stage * (len(ts) - 1)
-    _last = "fused tcgen05 3xTF32 MLP stage kernel (tdyn_mlp_tc_stage)"
+    _last = "fused tcgen05 split-precision (TF32 + bf16 corrections) MLP stage kernel (tdyn_mlp_tc_stage)"
     return sol
