@@ -18,6 +18,7 @@
 // K-major swizzled layout by the store pattern; the accumulator is flushed into fp32 registers every 256 rows so the
 // tensor core's truncating accumulation never runs over more than 96 partial sums; per-CTA partials are reduced in a
 // fixed order by a second kernel (deterministic).
+#include <cuda_bf16.h>
 #include "tdyn_tc_ptx.cuh"
 
 namespace tdyn {
@@ -69,27 +70,42 @@ __device__ __forceinline__ float dact_from_out(float a) {
     return fmaf(-a, a, 1.f);                                  // 1 - tanh^2
 }
 
-__device__ __forceinline__ void split8_to_tmem(uint32_t t_hi, uint32_t t_lo, const float (&a)[8]) {
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float h = tf32_rna_fast(a[i]);
-        hi[i] = __float_as_uint(h);
-        lo[i] = __float_as_uint(a[i] - h);
-    }
-    tmem_st8(t_hi, hi);
-    tmem_st8(t_lo, lo);
+// Split precision (same scheme as the fused stage kernel, tdyn_mlp_tc.cu): a = hi + lo, hi = rna_tf32(a).  The main term
+// A_hi*W_hi runs as kind::tf32, both correction terms as ONE kind::f16 (bf16) chain over a concatenated K:
+// A' = [bf16(a_hi) | bf16(a_lo)], W' = [bf16(w_lo) ; bf16(w_hi)].  A TMEM operand slot (64 columns) of one 32-wide K-block:
+// columns [0,32) TF32 hi, [32,48) bf16(hi) packed two per column, [48,64) bf16(lo) packed.
+__device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(lo_elem, hi_elem);     // .x (low 16 bits) = element with the lower K index
+    return *reinterpret_cast<const uint32_t*>(&p);
 }
 
-// 3xTF32 K-block with both A halves in TMEM: D (+)= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi
-__device__ __forceinline__ void issue_kblock_tt(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                                uint32_t idesc, bool first) {
+// 8 consecutive K values of this thread's row: `k8` = their index / 8 inside the K-block (0..3)
+__device__ __forceinline__ void split8_to_tmem(uint32_t slot, int k8, const float (&a)[8]) {
+    uint32_t hi[8], hb[4], lb[4];
+    float h[8], l[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d_tmem, a_lo + k * 8, umma_desc(b_hi + k * 32), idesc, (first && k == 0) ? 0u : 1u);
+    for (int i = 0; i < 8; ++i) {
+        h[i] = tf32_rna_fast(a[i]);
+        hi[i] = __float_as_uint(h[i]);
+        l[i] = a[i] - h[i];
+    }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d_tmem, a_hi + k * 8, umma_desc(b_lo + k * 32), idesc, 1u);
+    for (int i = 0; i < 4; ++i) {
+        hb[i] = pack_bf16(h[2 * i], h[2 * i + 1]);
+        lb[i] = pack_bf16(l[2 * i], l[2 * i + 1]);
+    }
+    tmem_st8(slot + (uint32_t)(k8 * 8), hi);
+    tmem_st4(slot + 32u + (uint32_t)(k8 * 4), hb);
+    tmem_st4(slot + 48u + (uint32_t)(k8 * 4), lb);
+}
+
+// one K-block with the A operand in TMEM: D (+)= A'*W' (4 bf16 MMAs, K = 16) + A_hi*W_hi (4 TF32 MMAs, K = 8)
+__device__ __forceinline__ void issue_kblock_tt(uint32_t d_tmem, uint32_t a_slot, uint32_t b_hi, uint32_t b_corr, int n, bool first) {
+    const uint32_t id32 = umma_idesc(n), id16 = umma_idesc_bf16(n);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d_tmem, a_hi + k * 8, umma_desc(b_hi + k * 32), idesc, 1u);
+    for (int k = 0; k < 4; ++k) tc_mma_bf16_ts(d_tmem, a_slot + 32u + k * 8, umma_desc(b_corr + k * 32), id16, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tc_mma_tf32_ts(d_tmem, a_slot + k * 8, umma_desc(b_hi + k * 32), id32, 1u);
 }
 
 template <int ACT, int MODE>
@@ -150,7 +166,6 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t ait = 0, bit = 0, sc = 0;
-            const uint32_t idesc = umma_idesc(P.Nc);
             for (int item = 0; item < items; ++item) {
                 for (int kb0 = 0; kb0 < nkb; kb0 += kSegKB, ++sc) {           // one accumulator buffer per K segment
                     const uint32_t buf = sc & 1, u = sc >> 1;
@@ -166,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
                         tc_fence_after();
                         const uint32_t a_hi = tmem + kColA + as * 64u;
                         const uint32_t b_hi = sbase + kLSmemB + bs * kBStage;
-                        issue_kblock_tt(d, a_hi, a_hi + 32u, b_hi, b_hi + slab / 2, idesc, kb == kb0);
+                        issue_kblock_tt(d, a_hi, b_hi, b_hi + slab / 2, P.Nc, kb == kb0);
                         if (!resident || c == nchunks - 1) tc_commit(bar(LA_EMPTY0 + as));
                         tc_commit(bar(LB_EMPTY0 + bs));
                         // resident: the ring position runs over (tile, kb) only and is rewound for every further chunk
@@ -182,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
         const int quarter = warp & 3;
         const int cg = (warp - 2) >> 2;                           // which 16 of the 32 K values
         const int row = quarter * 32 + lane;
-        const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + kColA + (uint32_t)(cg * 16);
+        const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + kColA;
         const int total = (resident ? my_tiles : items) * nkb;
         const int per_tile = resident ? 1 : nchunks;
         auto load = [&](float4 (&r)[4], int n) {
@@ -202,11 +217,11 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
             const uint32_t as = (uint32_t)n % aring, au = (uint32_t)n / aring;
             mbar_wait(bar(LA_EMPTY0 + as), (au & 1) ^ 1);
             tc_fence_after();
-            const uint32_t t_hi = lane_addr + as * 64u;
+            const uint32_t slot = lane_addr + as * 64u;
             const float a0[8] = {r[0].x, r[0].y, r[0].z, r[0].w, r[1].x, r[1].y, r[1].z, r[1].w};
             const float a1[8] = {r[2].x, r[2].y, r[2].z, r[2].w, r[3].x, r[3].y, r[3].z, r[3].w};
-            split8_to_tmem(t_hi, t_hi + 32u, a0);
-            split8_to_tmem(t_hi + 8u, t_hi + 40u, a1);
+            split8_to_tmem(slot, cg * 2, a0);
+            split8_to_tmem(slot, cg * 2 + 1, a1);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(bar(LA_FULL0 + as));
@@ -365,7 +380,10 @@ __global__ void lin_prepare_kernel(const float* __restrict__ w, int w_rows, int 
         const float v = w[idx];
         const float hi = tf32_rna(v);
         *reinterpret_cast<float*>(img + off) = hi;
-        *reinterpret_cast<float*>(img + off + slab / 2) = tf32_rna(v - hi);
+        // correction part W' [Nc][64 k'] bf16: k' = kk -> bf16(w_lo) (pairs with bf16(a_hi)), k' = 32 + kk -> bf16(w_hi)
+        const size_t corr = ((size_t)c * nkb + kb) * slab + slab / 2;
+        *reinterpret_cast<__nv_bfloat16*>(img + corr + swz((uint32_t)nl, (uint32_t)(kk >> 3)) + (kk & 7) * 2) = __float2bfloat16_rn(v - hi);
+        *reinterpret_cast<__nv_bfloat16*>(img + corr + swz((uint32_t)nl, (uint32_t)(4 + (kk >> 3))) + (kk & 7) * 2) = __float2bfloat16_rn(hi);
     }
     (void)Np;
 }
@@ -436,7 +454,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradParams
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc(P.Nk);
             for (int j = 0; j < nkb; ++j) {
                 const int seg = j / kSegKB;
                 const uint32_t buf = seg & 1;
@@ -449,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradParams
                 tc_fence_after();
                 const uint32_t a_hi = tmem + kColA + s * 64u;
                 const uint32_t b_hi = sbase + kWSmemOp + s * kBStage;
-                issue_kblock_tt(tmem + (buf ? kColAcc1 : kColAcc0), a_hi, a_hi + 32u, b_hi, b_hi + bhalf, idesc, j % kSegKB == 0);
+                issue_kblock_tt(tmem + (buf ? kColAcc1 : kColAcc0), a_hi, b_hi, b_hi + bhalf, P.Nk, j % kSegKB == 0);
                 tc_commit(bar(W_EMPTY0 + s));
                 if (j % kSegKB == kSegKB - 1 || j == nkb - 1) tc_commit(bar(WACC_FULL0 + buf));
             }
@@ -526,16 +543,24 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradParams
             isrc += (size_t)kKB * P.Ki;
         };
         const float* rd = reinterpret_cast<const float*>(smem + kWSmemRawG) + w * 512 + lane;       // + stage * 2 * kRawTile / 4
+        // B operand of a stage: TF32 tile [Nk][32 r] fp32 | correction tile B' [Nk][64 r'] bf16 with r' = r -> bf16(in_lo)
+        // (pairs with bf16(g_hi)), r' = 32 + r -> bf16(in_hi); a unit = 4 consecutive rows r = 4*ch.. of one feature
         uint8_t* b_wr0 = smem + kWSmemOp + swz((uint32_t)(colb + lane), (uint32_t)ch0);
         uint8_t* b_wr1 = smem + kWSmemOp + swz((uint32_t)(colb + lane), (uint32_t)ch1);
-        const uint32_t t_a = lane_base + kColA + (uint32_t)(rg * 8);
+        uint8_t* c_wr0 = smem + kWSmemOp + bhalf + swz((uint32_t)(colb + lane), (uint32_t)(ch0 >> 1)) + (ch0 & 1) * 8;
+        uint8_t* c_wr1 = smem + kWSmemOp + bhalf + swz((uint32_t)(colb + lane), (uint32_t)(ch1 >> 1)) + (ch1 & 1) * 8;
+        const uint32_t c_hi0 = swz((uint32_t)(colb + lane), (uint32_t)(4 + (ch0 >> 1))) - swz((uint32_t)(colb + lane), (uint32_t)(ch0 >> 1));
+        const uint32_t c_hi1 = swz((uint32_t)(colb + lane), (uint32_t)(4 + (ch1 >> 1))) - swz((uint32_t)(colb + lane), (uint32_t)(ch1 >> 1));
+        const uint32_t t_a = lane_base + kColA;
         const uint32_t bar0 = bar(0);
-        auto split4 = [&](const float (&v)[4], uint8_t* dst) {
-            float4 hi, lo;
-            hi.x = tf32_rna_fast(v[0]); lo.x = v[0] - hi.x; hi.y = tf32_rna_fast(v[1]); lo.y = v[1] - hi.y;
-            hi.z = tf32_rna_fast(v[2]); lo.z = v[2] - hi.z; hi.w = tf32_rna_fast(v[3]); lo.w = v[3] - hi.w;
+        auto split4 = [&](const float (&v)[4], uint8_t* dst, uint8_t* cdst, uint32_t c_hi) {
+            float4 hi;
+            float lo[4];
+            hi.x = tf32_rna_fast(v[0]); lo[0] = v[0] - hi.x; hi.y = tf32_rna_fast(v[1]); lo[1] = v[1] - hi.y;
+            hi.z = tf32_rna_fast(v[2]); lo[2] = v[2] - hi.z; hi.w = tf32_rna_fast(v[3]); lo[3] = v[3] - hi.w;
             *reinterpret_cast<float4*>(dst) = hi;
-            *reinterpret_cast<float4*>(dst + bhalf) = lo;
+            *reinterpret_cast<uint2*>(cdst) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+            *reinterpret_cast<uint2*>(cdst + c_hi) = make_uint2(pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
         };
 
         issue(0, 0);
@@ -568,20 +593,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradParams
             __syncwarp();                                         // all lanes have read this stage before it is refilled
             mbar_wait(bar0 + 8u * (W_EMPTY0 + st), ph ^ 1);
             tc_fence_after();
-            {
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float h = tf32_rna_fast(a[i]);
-                    hi[i] = __float_as_uint(h);
-                    lo[i] = __float_as_uint(a[i] - h);
-                }
-                tmem_st8(t_a + st * 64u, hi);
-                tmem_st8(t_a + st * 64u + 32u, lo);
-            }
+            split8_to_tmem(t_a + st * 64u, rg, a);                // rows rg*8.. of the K-block = K values rg*8..
             if (want_bias) bs32 += ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-            if (has0) split4(b0, b_wr0 + st * kBStage);
-            if (has1) split4(b1, b_wr1 + st * kBStage);
+            if (has0) split4(b0, b_wr0 + st * kBStage, c_wr0 + st * kBStage, c_hi0);
+            if (has1) split4(b1, b_wr1 + st * kBStage, c_wr1 + st * kBStage, c_hi1);
             tmem_wait_st();
             fence_proxy_async();
             tc_fence_before();
