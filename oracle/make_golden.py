@@ -299,6 +299,31 @@ def main():
                os.path.join(OUT, "c4r_cnf_hutch.pt"))
     print(f"c4r_cnf_hutch: nfe={outc['nfe_total']:.0f} attempts={[len(r['t']) for r in outc['traces']]}")
 
+    # fixed-step asynchronous leapfrog through odeint_symplectic (reference odeint.py:95-153, ode.py:107-135), forward and
+    # reversed span; the vector field carries `order = 1` (v' = f(t, x) on the position half of the state)
+    from torchdyn.numerics import odeint_symplectic as ref_symplectic
+
+    class _PosField(nn.Module):
+        order = 1
+
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.net = nn.Sequential(nn.Linear(3, 16), nn.Tanh(), nn.Linear(16, 3))
+
+        def forward(self, t, x):
+            return self.net(x)
+
+    fa = _PosField()
+    torch.manual_seed(1)
+    xs = torch.randn(7, 6)
+    with torch.no_grad():
+        t_a, s_a = ref_symplectic(fa, xs, torch.linspace(0, 1, 11), 'alf')
+        t_b, s_b = ref_symplectic(fa, xs, torch.linspace(1, 0, 5), 'alf')
+    torch.save(dict(x=xs, t_span=torch.linspace(0, 1, 11), params=[p.detach().clone() for p in fa.parameters()], sol=s_a,
+                    t_eval=t_a, sol_rev=s_b, t_rev=t_b), os.path.join(OUT, "fn_alf_symplectic.pt"))
+    print(f"fn_alf_symplectic: sol {tuple(s_a.shape)}")
+
     # spline: self-consistency vector (UNPINNED against torchcde, see oracle/__init__.py)
     torch.manual_seed(31)
     xs = torch.randn(5, 9, 3)

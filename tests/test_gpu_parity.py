@@ -632,3 +632,24 @@ def test_edge_shapes_and_views():
         _, e = odeint(f, off, t_span, "rk4")
         _, g = odeint(f, off.clone(), t_span, "rk4")
         assert torch.equal(e, g)
+
+
+def test_odeint_symplectic_alf_on_gpu_matches_reference():
+    """Fixed-step asynchronous leapfrog (plug-in solver, torch ops on the GPU) against the executed-reference fixture."""
+    from torchdyn_b200.numerics import odeint_symplectic
+    fx = load_golden("fn_alf_symplectic")
+
+    class PosField(torch.nn.Module):
+        order = 1
+
+        def __init__(self):
+            super().__init__()
+            self.net = build_mlp([3, 16, 3], "tanh", fx["params"], DEV)
+
+        def forward(self, t, x):
+            return self.net(x)
+
+    with torch.no_grad():
+        t_eval, sol = odeint_symplectic(PosField(), fx["x"].to(DEV), fx["t_span"], "alf")
+    assert torch.equal(t_eval.cpu(), fx["t_eval"])
+    assert_close(sol, fx["sol"], "alf trajectory", rtol=1e-5, atol_scale=2e-6)

@@ -222,3 +222,38 @@ def test_nan_error_ratio_raises_instead_of_hanging():
     from torchdyn_b200.numerics import odeint
     with torch.no_grad(), pytest.raises(RuntimeError, match="did not terminate"):
         odeint(lambda t, x: x * float("nan"), torch.ones(2, 2), torch.linspace(0, 1, 2), "dopri5")
+
+
+class _PosField(torch.nn.Module):
+    order = 1
+
+    def __init__(self, params):
+        super().__init__()
+        self.net = torch.nn.Sequential(torch.nn.Linear(3, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
+        with torch.no_grad():
+            for p, v in zip(self.net.parameters(), params):
+                p.copy_(v)
+
+    def forward(self, t, x):
+        return self.net(x)
+
+
+def test_odeint_symplectic_alf_bit_identical_to_reference():
+    """Fixed-step asynchronous leapfrog through odeint_symplectic (reference odeint.py:95-153, ode.py:107-135): the
+    executed-reference fixture, forward and reversed span, plus the reference's error behaviour."""
+    from torchdyn_b200.numerics import AsynchronousLeapfrog, odeint_symplectic
+    fx = load_golden("fn_alf_symplectic")
+    f = _PosField(fx["params"])
+    with torch.no_grad():
+        t1, s1 = odeint_symplectic(f, fx["x"], fx["t_span"], "alf")
+        t2, s2 = odeint_symplectic(f, fx["x"], torch.linspace(1, 0, 5), AsynchronousLeapfrog())
+    assert torch.equal(s1, fx["sol"]) and torch.equal(t1, fx["t_eval"])
+    assert torch.equal(s2, fx["sol_rev"]) and torch.equal(t2, fx["t_rev"])
+    with pytest.raises(RuntimeError, match="order"):
+        odeint_symplectic(lambda t, x: x, fx["x"], fx["t_span"], "alf")
+    f.order = 2
+    with pytest.raises(RuntimeError, match="first-order symplectic"):
+        odeint_symplectic(f, fx["x"], fx["t_span"], "alf")
+    f.order = 1
+    with pytest.raises(NotImplementedError):
+        odeint_symplectic(f, fx["x"], fx["t_span"], AsynchronousLeapfrog(stepping_class="adaptive"))

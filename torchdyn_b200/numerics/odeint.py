@@ -116,6 +116,30 @@ def odeint(f: Callable, x: Tensor, t_span: Union[List, Tensor], solver: Union[st
     raise ValueError(f"unknown stepping_class {stepping_class!r}")
 
 
+def odeint_symplectic(f: Callable, x: Tensor, t_span: Union[List, Tensor], solver: Union[str, nn.Module], atol: float = 1e-3,
+                      rtol: float = 1e-3, verbose: bool = False, return_all_eval: bool = False,
+                      save_at: Union[List, Tensor] = ()):
+    """IVP on a phase-space state with a symplectic stepper (reference odeint.py:95-153): same checks and errors, then the
+    fixed-step loop of ``odeint`` (the solver is a plug-in: its torch ``step`` runs unchanged).  The reference's adaptive
+    branch cannot run (its ALF step returns three values where the adaptive loop unpacks four): it raises here."""
+    from .solvers.ode import AsynchronousLeapfrog
+    if type(solver) == str:
+        solver = str_to_solver(solver, x.dtype)
+    if not hasattr(f, 'order'):
+        raise RuntimeError('The system order should be specified as an attribute `order` of `vector_field`')
+    if isinstance(solver, AsynchronousLeapfrog) and f.order == 2:
+        raise RuntimeError('ALF solver should be given a vector field specified as a first-order symplectic system: v = f(t, x)')
+    solver.x_shape = x.shape[-1] // 2
+    if len(_host_times(t_span).shape) > 1:
+        raise NotImplementedError("Parallel routines not implemented yet, check experimental versions of `torchdyn`")
+    if solver.stepping_class != 'fixed':
+        raise NotImplementedError("adaptive symplectic stepping: the reference's adaptive ALF step is incompatible with its "
+                                  "own adaptive loop; use stepping_class='fixed'")
+    if atol != odeint_symplectic.__defaults__[0] or rtol != odeint_symplectic.__defaults__[1]:
+        warn("Setting tolerances has no effect on fixed-step methods")
+    return odeint(f, x, t_span, solver, verbose=verbose, return_all_eval=return_all_eval, save_at=save_at)
+
+
 # ----------------------------------------------------------------------------------------------
 # adaptive loop
 # ----------------------------------------------------------------------------------------------

@@ -204,11 +204,39 @@ class Tsitouras45(_Embedded54):
         self.tableau = construct_tsit5(dtype)
 
 
+class AsynchronousLeapfrog(DiffEqSolver):
+    """Explicit asynchronous-leapfrog stepper on a phase-space state ``[x, v]`` with ``v' = f(t, x)`` (reference
+    ode.py:107-135).  A plug-in solver: its ``step`` is torch code that ``odeint`` / ``odeint_symplectic`` drive through
+    the solver contract (f stays a torch call).  Only ``stepping_class='fixed'`` integrates: the reference's adaptive
+    variant returns a 3-tuple where its adaptive loop unpacks four values, i.e. it cannot run there either."""
+
+    def __init__(self, channel_index: int = -1, stepping_class: str = 'fixed', dtype=torch.float32):
+        super().__init__(order=2)
+        self.dtype = dtype
+        self.channel_index = channel_index
+        self.stepping_class = stepping_class
+        self.const = 1
+        self.tableau = construct_rk4(self.dtype)
+        self.x_shape = None
+
+    def step(self, f, xv, t, dt, k1=None, args=None):
+        half = xv.shape[-1] // 2
+        x, v = xv[..., :half], xv[..., half:]
+        if k1 is None:
+            k1 = f(t, x)                      # evaluated and not used, as in the reference (it is an NFE there too)
+        x_mid = x + 0.5 * dt * v
+        v_mid = f(t + 0.5 * dt, x_mid)
+        v_new = 2 * self.const * (v_mid - v) + v
+        x_new = x_mid + 0.5 * dt * v_new
+        xv_err = torch.cat([torch.zeros_like(x), v], -1) if self.stepping_class == 'adaptive' else None
+        return None, torch.cat([x_new, v_new], -1), xv_err
+
+
 BUILTIN_TYPES = (Euler, Midpoint, RungeKutta4, DormandPrince45, Tsitouras45)
 
-# name registry of the explicit RK solvers (reference ode.py:320-325; the other reference solvers -- alf, ieuler,
-# multiple shooting -- are outside this implementation: unknown names raise KeyError as there)
-SOLVER_DICT = {'euler': Euler, 'midpoint': Midpoint,
+# name registry of the explicit solvers (reference ode.py:320-325; ieuler and the multiple-shooting solvers are outside
+# this implementation: unknown names raise KeyError as there)
+SOLVER_DICT = {'euler': Euler, 'midpoint': Midpoint, 'alf': AsynchronousLeapfrog, 'AsynchronousLeapfrog': AsynchronousLeapfrog,
                'rk4': RungeKutta4, 'rk-4': RungeKutta4, 'RungeKutta4': RungeKutta4,
                'dopri5': DormandPrince45, 'DormandPrince45': DormandPrince45, 'DormandPrince5': DormandPrince45,
                'tsit5': Tsitouras45, 'Tsitouras45': Tsitouras45, 'Tsitouras5': Tsitouras45}
