@@ -324,6 +324,29 @@ def main():
                     t_eval=t_a, sol_rev=s_b, t_rev=t_b), os.path.join(OUT, "fn_alf_symplectic.pt"))
     print(f"fn_alf_symplectic: sol {tuple(s_a.shape)}")
 
+    # hybrid system (reference odeint.py:183-323): bouncing ball [height, velocity], jump = restitution 0.8 at the floor
+    from torchdyn.numerics import odeint_hybrid as ref_hybrid
+
+    class _Ball(nn.Module):
+        def forward(self, t, x):
+            return torch.cat([x[..., 1:], -9.81 * torch.ones_like(x[..., :1])], -1)
+
+    class _Bounce:
+        def check_event(self, t, x):
+            return bool((x[..., 0] <= 0).any())
+
+        def jump_map(self, t, x):
+            return torch.cat([x[..., :1] * 0 + 1e-3, -0.8 * x[..., 1:]], -1)
+
+    hyb = dict(x=torch.tensor([[1.0, 0.0]]), t_span=torch.linspace(0, 2, 5), j_span=3, atol=1e-5, rtol=1e-5, event_tol=1e-4)
+    with torch.no_grad():
+        for sv in ("dopri5", "tsit5"):
+            t_h, s_h = ref_hybrid(_Ball(), hyb["x"], hyb["t_span"], hyb["j_span"], sv, [_Bounce()], atol=hyb["atol"],
+                                  rtol=hyb["rtol"], event_tol=hyb["event_tol"])
+            hyb[sv] = dict(t_eval=t_h, sol=s_h)
+    torch.save(hyb, os.path.join(OUT, "fn_hybrid_bouncing_ball.pt"))
+    print(f"fn_hybrid_bouncing_ball: {[tuple(hyb[sv]['sol'].shape) for sv in ('dopri5', 'tsit5')]}")
+
     # spline: self-consistency vector (UNPINNED against torchcde, see oracle/__init__.py)
     torch.manual_seed(31)
     xs = torch.randn(5, 9, 3)

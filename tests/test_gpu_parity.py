@@ -653,3 +653,30 @@ def test_odeint_symplectic_alf_on_gpu_matches_reference():
         t_eval, sol = odeint_symplectic(PosField(), fx["x"].to(DEV), fx["t_span"], "alf")
     assert torch.equal(t_eval.cpu(), fx["t_eval"])
     assert_close(sol, fx["sol"], "alf trajectory", rtol=1e-5, atol_scale=2e-6)
+
+
+@pytest.mark.parametrize("solver", ["dopri5", "tsit5"])
+def test_odeint_hybrid_bouncing_ball_on_gpu(solver):
+    """Hybrid loop on the CUDA kernels: same event times / jumps as the executed reference (the bisection ends within
+    event_tol of the reference's switching time; states to the solver tolerance)."""
+    from torchdyn_b200.numerics import odeint_hybrid
+    fx = load_golden("fn_hybrid_bouncing_ball")
+
+    class Ball(torch.nn.Module):
+        def forward(self, t, x):
+            return torch.cat([x[..., 1:], -9.81 * torch.ones_like(x[..., :1])], -1)
+
+    class Bounce:
+        def check_event(self, t, x):
+            return bool((x[..., 0] <= 0).any())
+
+        def jump_map(self, t, x):
+            return torch.cat([x[..., :1] * 0 + 1e-3, -0.8 * x[..., 1:]], -1)
+
+    with torch.no_grad():
+        t_eval, sol = odeint_hybrid(Ball(), fx["x"].to(DEV), fx["t_span"], fx["j_span"], solver, [Bounce()], atol=fx["atol"],
+                                    rtol=fx["rtol"], event_tol=fx["event_tol"])
+    ref_t, ref_s = fx[solver]["t_eval"], fx[solver]["sol"]
+    assert t_eval.shape == ref_t.shape, (t_eval.shape, ref_t.shape)
+    np.testing.assert_allclose(t_eval.cpu().numpy(), ref_t.numpy(), rtol=2e-4, atol=2e-4)
+    assert torch.allclose(sol.cpu(), ref_s, rtol=2e-3, atol=2e-3)

@@ -257,3 +257,27 @@ def test_odeint_symplectic_alf_bit_identical_to_reference():
     f.order = 1
     with pytest.raises(NotImplementedError):
         odeint_symplectic(f, fx["x"], fx["t_span"], AsynchronousLeapfrog(stepping_class="adaptive"))
+
+
+class _Ball(torch.nn.Module):
+    def forward(self, t, x):
+        return torch.cat([x[..., 1:], -9.81 * torch.ones_like(x[..., :1])], -1)
+
+
+class _Bounce:
+    def check_event(self, t, x):
+        return bool((x[..., 0] <= 0).any())
+
+    def jump_map(self, t, x):
+        return torch.cat([x[..., :1] * 0 + 1e-3, -0.8 * x[..., 1:]], -1)
+
+
+@pytest.mark.parametrize("solver", ["dopri5", "tsit5"])
+def test_odeint_hybrid_bouncing_ball_bit_identical_to_reference(solver):
+    """Event detection, bisection of the triggering step and the jump map (reference odeint.py:183-323)."""
+    from torchdyn_b200.numerics import odeint_hybrid
+    fx = load_golden("fn_hybrid_bouncing_ball")
+    with torch.no_grad():
+        t_eval, sol = odeint_hybrid(_Ball(), fx["x"], fx["t_span"], fx["j_span"], solver, [_Bounce()], atol=fx["atol"],
+                                    rtol=fx["rtol"], event_tol=fx["event_tol"])
+    assert torch.equal(t_eval, fx[solver]["t_eval"]) and torch.equal(sol, fx[solver]["sol"])

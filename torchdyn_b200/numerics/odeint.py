@@ -140,6 +140,104 @@ def odeint_symplectic(f: Callable, x: Tensor, t_span: Union[List, Tensor], solve
     return odeint(f, x, t_span, solver, verbose=verbose, return_all_eval=return_all_eval, save_at=save_at)
 
 
+class EventState:
+    """Flags of the hybrid-system callbacks at one point (reference numerics/utils.py:76-82)."""
+
+    def __init__(self, evid):
+        self.evid = [bool(e) for e in evid]
+
+    def __ne__(self, other):
+        return sum(a != b for a, b in zip(self.evid, other.evid))
+
+    def newly_triggered(self, previous: "EventState") -> int:
+        """how many flags went from False (previous) to True (self)"""
+        return sum((a != b) and (b is False) for a, b in zip(self.evid, previous.evid))
+
+
+def odeint_hybrid(f, x, t_span, j_span, solver, callbacks, atol=1e-3, rtol=1e-3, event_tol=1e-4, priority='jump',
+                  seminorm: Tuple[bool, Union[int, None]] = (False, None)):
+    """IVP with state jumps defined by callbacks (``check_event(t, x) -> bool``, ``jump_map(t, x) -> x``); reference
+    odeint.py:183-323.  Same loop: adaptive steps of an embedded pair (stages, error norm and controller on this library's
+    kernels / host fp32 scalars, exactly as ``odeint``), after every attempted step the event flags are evaluated at the
+    step end, a False -> True transition is closed in on by bisection of the step (``event_tol``), the state is saved
+    before and after the jump.  Quirks kept: the flags are compared with those of the INITIAL point throughout (the
+    reference never updates ``event_states``), ``j_span`` only counts the initial jump, rejected steps still run the
+    controller, every accepted step is returned (``t_span`` interior points are hit exactly by the checkpoint clamp)."""
+    ts = _host_times(t_span)
+    if type(solver) == str:
+        solver = str_to_solver(solver, x.dtype)
+    x, _ = solver.sync_device_dtype(x, None)
+    x_shape = x.shape
+    builtin = type(solver) in BUILTIN_TYPES
+    t_eval, t, T = ts[1:], f32(ts[0]), f32(ts[-1])
+    tt = lambda v: torch.full((1,), float(v), dtype=x.dtype, device=x.device)      # noqa: E731  (callbacks see t as a [1] tensor)
+    ck, ck_flag, dt_keep, jnum = 0, False, None, 0
+
+    events0 = EventState([False for _ in callbacks])
+    if priority == 'jump':
+        ev = EventState([cb.check_event(tt(t), x) for cb in callbacks])
+        if ev.newly_triggered(events0) > 0:
+            i = min(i for i, flag in enumerate(ev.evid) if flag)
+            x = callbacks[i].jump_map(tt(t), x)
+            jnum += 1
+
+    if builtin:
+        if isinstance(x, Tensor) and not x.is_contiguous():
+            x = x.contiguous()
+        kern = _kernels.get(x)
+        k1 = call_vf(kern, f, t, x)
+        dt = init_step(f, k1, x, t, solver.order, atol, rtol)
+        attempt = _KernelAttempt(solver, x, atol, rtol, seminorm, None)
+    else:
+        k1 = f(tt(t)[0], x)
+        dt = _init_step_torch(f, k1, x, tt(t)[0], solver.order, atol, rtol)
+        attempt = _TorchAttempt(solver, x, atol, rtol, seminorm, None, None)
+    safety, min_factor, max_factor = solver.controller_constants()
+
+    times, sol = [t], [x]
+    n_attempts = 0
+    while t < T and jnum < j_span:
+        n_attempts += 1
+        if n_attempts > MAX_STEPS or np.isnan(dt):
+            raise RuntimeError(f"torchdyn_b200.odeint_hybrid: loop did not terminate (t={t}, dt={dt})")
+        if f32(t + dt) > T:
+            dt = f32(T - t)
+        if ck < len(t_eval) and f32(t + dt) > t_eval[ck]:
+            dt_keep, ck_flag = dt, True
+            dt = f32(t_eval[ck] - t)
+            ck += 1
+
+        f_new, x_new, _, ratio = attempt(f, x, t, dt, k1)
+        ev = EventState([cb.check_event(tt(f32(t + dt)), x_new) for cb in callbacks])
+
+        if ev.newly_triggered(events0) > 0:
+            # close in on the switching state inside [t, t + dt] by bisection of the step
+            dt_pre, t_in, dt_in, x_in, niters = dt, t, dt, x, 0
+            while niters < 100 and event_tol < dt_in:
+                with torch.no_grad():
+                    dt_in = f32(dt_in / f32(2))
+                    f_new, x_try, _, _ = attempt(f, x_in, t_in, dt_in, k1)
+                    ev = EventState([cb.check_event(tt(f32(t_in + dt_in)), x_try) for cb in callbacks])
+                    niters += 1
+                if ev.newly_triggered(events0) == 0:      # no event yet: advance the start of the search
+                    x_in, t_in, dt_in, k1 = x_try, f32(t_in + dt_in), dt, f_new
+            x, t = x_in, t_in
+            i = min(i for i, flag in enumerate(ev.evid) if flag)
+            sol.append(x.reshape(x_shape)); times.append(t)          # state and time BEFORE the jump
+            x = callbacks[i].jump_map(tt(t), x)
+            sol.append(x.reshape(x_shape)); times.append(t)          # ... and AFTER it
+            k1, dt = None, dt_pre                                    # the next step evaluates f at the jumped state
+        else:
+            if ratio <= 1:
+                t, x, k1 = f32(t + dt), x_new, f_new
+                sol.append(x.reshape(x_shape)); times.append(t)
+            if ck_flag:
+                dt = f32(dt_keep - dt)
+                ck_flag = False
+            dt = adapt_step(dt, ratio, safety, min_factor, max_factor, solver.order)
+    return _times_tensor(times, x), torch.stack(sol)
+
+
 # ----------------------------------------------------------------------------------------------
 # adaptive loop
 # ----------------------------------------------------------------------------------------------
