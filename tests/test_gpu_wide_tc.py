@@ -206,3 +206,35 @@ def test_wide_fixture_runs_on_the_tensor_core_kernels(name):
     nfe_adj = out["model"].vf.nfe - out["nfe_fwd"]
     n_layers = len(fx["dims"]) - 1
     assert sum(r[0] == "wgrad_tc" for r in timer.records) == n_layers * nfe_adj or fx["kw"]["sensitivity"] == "adjoint"
+
+
+def test_cfg3_full_size_duplicated_batch_property():
+    """BASELINE config 3 at full size on the tensor-core kernels (128-1024-128, 262 144 rows, tsit5 + interpolated
+    adjoint).  Size-independent property: for the batch [x0; x0] every global RMS norm equals that of x0 alone (fp64 sums
+    double exactly), so the forward controller takes the same steps and both halves of the solution equal the half-batch
+    solution BIT FOR BIT (rows are computed independently of their position).  In the backward the parameter-gradient
+    block mu sits inside the interpolated adjoint's error norm and doubles with the batch, so the backward steps may
+    differ: the two halves of dL/dx0 are bit-identical to each other and agree with the half-batch run to the solver
+    tolerance, the parameter gradient of the SUM loss doubles to the same tolerance."""
+    from torchdyn_b200.core import NeuralODE
+    torch.manual_seed(11)
+    net = build_mlp([128, 1024, 128], "tanh").to(DEV)
+    x0 = torch.randn(131072, 128, device=DEV)
+    t_span = torch.linspace(0, 1, 2)
+
+    def step(x):
+        net.zero_grad()
+        model = NeuralODE(net, solver="tsit5", sensitivity="interpolated_adjoint")
+        xx = x.clone().requires_grad_(True)
+        _, sol = model(xx, t_span)
+        sol[-1].pow(2).sum().backward()
+        assert "tdyn_lin_tc_apply" in fused.last_used()
+        return sol[-1].detach(), xx.grad.clone(), torch.cat([p.grad.flatten() for p in net.parameters()]).clone(), float(model.vf.nfe)
+
+    s1, gx1, gp1, nfe1 = step(x0)
+    s2, gx2, gp2, nfe2 = step(torch.cat([x0, x0]))
+    assert torch.equal(s2[:131072], s1) and torch.equal(s2[131072:], s1)
+    assert torch.equal(gx2[:131072], gx2[131072:])
+    assert abs(nfe1 - nfe2) <= 12
+    assert_close(gx2[:131072], gx1, "dL/dx0 of the duplicated batch", rtol=2e-2, atol_scale=2e-3)
+    assert_close(gp2, 2 * gp1, "parameter gradient of the duplicated batch", rtol=2e-2, atol_scale=2e-3)
