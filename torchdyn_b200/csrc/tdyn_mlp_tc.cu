@@ -348,6 +348,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
         for (int t = 0; t < my_tiles; ++t) {
             const uint32_t tpar = t & 1;
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            if (t + 1 < my_tiles && w.sub == 0) {
+                // the next tile's stage-input rows (x and the k's, 128 B each) are consumed by prologue() half a tile
+                // from now: pull them into L2 so that those loads do not pay the DRAM latency
+                const int64_t nrow = (tile + gridDim.x) * kTileM + w.row;
+                if (nrow < P.rows) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.x + (size_t)nrow * kD));
+                    for (int j = 0; j < P.n_k; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.k.p[j] + (size_t)nrow * kD));
+                }
+            }
             // ---- two activation epilogues: D1 -> layer-2 operand, D2 -> layer-3 operand
 #pragma unroll 1
             for (int layer = 0; layer < 2; ++layer) {
