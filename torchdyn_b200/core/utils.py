@@ -1,24 +1,26 @@
-"""``standardize_vf_call_signature`` (reference torchdyn/core/utils.py:19-35)."""
+"""``standardize_vf_call_signature`` (reference torchdyn/core/utils.py:19-35): every vector field handed to ODEProblem /
+NeuralODE ends up callable as ``(t, x)``."""
 from inspect import getfullargspec
 
 import torch.nn as nn
 
 from .defunc import DEFunc, DEFuncBase
 
+_NOTICE = ("Your vector field callable ({kind}) should have both time `t` and state `x` as arguments, "
+           "we've wrapped it for you.")
+
+
+def _takes_time(vf) -> bool:
+    """True if the callable's own signature names a ``t`` argument (a module is judged by its ``forward``)."""
+    target = vf.forward if isinstance(vf, nn.Module) else vf
+    return 't' in getfullargspec(target).args
+
 
 def standardize_vf_call_signature(vector_field, order=1, defunc_wrap=False):
-    "Make callables / nn.Modules handed to ODEProblem and NeuralODE callable as (t, x)."
-    if issubclass(type(vector_field), nn.Module):
-        if 't' not in getfullargspec(vector_field.forward).args:
-            print("Your vector field callable (nn.Module) should have both time `t` and state `x` as arguments, "
-                  "we've wrapped it for you.")
-            vector_field = DEFuncBase(vector_field, has_time_arg=False)
-    else:
-        # plain functions / lambdas: inspect the function itself
-        if 't' not in getfullargspec(vector_field).args:
-            print("Your vector field callable (lambda) should have both time `t` and state `x` as arguments, "
-                  "we've wrapped it for you.")
-            vector_field = DEFuncBase(vector_field, has_time_arg=False)
-        else:
-            vector_field = DEFuncBase(vector_field, has_time_arg=True)
+    is_module = isinstance(vector_field, nn.Module)
+    timed = _takes_time(vector_field)
+    if not timed:
+        print(_NOTICE.format(kind="nn.Module" if is_module else "lambda"))
+    if not (is_module and timed):            # a module that already takes (t, x) is used as it is
+        vector_field = DEFuncBase(vector_field, has_time_arg=timed)
     return DEFunc(vector_field, order) if defunc_wrap else vector_field
