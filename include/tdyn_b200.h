@@ -178,7 +178,8 @@ TDYN_API int tdyn_mlp_solve_interp(const tdyn_mlp_t* mlp, const tdyn_rk_plan_t* 
                                    void* workspace, int* status, float* trace, int trace_cap, int64_t rows, int max_steps,
                                    void* stream);
 
-/* K2. Tensor-core (tcgen05, 3xTF32) stage kernel for wide MLPs (all hidden widths multiples of 64, >= 128):
+/* K2. Tensor-core (tcgen05, split precision: TF32 main term + bf16 correction chain) stage kernel for the
+ * 32-256-256-32 MLP class of BASELINE configs[1] (tdyn_mlp_tc_supported tells; other wide shapes: tdyn_lin_tc_* below):
  *   y = combine(x, k[], coef, mode, dt)   (same semantics as tdyn_rk_combine; n_k == 0 -> y = x)
  *   k_out = f(y)                          [rows, dims[0]]
  * and, when x_new != NULL (last stage of a fixed-step method), additionally
@@ -198,7 +199,7 @@ TDYN_API int tdyn_mlp_tc_stage(const tdyn_mlp_t* mlp, const void* wsplit, float*
  * Replaces, per layer, the nn.Linear / activation calls of the vector field (reference core/defunc.py:30-35) and the
  * autograd VJP `grad(dx, (x, t) + params, -lambda)` of the adjoint dynamics (numerics/sensitivity.py:62-66, 134-138).
  *
- * tdyn_lin_tc_prepare: image of the B operand of one layer (3xTF32 hi/lo, swizzled), `transpose` = 0 for the forward
+ * tdyn_lin_tc_prepare: image of the B operand of one layer (TF32 hi part + bf16 correction part, swizzled), `transpose` = 0 for the forward
  *   (B = W [w_rows = out, w_cols = in]) and 1 for the input gradient (B = W^T).  Rebuild after a parameter update.
  * tdyn_lin_tc_apply:  out[r, n] = scale * epi(sum_k in[r, k] B[n, k] + bias[n]);  mode 0: epi = identity,
  *   1: epi = act, 2: epi(v) = v * act'(z) with act' evaluated from the saved activation OUTPUT saved[r, n].

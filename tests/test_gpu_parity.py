@@ -251,7 +251,7 @@ def _c2_net(seed=8):
 @pytest.mark.parametrize("act", ["tanh", "softplus", "relu"])
 def test_mlp_tc_single_stage_matches_fp64_reference(act):
     """One tdyn_mlp_tc_stage launch (prologue combine + MLP + x_new epilogue) against an fp64 evaluation:
-    3xTF32 must keep fp32-level accuracy (max error ~1e-6 relative to the output scale)."""
+    the split-precision scheme must keep fp32-level accuracy (max error ~1e-6 relative to the output scale)."""
     from torchdyn_b200 import fused
     torch.manual_seed(8)
     net = build_mlp([32, 256, 256, 32], act)

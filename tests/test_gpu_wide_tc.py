@@ -161,7 +161,7 @@ def test_wide_forward_field_matches_torch():
 @pytest.mark.parametrize("dims", [[32, 256, 32], [32, 256, 256, 32]])
 def test_wide_neuralode_training_step_matches_generic_path(sens, solver, dims):
     """A training step (forward + adjoint) on the tensor-core kernels against the same step with f / VJP as torch
-    calls (fused.DISABLED): same accepted-step count, final state and gradients to the 3xTF32 bound."""
+    calls (fused.DISABLED): same accepted-step count, final state and gradients to the split-precision bound."""
     from torchdyn_b200.core import NeuralODE
     torch.manual_seed(3)
     net = build_mlp(dims, "tanh").to(DEV)

@@ -1,4 +1,4 @@
-// K10/K11: layer-wise tensor-core (tcgen05 / TMEM, 3xTF32) kernels for WIDE MLP vector fields of any shape whose layer
+// K10/K11: layer-wise tensor-core (tcgen05 / TMEM, split precision: TF32 + bf16 corrections) kernels for WIDE MLP vector fields of any shape whose layer
 // widths are multiples of 32 (BASELINE.json configs[2]: 128-1024-128) and for the adjoint of the 32-256-256-32 class.
 //
 //   K10 tdyn_lin_tc_apply : OUT[r, n] = scale * epi( sum_k IN[r, k] * B[n, k] (+ bias[n]) )
@@ -9,7 +9,8 @@
 //   K11 tdyn_wgrad_tc     : dW[n, k] = scale * sum_r G[r, n] * IN[r, k],  db[n] = scale * sum_r G[r, n]
 //        = the parameter half of the VJP, -lambda^T df/dtheta, contracted over the batch (sensitivity.py:66, 138).
 //
-// Both keep the 3xTF32 split (hi = rna_tf32(a), lo = a - hi; lo*hi + hi*lo + hi*hi with fp32 accumulation in TMEM).
+// Both use the split a = hi + lo (hi = rna_tf32(a)): hi*hi as kind::tf32, hi*lo + lo*hi as one bf16 chain, fp32
+// accumulation in TMEM (see split8_to_tmem).
 // K10: M = 128 batch rows per tile, the A operand (activations) is split by producer warps straight from global memory
 // into a TMEM ring (both halves: every MMA is the A-from-TMEM form, shared memory only carries B), the pre-split /
 // pre-swizzled weight image is streamed from L2 with bulk copies, accumulators are double-buffered [128 x <=128] TMEM

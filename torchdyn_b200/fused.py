@@ -4,7 +4,7 @@ A vector field is *fusable* when, after unwrapping torchdyn's call-signature ada
 ``DEFuncBase(has_time_arg=False)``, reference core/defunc.py:19-94) or this module's ``MLPField``, it is an
 ``nn.Sequential`` of ``Linear`` layers separated by one kind of activation out of Tanh / Softplus(beta=1,
 threshold=20) / ReLU, time-independent, fp32 on CUDA.  The fused kernels evaluate the field inside this library
-(``tdyn_mlp_tc_stage``: tcgen05 3xTF32), so ``f`` is never called; the wrappers' ``nfe`` counters are advanced by
+(``tdyn_mlp_tc_stage``: tcgen05, split precision TF32 + bf16 corrections), so ``f`` is never called; the wrappers' ``nfe`` counters are advanced by
 the same amounts the reference would count (core/defunc.py:31,61).
 """
 from __future__ import annotations
@@ -257,7 +257,7 @@ def _aligned(t):
 
 
 def wide_forward(fm: "FusedMLP", kern, y, out, sign: float = 1.0):
-    """Layer-by-layer forward of a wide MLP on the tensor cores (``tdyn_lin_tc_apply``, 3xTF32): hidden layers write
+    """Layer-by-layer forward of a wide MLP on the tensor cores (``tdyn_lin_tc_apply``, TF32 + bf16 corrections): hidden layers write
     their activation outputs (returned: the adjoint reuses them), the last layer writes ``sign * f`` into ``out``
     (skipped when ``out`` is None: the interpolated adjoint does not need f itself)."""
     imgs, dims, rows = fm.wide_images(kern), fm.dims, y.numel() // fm.dims[0]
@@ -397,7 +397,7 @@ def wrap(f, x):
         return f
     _last = ("fused MLP vector field (tdyn_mlp_tc_stage)" if fm.ready(kern) else
              "fused MLP vector field (tdyn_mlp_ffma_forward)" if fm.ready_ffma(kern) else
-             "wide MLP vector field, layer-wise tcgen05 3xTF32 (tdyn_lin_tc_apply)")
+             "wide MLP vector field, layer-wise tcgen05 split-precision kernels (tdyn_lin_tc_apply)")
     return FusedField(f, fm, counters, kern)
 
 
