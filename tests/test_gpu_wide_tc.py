@@ -106,7 +106,8 @@ def test_wgrad_tc_matches_fp64(n_out, k_in, rows):
 
 
 WIDE_NETS = [([128, 1024, 128], "tanh", 300), ([32, 256, 256, 32], "tanh", 200), ([32, 256, 256, 32], "softplus", 1000),
-             ([64, 512, 256, 64], "relu", 129), ([32, 256, 32], "tanh", 4099), ([128, 1024, 1024, 128], "softplus", 64)]
+             ([64, 512, 256, 64], "relu", 129), ([32, 256, 32], "tanh", 4099), ([128, 1024, 1024, 128], "softplus", 64),
+             ([32, 128, 256, 128, 32], "tanh", 515), ([64, 2048, 64], "relu", 77)]
 
 
 @pytest.mark.parametrize("dims,act,rows", WIDE_NETS)
