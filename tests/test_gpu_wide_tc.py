@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from torchdyn_b200 import _kernels, fused
+from torchdyn_b200.numerics import odeint
 from torchdyn_b200._lib import ACT_RELU, ACT_SOFTPLUS, ACT_TANH
 from conftest import build_mlp
 from parity_helpers import assert_close
@@ -239,3 +240,37 @@ def test_cfg3_full_size_duplicated_batch_property():
     assert abs(nfe1 - nfe2) <= 12
     assert_close(gx2[:131072], gx1, "dL/dx0 of the duplicated batch", rtol=2e-2, atol_scale=2e-3)
     assert_close(gp2, 2 * gp1, "parameter gradient of the duplicated batch", rtol=2e-2, atol_scale=2e-3)
+
+
+@pytest.mark.parametrize("case", ["reversed", "dense4th", "all_eval", "rk4_save_at"])
+def test_wide_field_through_odeint_variants(case):
+    """The functional API on a 64-256-64 field (layer-wise tensor-core forward) against the same call with f as a
+    torch call: reversed span, dopri5 with the 4th-order dense output, return_all_eval, fixed-step rk4 with save_at."""
+    torch.manual_seed(21)
+    net = build_mlp([64, 256, 64], "tanh").to(DEV)
+    x = torch.randn(700, 64, device=DEV)
+    field = fused.MLPField(net)
+    kw = {"reversed": dict(t_span=torch.linspace(1, 0, 4), solver="dopri5", atol=1e-5, rtol=1e-5),
+          "dense4th": dict(t_span=torch.linspace(0, 1, 7), solver="dopri5", atol=1e-5, rtol=1e-5, interpolator="4th"),
+          "all_eval": dict(t_span=torch.linspace(0, 1, 3), solver="tsit5", atol=1e-5, rtol=1e-5, return_all_eval=True),
+          "rk4_save_at": dict(t_span=torch.linspace(0, 1, 21), solver="rk4", save_at=torch.linspace(0, 1, 21)[::5])}[case]
+    t_span = kw.pop("t_span")
+    solver = kw.pop("solver")
+    res = {}
+    for disabled in (True, False):
+        fused.DISABLED = disabled
+        try:
+            with torch.no_grad():
+                res[disabled] = odeint(field, x, t_span, solver, **kw)
+            if not disabled:
+                assert "tdyn_lin_tc_apply" in (fused.last_used() or ""), fused.last_used()
+        finally:
+            fused.DISABLED = False
+    (t0, s0), (t1, s1) = res[True], res[False]
+    if case == "all_eval":
+        # every accepted step is returned: the step SIZES of a default-initialised net at tol 1e-5 are decided at the
+        # fp32 noise floor of the error estimate, so only the end points are comparable between two f implementations
+        assert abs(t0.shape[0] - t1.shape[0]) <= 2 and torch.allclose(t0[[0, -1]], t1[[0, -1]])
+        t0, s0, t1, s1 = t0[-1:], s0[-1:], t1[-1:], s1[-1:]
+    assert t0.shape == t1.shape and torch.allclose(t0, t1, rtol=2e-4, atol=1e-6)
+    assert_close(s1, s0, f"solution ({case})", rtol=1e-4, atol_scale=2e-5)

@@ -29,6 +29,11 @@ def last_used():
     return _last
 
 
+def reset_last():
+    global _last
+    _last = None
+
+
 class MLPField(nn.Module):
     """Functional-API helper: ``odeint(MLPField(net), x, t_span, ...)`` == ``odeint(lambda t, x: net(x), ...)`` but
     lets the library see (and fuse) the network."""
@@ -639,7 +644,6 @@ def try_fixed(f, x, ts, sv, solver) -> Optional[List[torch.Tensor]]:
     ``tdyn_mlp_tc_stage`` launch per RK stage (stage combination in its prologue, the solution update in the
     last stage's epilogue).  Returns the list of saved states or None when the generic path must be used."""
     global _last
-    _last = None
     if DISABLED or not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
         return None
     if isinstance(f, FusedField):

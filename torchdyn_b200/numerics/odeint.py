@@ -65,6 +65,8 @@ def odeint(f: Callable, x: Tensor, t_span: Union[List, Tensor], solver: Union[st
     if isinstance(x, Tensor) and x.is_cuda and (type(solver) == str or type(solver) in BUILTIN_TYPES) \
             and not torch.is_grad_enabled():
         from .. import fused
+        if not hasattr(f, "tdyn_eval"):     # (the adjoints' own dynamics objects keep the label of the user-level solve)
+            fused.reset_last()
         f = fused.wrap(f, x)            # MLP vector fields are evaluated by this library's kernels (no autograd graph)
     if ts[1] < ts[0]:   # reversed time: integrate -f(-t, x) over the negated span (odeint.py:54-58)
         if verbose:
