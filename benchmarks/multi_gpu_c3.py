@@ -27,11 +27,16 @@ def main():
     import torchdyn_b200
     from torchdyn_b200 import distributed as tdist, fused
 
+    weak = "--weak" in sys.argv                 # 262 144 rows PER GPU instead of in total
     torch.manual_seed(0)
     net = nn.Sequential(nn.Linear(128, 1024), nn.Tanh(), nn.Linear(1024, 128)).to(dev)
-    B = 262144
-    g = torch.Generator().manual_seed(1)
-    x_full = torch.randn(B, 128, generator=g).to(dev)
+    B = 262144 * (world if weak else 1)
+    if weak:
+        g = torch.Generator(device=dev).manual_seed(1 + rank)
+        x_full = None
+    else:
+        g = torch.Generator().manual_seed(1)
+        x_full = torch.randn(B, 128, generator=g).to(dev)
     t_span = torch.linspace(0, 1, 2)
 
     def step(x, sharded):
@@ -61,12 +66,16 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
         return ms, nfe
 
-    shard = tdist.shard(x_full, rank, world).contiguous()
+    shard = (torch.randn(262144, 128, generator=g, device=dev) if weak else tdist.shard(x_full, rank, world).contiguous())
     ms, nfe_s = timed(shard, True)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     g_s = [p.grad.clone() for p in net.parameters()]
     path = fused.last_used()
-    if rank == 0:
+    if rank == 0 and weak:
+        print(json.dumps({"config": "c3 tsit5 + interpolated adjoint, MLP 128-1024-128, 262144 rows per GPU (weak scaling)",
+                          "world": world, "global_batch": B, "ms_per_iter_sharded_max_over_ranks": float(ms),
+                          "sample_nfe_per_s": B * nfe_s / (float(ms) * 1e-3), "nfe_sharded": nfe_s, "path": path}), flush=True)
+    elif rank == 0:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         step(x_full, False)
         e0.record()
