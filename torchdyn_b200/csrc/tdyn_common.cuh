@@ -64,4 +64,15 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Per-device kernel attributes (opt-in shared memory sizes) live in each device's context: true exactly once per
+// (calling thread, current device) for the `seen` mask of one call site.
+inline bool first_use_on_device(unsigned long long& seen) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen & bit) return false;
+    seen |= bit;
+    return true;
+}
+
 }  // namespace tdyn

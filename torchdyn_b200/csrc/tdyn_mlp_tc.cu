@@ -539,12 +539,11 @@ int tdyn_mlp_tc_stage(const tdyn_mlp_t* m, const void* wsplit, float* k_out, flo
     P.act = m->act;
     const int grid = P.num_tiles < kNumSMs ? P.num_tiles : kNumSMs;
     cudaStream_t st = (cudaStream_t)stream;
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
+    static thread_local unsigned long long seen = 0;
+    if (first_use_on_device(seen)) {
         TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
         TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_SOFTPLUS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
         TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
-        attr_set = true;
     }
     switch (m->act) {
         case TDYN_ACT_TANH: tc::mlp_tc_stage_kernel<TDYN_ACT_TANH><<<grid, tc::kThreads, tc::kSmemTotal, st>>>(P); break;

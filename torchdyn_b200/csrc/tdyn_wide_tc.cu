@@ -686,10 +686,9 @@ using namespace tdyn;
 
 template <int ACT, int MODE>
 static int launch_lin(const wtc::LinParams& P, int grid, cudaStream_t st) {
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
+    static thread_local unsigned long long seen = 0;
+    if (first_use_on_device(seen)) {
         TDYN_CHECK_CUDA(cudaFuncSetAttribute(wtc::lin_tc_kernel<ACT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, wtc::kLSmemTotal));
-        attr_set = true;
     }
     wtc::lin_tc_kernel<ACT, MODE><<<grid, wtc::kThreads, wtc::kLSmemTotal, st>>>(P);
     TDYN_CHECK_CUDA(cudaGetLastError());
@@ -766,10 +765,9 @@ int tdyn_wgrad_tc(const float* g, int n_out, const float* in, int k_in, float* d
     P.No = n_out; P.Ki = k_in; P.Nk = p.Nk; P.n_tiles = p.n_tiles; P.k_tiles = p.k_tiles; P.splits = p.splits;
     P.rows = rows; P.rows_per_split = p.rows_per_split;
     cudaStream_t st = (cudaStream_t)stream;
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
+    static thread_local unsigned long long seen = 0;
+    if (first_use_on_device(seen)) {
         TDYN_CHECK_CUDA(cudaFuncSetAttribute(wtc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wtc::kWSmemTotal));
-        attr_set = true;
     }
     wtc::wgrad_tc_kernel<<<p.n_tiles * p.k_tiles * p.splits, wtc::kThreads, wtc::kWSmemTotal, st>>>(P);
     TDYN_CHECK_CUDA(cudaGetLastError());
