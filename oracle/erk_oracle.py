@@ -441,8 +441,9 @@ def _flat_params(vf) -> Tensor:
     return torch.cat([p.contiguous().flatten() for p in vf.parameters()])
 
 
-def _vjp_pack(vf, t, x, lam, with_dt: bool):
-    """(dx, dlam, dmu[, dt]) = (f, -lam^T df/dx, -lam^T df/dtheta[, -lam^T df/dt])  (sensitivity.py:62-74)."""
+def _vjp_pack(vf, t, x, lam, with_dt: bool, integral_loss=None):
+    """(dx, dlam, dmu[, dt]) = (f, -lam^T df/dx [- dg/dx], -lam^T df/dtheta[, -lam^T df/dt])  (sensitivity.py:62-74;
+    the running cost g = integral_loss(t, x) enters the co-state dynamics, :67-69 and :141-143)."""
     with torch.set_grad_enabled(True):
         x = x.requires_grad_(True)
         t = t.requires_grad_(True)
@@ -450,6 +451,9 @@ def _vjp_pack(vf, t, x, lam, with_dt: bool):
         params = tuple(vf.parameters())
         g = torch.autograd.grad(dx, (x, t) + params, -lam, allow_unused=True, retain_graph=False)
         dlam, dtt, dmu = g[0], g[1], g[2:]
+        if integral_loss:
+            dg = torch.autograd.grad(integral_loss(t, x).sum(), x, allow_unused=True, retain_graph=True)[0]
+            dlam = dlam - dg
         dmu = torch.cat([e.flatten() if e is not None else torch.zeros(1) for e in dmu], dim=-1)
         if dtt is None:
             dtt = torch.zeros(1).to(t)
@@ -459,7 +463,7 @@ def _vjp_pack(vf, t, x, lam, with_dt: bool):
 
 
 def make_adjoint_function(vf, solver, atol, rtol, interpolator, solver_adjoint, atol_adjoint, rtol_adjoint,
-                          kind: str, traces: Optional[list] = None):
+                          kind: str, traces: Optional[list] = None, integral_loss=None):
     """Build the autograd.Function for ``kind`` in {'adjoint', 'interpolated_adjoint'}.
     ``traces``: optional list; a Trace is appended per odeint call (forward first, then each backward interval)."""
     assert kind in ("adjoint", "interpolated_adjoint")
@@ -493,7 +497,7 @@ def make_adjoint_function(vf, solver, atol, rtol, interpolator, solver_adjoint, 
                     t = t[0]
                 x = A[:n].reshape(xT.shape)
                 lam = A[n:2 * n].reshape(lamT.shape)
-                dx, dlam, dmu, dtt = _vjp_pack(vf, t, x, lam, True)
+                dx, dlam, dmu, dtt = _vjp_pack(vf, t, x, lam, True, integral_loss)
                 return torch.cat([dx.flatten(), dlam.flatten(), dmu.flatten(), dtt.flatten()])
 
             dLdt = torch.zeros(len(t_sol)).to(xT)
@@ -533,7 +537,7 @@ def make_adjoint_function(vf, solver, atol, rtol, interpolator, solver_adjoint, 
                     t = t[0]
                 x = spline.evaluate(t)
                 lam = A[:n].reshape(lamT.shape)
-                _, dlam, dmu, _ = _vjp_pack(vf, t, x, lam, False)
+                _, dlam, dmu, _ = _vjp_pack(vf, t, x, lam, False, integral_loss)
                 return torch.cat([dlam.flatten(), dmu.flatten()])
 
             for i in range(len(t_span) - 1, 0, -1):
@@ -554,9 +558,10 @@ class OracleNeuralODE(torch.nn.Module):
     ``vf`` is called as vf(t, x); modules taking only x are wrapped; ``nfe`` counts calls (defunc.py:61)."""
 
     def __init__(self, vector_field, solver="tsit5", atol=1e-3, rtol=1e-3, sensitivity="autograd",
-                 solver_adjoint=None, atol_adjoint=1e-4, rtol_adjoint=1e-4, interpolator=None):
+                 solver_adjoint=None, atol_adjoint=1e-4, rtol_adjoint=1e-4, interpolator=None, integral_loss=None):
         super().__init__()
         import inspect
+        self.integral_loss = integral_loss
         self.net = vector_field
         fwd = vector_field.forward if isinstance(vector_field, torch.nn.Module) else vector_field
         self._has_t = "t" in inspect.getfullargspec(fwd).args
@@ -572,6 +577,14 @@ class OracleNeuralODE(torch.nn.Module):
 
     def vf(self, t, x):
         self.nfe += 1
+        if self.integral_loss is not None and self.sensitivity == "autograd":
+            # the running cost is integrated in column 0 of the (user-augmented) state (core/defunc.py:68-77)
+            x_dyn = x[:, 1:]
+            dlds = self.integral_loss(t, x_dyn)
+            if len(dlds.shape) == 1:
+                dlds = dlds[:, None]
+            f = self.net(t, x_dyn) if self._has_t else self.net(x_dyn)
+            return torch.cat([dlds, f], 1).to(f)
         return self.net(t, x) if self._has_t else self.net(x)
 
     def forward(self, x, t_span=None):
@@ -584,7 +597,7 @@ class OracleNeuralODE(torch.nn.Module):
             return odeint(vfw, x, t_span, self.solver, self.atol, self.rtol, self.interpolator,
                           tableau_dtype=torch.float32, trace=tr)
         fn = make_adjoint_function(vfw, self.solver, self.atol, self.rtol, self.interpolator, self.solver_adjoint,
-                                   self.atol_adjoint, self.rtol_adjoint, self.sensitivity, self.traces)
+                                   self.atol_adjoint, self.rtol_adjoint, self.sensitivity, self.traces, self.integral_loss)
         return fn.apply(_flat_params(vfw), x, t_span)
 
 

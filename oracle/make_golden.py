@@ -150,6 +150,19 @@ def neuralode_cases():
     cases["act_tsit5_interp"] = dict(
         dims=[4, 64, 4], act="tanh", seed=5, gain=4.0, x=xa, y=None, t_span=torch.tensor([0.0, 4.0]), loss="sqmean",
         kw=dict(solver="tsit5", atol=1e-4, rtol=1e-4, sensitivity="interpolated_adjoint"))
+    # integral losses (reference sensitivity.py:67-69, 141-143; core/defunc.py:68-77): adjoint / interpolated adjoint add
+    # -dg/dx to the co-state dynamics; sensitivity='autograd' propagates the running cost in column 0 of the state
+    torch.manual_seed(13)
+    xi = torch.randn(96, 4)
+    cases["il_dopri5_adjoint"] = dict(
+        dims=[4, 32, 4], act="tanh", seed=13, x=xi, y=None, t_span=torch.linspace(0, 1, 3), loss="sqmean", integral="sq",
+        kw=dict(solver="dopri5", atol=1e-5, rtol=1e-5, sensitivity="adjoint", atol_adjoint=1e-5, rtol_adjoint=1e-5))
+    cases["il_tsit5_interp"] = dict(
+        dims=[4, 32, 4], act="tanh", seed=13, x=xi, y=None, t_span=torch.linspace(0, 1, 3), loss="sqmean", integral="sq",
+        kw=dict(solver="tsit5", atol=1e-5, rtol=1e-5, sensitivity="interpolated_adjoint"))
+    cases["il_rk4_autograd"] = dict(
+        dims=[4, 32, 4], act="tanh", seed=13, x=torch.cat([torch.zeros(96, 1), xi], 1), y=None,
+        t_span=torch.linspace(0, 1, 11), loss="il_aug", integral="sq", kw=dict(solver="rk4", sensitivity="autograd"))
     # wide nets (widths multiples of 32, hidden 256): the layer-wise tensor-core kernels (tdyn_lin_tc_apply / tdyn_wgrad_tc)
     torch.manual_seed(9)
     cases["w256_tsit5_interp"] = dict(
@@ -163,7 +176,11 @@ def neuralode_cases():
     return cases
 
 
+INTEGRALS = {"sq": lambda t, x: 0.5 * x.pow(2).sum(1)}          # running cost of the integral-loss cases
+
 LOSSES = {
+    # terminal cost + the integral propagated in column 0 of the augmented state (sensitivity='autograd' + integral_loss)
+    "il_aug": lambda sol, y: sol[-1][:, 1:].pow(2).mean() + sol[-1][:, 0].mean(),
     "sq": lambda sol, y: sol[-1].pow(2).sum(),
     "sqmean": lambda sol, y: sol[-1].pow(2).mean(),
     "ce": lambda sol, y: nn.CrossEntropyLoss()(sol[-1], y),
@@ -215,11 +232,14 @@ def main():
             continue
         net = mlp(c["dims"], c["act"], c["seed"], c.get("gain", 1.0))
         loss_fn = (lambda sol, c=c: LOSSES[c["loss"]](sol, c["y"]))
-        out = run_ref_neuralode(net, c["x"], c["t_span"], loss_fn, **c["kw"])
+        kw_ref = dict(c["kw"])
+        if c.get("integral"):
+            kw_ref["integral_loss"] = INTEGRALS[c["integral"]]
+        out = run_ref_neuralode(net, c["x"], c["t_span"], loss_fn, **kw_ref)
         if args.check:
-            check_same(out, run_oracle_neuralode(net, c["x"], c["t_span"], loss_fn, **c["kw"]), name)
+            check_same(out, run_oracle_neuralode(net, c["x"], c["t_span"], loss_fn, **kw_ref), name)
         fix = dict(kind="neuralode", dims=c["dims"], act=c["act"], x=c["x"], y=c["y"], t_span=c["t_span"], loss=c["loss"],
-                   kw=c["kw"], params=[p.detach().clone() for p in net.parameters()], ref=out)
+                   kw=c["kw"], integral=c.get("integral"), params=[p.detach().clone() for p in net.parameters()], ref=out)
         torch.save(fix, os.path.join(OUT, name + ".pt"))
         ntr = [len(r["t"]) for r in out["traces"]]
         print(f"{name}: nfe={out['nfe_total']:.0f} attempts per odeint call={ntr} len(t_eval)={len(out['t_eval'])}")

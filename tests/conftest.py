@@ -56,7 +56,10 @@ class VDP(nn.Module):
         return torch.cat([x2 * self.p, self.alpha * (1 - x1 ** 2) * x2 - x1], -1)
 
 
+INTEGRALS = {"sq": lambda t, x: 0.5 * x.pow(2).sum(1)}          # running cost of the integral-loss fixtures
+
 LOSSES = {
+    "il_aug": lambda sol, y: sol[-1][:, 1:].pow(2).mean() + sol[-1][:, 0].mean(),
     "sq": lambda sol, y: sol[-1].pow(2).sum(),
     "sqmean": lambda sol, y: sol[-1].pow(2).mean(),
     "ce": lambda sol, y: nn.CrossEntropyLoss()(sol[-1], y),
@@ -64,7 +67,8 @@ LOSSES = {
 
 NEURALODE_CASES = ["c1_moons_dopri5_adjoint", "c1_moons_tsit5_interp", "mlp3_tsit5_adjoint_tspan5",
                    "mlp_relu_dopri5_interp_tspan4", "c3r_tsit5_interp", "act_dopri5_adjoint", "act_tsit5_interp",
-                   "w256_tsit5_interp", "w256_dopri5_adjoint"]
+                   "w256_tsit5_interp", "w256_dopri5_adjoint",
+                   "il_dopri5_adjoint", "il_tsit5_interp", "il_rk4_autograd"]
 FUNCTIONAL_CASES = ["fn_euler_tspan10", "fn_midpoint_tspan10", "fn_rk4_tspan10", "fn_dopri5_tspan10", "fn_tsit5_tspan10",
                     "fn_dopri5_4th_tspan10", "fn_dopri5_reversed", "fn_tsit5_all_eval", "fn_rk4_save_at", "c2r_rk4_100",
                     "act_tsit5_fn", "act_dopri5_4th_fn"]

