@@ -163,6 +163,20 @@ def neuralode_cases():
     cases["il_rk4_autograd"] = dict(
         dims=[4, 32, 4], act="tanh", seed=13, x=torch.cat([torch.zeros(96, 1), xi], 1), y=None,
         t_span=torch.linspace(0, 1, 11), loss="il_aug", integral="sq", kw=dict(solver="rk4", sensitivity="autograd"))
+    # DEFunc features (reference core/defunc.py:42-94, core/neuralde.py:96-121): higher-order dynamics, depth
+    # concatenation, data control
+    torch.manual_seed(14)
+    cases["ho_order2_dopri5_adjoint"] = dict(
+        special="order2", dims=None, act=None, seed=14, x=torch.randn(48, 4), y=None, t_span=torch.linspace(0, 1, 3),
+        loss="sqmean", kw=dict(order=2, solver="dopri5", atol=1e-5, rtol=1e-5, sensitivity="adjoint", atol_adjoint=1e-5,
+                               rtol_adjoint=1e-5))
+    cases["dc_depthcat_tsit5_autograd"] = dict(
+        special="depthcat_datacontrol", dims=None, act=None, seed=15, x=torch.randn(48, 3), y=None,
+        t_span=torch.linspace(0, 1, 3), loss="sqmean", kw=dict(solver="tsit5", atol=1e-5, rtol=1e-5, sensitivity="autograd"))
+    cases["dc_depthcat_dopri5_interp"] = dict(
+        special="depthcat_datacontrol", dims=None, act=None, seed=15, x=torch.randn(48, 3), y=None,
+        t_span=torch.linspace(0, 1, 3), loss="sqmean", kw=dict(solver="dopri5", atol=1e-5, rtol=1e-5,
+                                                                sensitivity="interpolated_adjoint"))
     # wide nets (widths multiples of 32, hidden 256): the layer-wise tensor-core kernels (tdyn_lin_tc_apply / tdyn_wgrad_tc)
     torch.manual_seed(9)
     cases["w256_tsit5_interp"] = dict(
@@ -174,6 +188,16 @@ def neuralode_cases():
         loss="sqmean", kw=dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="adjoint", atol_adjoint=1e-4,
                                rtol_adjoint=1e-4))
     return cases
+
+
+def special_net(kind, layers, seed):
+    """Vector fields that are not plain MLPs; `layers` provides DepthCat / DataControl (reference torchdyn.nn here)."""
+    torch.manual_seed(seed)
+    if kind == "order2":            # second-order system on [q, p]: the net maps the full state to the acceleration
+        return nn.Sequential(nn.Linear(4, 16), nn.Tanh(), nn.Linear(16, 2))
+    if kind == "depthcat_datacontrol":   # state 3 + control 3 + depth 1 -> 3
+        return nn.Sequential(layers.DataControl(), layers.DepthCat(1), nn.Linear(7, 16), nn.Tanh(), nn.Linear(16, 3))
+    raise ValueError(kind)
 
 
 INTEGRALS = {"sq": lambda t, x: 0.5 * x.pow(2).sum(1)}          # running cost of the integral-loss cases
@@ -230,7 +254,11 @@ def main():
     for name, c in neuralode_cases().items():
         if only and name not in only:
             continue
-        net = mlp(c["dims"], c["act"], c["seed"], c.get("gain", 1.0))
+        if c.get("special"):
+            import torchdyn.nn as ref_layers
+            net = special_net(c["special"], ref_layers, c["seed"])
+        else:
+            net = mlp(c["dims"], c["act"], c["seed"], c.get("gain", 1.0))
         loss_fn = (lambda sol, c=c: LOSSES[c["loss"]](sol, c["y"]))
         kw_ref = dict(c["kw"])
         if c.get("integral"):
@@ -239,7 +267,7 @@ def main():
         if args.check:
             check_same(out, run_oracle_neuralode(net, c["x"], c["t_span"], loss_fn, **kw_ref), name)
         fix = dict(kind="neuralode", dims=c["dims"], act=c["act"], x=c["x"], y=c["y"], t_span=c["t_span"], loss=c["loss"],
-                   kw=c["kw"], integral=c.get("integral"), params=[p.detach().clone() for p in net.parameters()], ref=out)
+                   kw=c["kw"], integral=c.get("integral"), special=c.get("special"), params=[p.detach().clone() for p in net.parameters()], ref=out)
         torch.save(fix, os.path.join(OUT, name + ".pt"))
         ntr = [len(r["t"]) for r in out["traces"]]
         print(f"{name}: nfe={out['nfe_total']:.0f} attempts per odeint call={ntr} len(t_eval)={len(out['t_eval'])}")

@@ -56,6 +56,22 @@ class VDP(nn.Module):
         return torch.cat([x2 * self.p, self.alpha * (1 - x1 ** 2) * x2 - x1], -1)
 
 
+def special_net(kind, params=None, device="cpu"):
+    """The non-MLP vector fields of the fixtures (same construction as oracle/make_golden.py, with this package's layers)."""
+    from torchdyn_b200.nn import DataControl, DepthCat
+    if kind == "order2":
+        net = nn.Sequential(nn.Linear(4, 16), nn.Tanh(), nn.Linear(16, 2))
+    elif kind == "depthcat_datacontrol":
+        net = nn.Sequential(DataControl(), DepthCat(1), nn.Linear(7, 16), nn.Tanh(), nn.Linear(16, 3))
+    else:
+        raise ValueError(kind)
+    if params is not None:
+        with torch.no_grad():
+            for p, v in zip(net.parameters(), params):
+                p.copy_(v)
+    return net.to(device)
+
+
 INTEGRALS = {"sq": lambda t, x: 0.5 * x.pow(2).sum(1)}          # running cost of the integral-loss fixtures
 
 LOSSES = {
@@ -68,7 +84,8 @@ LOSSES = {
 NEURALODE_CASES = ["c1_moons_dopri5_adjoint", "c1_moons_tsit5_interp", "mlp3_tsit5_adjoint_tspan5",
                    "mlp_relu_dopri5_interp_tspan4", "c3r_tsit5_interp", "act_dopri5_adjoint", "act_tsit5_interp",
                    "w256_tsit5_interp", "w256_dopri5_adjoint",
-                   "il_dopri5_adjoint", "il_tsit5_interp", "il_rk4_autograd"]
+                   "il_dopri5_adjoint", "il_tsit5_interp", "il_rk4_autograd",
+                   "ho_order2_dopri5_adjoint", "dc_depthcat_tsit5_autograd", "dc_depthcat_dopri5_interp"]
 FUNCTIONAL_CASES = ["fn_euler_tspan10", "fn_midpoint_tspan10", "fn_rk4_tspan10", "fn_dopri5_tspan10", "fn_tsit5_tspan10",
                     "fn_dopri5_4th_tspan10", "fn_dopri5_reversed", "fn_tsit5_all_eval", "fn_rk4_save_at", "c2r_rk4_100",
                     "act_tsit5_fn", "act_dopri5_4th_fn"]

@@ -10,7 +10,7 @@ import torchdyn_b200
 from torchdyn_b200.numerics import odeint as product_odeint
 import sys
 odeint_mod = sys.modules["torchdyn_b200.numerics.odeint"]   # the package re-exports a function of the same name
-from conftest import INTEGRALS, LOSSES, VDP, build_mlp
+from conftest import INTEGRALS, LOSSES, VDP, build_mlp, special_net
 
 # Tolerances (north_star): identical accepted-step count / accept-reject sequence; t, dt sequence equal to fp32
 # round-off (CPU vs GPU powf / tanhf / GEMM summation order differ in the last bits); final state and gradients
@@ -78,7 +78,8 @@ def assert_traces(ref_traces, got_traces, exact=False):
 
 
 def run_neuralode_case(fx, device, net=None):
-    net = build_mlp(fx["dims"], fx["act"], fx["params"], device) if net is None else net
+    if net is None:
+        net = special_net(fx["special"], fx["params"], device) if fx.get("special") else build_mlp(fx["dims"], fx["act"], fx["params"], device)
     y = fx["y"].to(device) if fx.get("y") is not None else None
     kw = dict(fx["kw"])
     if fx.get("integral"):

@@ -33,6 +33,8 @@ def _check_traces(ref_traces, ora_traces):
 def test_oracle_neuralode_bit_exact(name):
     torch.set_num_threads(1)
     fx = load_golden(name)
+    if fx.get("special"):
+        pytest.skip("DEFunc features (order, DepthCat, DataControl) belong to the module API, which the oracle does not restate")
     net = build_mlp(fx["dims"], fx["act"], fx["params"])
     model, x, t_eval, sol, loss = _run_oracle(net, fx, lambda s: LOSSES[fx["loss"]](s, fx["y"]))
     ref = fx["ref"]
