@@ -395,6 +395,23 @@ def main():
     torch.save(hyb, os.path.join(OUT, "fn_hybrid_bouncing_ball.pt"))
     print(f"fn_hybrid_bouncing_ball: {[tuple(hyb[sv]['sol'].shape) for sv in ('dopri5', 'tsit5')]}")
 
+    # ODEProblem on a parameter-free callable with `optimizable_params` (reference core/problems.py:82-93)
+    from torchdyn.core import ODEProblem as RefProblem
+    opt = {}
+    for sens in ("adjoint", "interpolated_adjoint", "autograd"):
+        torch.manual_seed(0)
+        A = nn.Parameter(torch.randn(3, 3) * 0.5)
+        prob = RefProblem(lambda t, x, args={}: torch.tanh(x @ A.T) * (1 + t), solver="dopri5", sensitivity=sens, atol=1e-5,
+                          rtol=1e-5, atol_adjoint=1e-5, rtol_adjoint=1e-5, optimizable_params=[A])
+        xo = torch.randn(20, 3, generator=torch.Generator().manual_seed(1)).requires_grad_(True)
+        _, so = prob.odeint(xo, torch.linspace(0, 1, 3))
+        so[-1].pow(2).mean().backward()
+        opt[sens] = dict(sol=so.detach(), gx=xo.grad.clone(), gA=A.grad.clone())
+    torch.manual_seed(0)
+    torch.save(dict(A=torch.randn(3, 3) * 0.5, x=torch.randn(20, 3, generator=torch.Generator().manual_seed(1)),
+                    t_span=torch.linspace(0, 1, 3), ref=opt), os.path.join(OUT, "api_optimizable_params.pt"))
+    print("api_optimizable_params: ok")
+
     # spline: self-consistency vector (UNPINNED against torchcde, see oracle/__init__.py)
     torch.manual_seed(31)
     xs = torch.randn(5, 9, 3)

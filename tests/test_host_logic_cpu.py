@@ -281,3 +281,23 @@ def test_odeint_hybrid_bouncing_ball_bit_identical_to_reference(solver):
         t_eval, sol = odeint_hybrid(_Ball(), fx["x"], fx["t_span"], fx["j_span"], solver, [_Bounce()], atol=fx["atol"],
                                     rtol=fx["rtol"], event_tol=fx["event_tol"])
     assert torch.equal(t_eval, fx[solver]["t_eval"]) and torch.equal(sol, fx[solver]["sol"])
+
+
+@pytest.mark.parametrize("sens", ["adjoint", "interpolated_adjoint", "autograd"])
+def test_odeproblem_optimizable_params_matches_reference(sens):
+    """ODEProblem on a parameter-free callable whose trainable tensor is handed over through `optimizable_params`
+    (reference core/problems.py:82-93): time-dependent field, gradients w.r.t. the state and that tensor."""
+    from torchdyn_b200.core import ODEProblem
+    fx = load_golden("api_optimizable_params")
+    A = nn.Parameter(fx["A"].clone())
+    prob = ODEProblem(lambda t, x, args={}: torch.tanh(x @ A.T) * (1 + t), solver="dopri5", sensitivity=sens, atol=1e-5,
+                      rtol=1e-5, atol_adjoint=1e-5, rtol_adjoint=1e-5, optimizable_params=[A])
+    x = fx["x"].clone().requires_grad_(True)
+    _, sol = prob.odeint(x, fx["t_span"])
+    sol[-1].pow(2).mean().backward()
+    ref = fx["ref"][sens]
+    assert torch.equal(sol.detach(), ref["sol"])
+    if sens == "autograd":      # differently shaped autograd graph: fp32 round-off (see parity_helpers.check_neuralode_case)
+        assert torch.allclose(x.grad, ref["gx"], rtol=2e-6, atol=1e-7) and torch.allclose(A.grad, ref["gA"], rtol=2e-6, atol=2e-7)
+    else:
+        assert torch.equal(x.grad, ref["gx"]) and torch.equal(A.grad, ref["gA"])
