@@ -14,7 +14,7 @@ absent from the reference tree; restated from its published algorithm: UNPINNED)
 from __future__ import annotations
 
 from fractions import Fraction as Fr
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional
 
 import torch
 from torch import Tensor

@@ -10,7 +10,7 @@ import torchdyn_b200
 from torchdyn_b200.numerics import odeint as product_odeint
 import sys
 odeint_mod = sys.modules["torchdyn_b200.numerics.odeint"]   # the package re-exports a function of the same name
-from conftest import INTEGRALS, LOSSES, VDP, build_mlp, special_net
+from conftest import INTEGRALS, LOSSES, build_mlp, special_net
 
 # Tolerances (north_star): identical accepted-step count / accept-reject sequence; t, dt sequence equal to fp32
 # round-off (CPU vs GPU powf / tanhf / GEMM summation order differ in the last bits); final state and gradients

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _kernels, _lib
-from ._lib import ACT_RELU, ACT_SOFTPLUS, ACT_TANH, MODE_CHAIN, MODE_INNER
+from ._lib import ACT_RELU, ACT_SOFTPLUS, ACT_TANH, MODE_INNER
 
 f32 = np.float32
 DISABLED = False          # bench.py --force-generic / A-B parity runs: keep f a torch call
