@@ -10,8 +10,10 @@ Contents
 --------
 ``erk_oracle.py``   torch-CPU restatement of the reference algorithm
                     (tableaus, steppers, controller, adaptive / fixed loops,
-                    dense output, backsolve + interpolated adjoint, natural
-                    cubic spline).  Every function cites the reference
+                    dense output, backsolve + interpolated adjoint incl.
+                    integral losses, natural cubic spline, hybrid / ALF
+                    loops are pinned through fixtures of the executed
+                    reference instead).  Every function cites the reference
                     file:line it follows.
 ``ref_shim.py``     imports the *real* reference from ``/root/reference`` with
                     the three absent third-party packages stubbed.  Only
