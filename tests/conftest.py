@@ -15,6 +15,33 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+# ---- strict / loose bookkeeping of the end-to-end fixture comparisons (tests/parity_helpers.py::assert_traces) ----------
+# Every fixture comparison records, per odeint call, whether the STRICT step-sequence comparison passed.  The table is
+# printed at the end of the pytest run (so GPUTEST logs show it) and every GPU fixture test asserts that a fixture whose
+# name is not in tests/golden/LOOSE_ALLOWED.json went strict on every call.
+STRICT_REPORT = {}        # fixture name -> [bool per odeint call]
+
+
+def loose_allowed():
+    import json
+    with open(os.path.join(GOLDEN, "LOOSE_ALLOWED.json")) as fh:
+        return set(json.load(fh)["fixtures"])
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    if not STRICT_REPORT:
+        return
+    tr = terminalreporter
+    tr.write_sep("-", "fixture step-sequence comparison: strict (S) / loose fallback (L) per odeint call")
+    allowed = loose_allowed()
+    for name in sorted(STRICT_REPORT):
+        flags = STRICT_REPORT[name]
+        mark = "strict" if all(flags) else ("LOOSE (allow-listed)" if name in allowed else "LOOSE (NOT allowed)")
+        tr.write_line(f"  {name:40s} {''.join('S' if f else 'L' for f in flags):24s} {mark}")
+    n_loose = sum(not all(f) for f in STRICT_REPORT.values())
+    tr.write_line(f"  {len(STRICT_REPORT) - n_loose} of {len(STRICT_REPORT)} fixtures strict on every call")
+
+
 def pytest_collection_modifyitems(config, items):
     if torch.cuda.is_available():
         return
@@ -83,13 +110,14 @@ LOSSES = {
 
 NEURALODE_CASES = ["c1_moons_dopri5_adjoint", "c1_moons_tsit5_interp", "mlp3_tsit5_adjoint_tspan5",
                    "mlp_relu_dopri5_interp_tspan4", "c3r_tsit5_interp", "act_dopri5_adjoint", "act_tsit5_interp",
-                   "w256_tsit5_interp", "w256_dopri5_adjoint",
+                   "w256_tsit5_interp", "w256_dopri5_adjoint", "act_w256x2_dopri5_adjoint", "act_w1024_tsit5_interp",
                    "il_dopri5_adjoint", "il_tsit5_interp", "il_rk4_autograd",
                    "ho_order2_dopri5_adjoint", "dc_depthcat_tsit5_autograd", "dc_depthcat_dopri5_interp"]
 FUNCTIONAL_CASES = ["fn_euler_tspan10", "fn_midpoint_tspan10", "fn_rk4_tspan10", "fn_dopri5_tspan10", "fn_tsit5_tspan10",
                     "fn_dopri5_4th_tspan10", "fn_dopri5_reversed", "fn_tsit5_all_eval", "fn_rk4_save_at", "c2r_rk4_100",
                     "act_tsit5_fn", "act_dopri5_4th_fn"]
 # fixtures whose controller is ACTIVE (error ratios ~0.2-0.9, rejections): the GPU must reproduce the step sequence
-ACTIVE_CASES = ["act_dopri5_adjoint", "act_tsit5_interp", "act_tsit5_fn", "act_dopri5_4th_fn"]
+ACTIVE_CASES = ["act_dopri5_adjoint", "act_tsit5_interp", "act_tsit5_fn", "act_dopri5_4th_fn",
+                "act_w256x2_dopri5_adjoint", "act_w1024_tsit5_interp"]
 VDP_CASES = ["vdp_dopri5_adjoint", "vdp_tsit5_adjoint", "vdp_dopri5_interpolated_adjoint",
              "vdp_tsit5_interpolated_adjoint"]

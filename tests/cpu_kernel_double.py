@@ -21,6 +21,11 @@ class CpuKernels:
         (exact while numel < 2**29): lets the host controller reproduce the reference's fp32 mean bit for bit."""
         return v.abs().pow(2).mean().double() * v.numel()
 
+    @staticmethod
+    def sqrt32(v):
+        """torch's CPU fp32 sqrt (what the executed reference used; differs from the IEEE sqrt in ~0.6 % of the cases)"""
+        return np.float32(torch.tensor(float(v), dtype=torch.float32).sqrt().item())
+
     def empty_like(self, x):
         return torch.empty_like(x)
 

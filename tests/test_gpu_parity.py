@@ -14,7 +14,7 @@ from torchdyn_b200 import _kernels
 from torchdyn_b200._lib import MODE_CHAIN, MODE_INNER
 from torchdyn_b200.numerics import odeint
 from torchdyn_b200.numerics.spline import NaturalCubicSpline
-from conftest import FUNCTIONAL_CASES, NEURALODE_CASES, VDP, VDP_CASES, build_mlp, load_golden
+from conftest import ACTIVE_CASES, FUNCTIONAL_CASES, NEURALODE_CASES, VDP, VDP_CASES, build_mlp, load_golden
 from cpu_kernel_double import CpuKernels
 from oracle import erk_oracle as eo
 from parity_helpers import (assert_close, check_functional_case, check_neuralode_case, run_cnf_case,
@@ -143,23 +143,23 @@ def test_spline_matches_checker(m):
 @pytest.mark.parametrize("name", [n for n in FUNCTIONAL_CASES if not n.startswith("act_")])
 def test_functional_odeint_matches_reference(name):
     fx = load_golden(name)
-    check_functional_case(fx, *run_functional_case(fx, DEV))
+    check_functional_case(fx, *run_functional_case(fx, DEV), name=name)
 
 
 @pytest.mark.parametrize("name", [n for n in NEURALODE_CASES if not n.startswith("act_")])
 def test_neuralode_adjoints_match_reference(name):
     fx = load_golden(name)
-    check_neuralode_case(fx, run_neuralode_case(fx, DEV))
+    check_neuralode_case(fx, run_neuralode_case(fx, DEV), name=name)
 
 
 @pytest.mark.parametrize("name", VDP_CASES)
 def test_vdp_adjoint_matches_reference(name):
     fx = load_golden(name)
     f = VDP(fx["alpha"]).to(DEV)
-    check_neuralode_case(fx, run_neuralode_case(dict(fx, dims=None, act=None, params=None), DEV, net=f))
+    check_neuralode_case(fx, run_neuralode_case(dict(fx, dims=None, act=None, params=None), DEV, net=f), name=name)
 
 
-@pytest.mark.parametrize("name", ["act_tsit5_fn", "act_dopri5_4th_fn", "act_dopri5_adjoint", "act_tsit5_interp"])
+@pytest.mark.parametrize("name", ACTIVE_CASES)
 def test_active_controller_step_sequence_identical(name):
     """Fixtures whose error ratios sit at 0.2-0.9 (with rejections): the GPU run must reproduce the reference's
     attempted-step count, accept/reject pattern and t sequence -- no noise-driven fallback allowed."""
@@ -168,10 +168,10 @@ def test_active_controller_step_sequence_identical(name):
     # amplified ~100x along the trajectory, so the STATE is compared at 2e-4; the step sequence is compared below.
     if fx["kind"] == "functional":
         t_eval, sol, traces = run_functional_case(fx, DEV)
-        check_functional_case(fx, t_eval, sol, traces, state_rtol=2e-4)
+        check_functional_case(fx, t_eval, sol, traces, state_rtol=2e-4, name=name)
     else:
         out = run_neuralode_case(fx, DEV)
-        check_neuralode_case(fx, out, state_rtol=2e-4)
+        check_neuralode_case(fx, out, state_rtol=2e-4, name=name)
         traces = out["traces"]
     # forward solve (first odeint call): identical attempted-step count and accept/reject pattern; step times within
     # 1e-3 (dt = dt*0.9/ratio**0.2 carries the ~1e-4..1e-3 relative noise of the error ratio of f's last bits)
@@ -185,7 +185,7 @@ def test_active_controller_step_sequence_identical(name):
 def test_cnf_hutchinson_adjoint_matches_reference():
     """cfg 4 (reduced) on the GPU: generic kernels, f and its VJPs via torch autograd."""
     fx = load_golden("c4r_cnf_hutch")
-    check_neuralode_case(fx, run_cnf_case(fx, DEV))
+    check_neuralode_case(fx, run_cnf_case(fx, DEV), name="c4r_cnf_hutch")
 
 
 def test_generic_path_against_live_oracle_conv_state():

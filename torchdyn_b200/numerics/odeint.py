@@ -274,7 +274,7 @@ class _KernelAttempt:
         if torch.is_grad_enabled() and (x.requires_grad or any(k.requires_grad for k in ks)):
             # sensitivity='autograd': the new state must stay on the graph (same values as the fused finish)
             x_new = rk_combine(kern, x, ks[:len(p.bsol)], p.bsol, 1, dt)
-        return ks[-1], x_new, ks, rms_from_sumsq(sumsq, count)
+        return ks[-1], x_new, ks, rms_from_sumsq(sumsq, count, kern)
 
     def dense(self, x, x_new, ks, t, dt, t_out):
         if type(self.interp) is FourthOrder and not (torch.is_grad_enabled() and (x_new.requires_grad or x.requires_grad)):
