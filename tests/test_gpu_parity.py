@@ -680,3 +680,100 @@ def test_odeint_hybrid_bouncing_ball_on_gpu(solver):
     assert t_eval.shape == ref_t.shape, (t_eval.shape, ref_t.shape)
     np.testing.assert_allclose(t_eval.cpu().numpy(), ref_t.numpy(), rtol=2e-4, atol=2e-4)
     assert torch.allclose(sol.cpu(), ref_s, rtol=2e-3, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------ limits, stale caches, devices
+
+def test_persistent_solver_limits_fall_back_to_the_host_loop():
+    """t_span longer than the persistent kernel's 1024-entry slot and solves needing more attempts than one launch takes
+    (4000) run on the host-driven loop instead of raising; same results as with the persistent path switched off."""
+    from torchdyn_b200 import fused
+    torch.manual_seed(3)
+    net = build_mlp([2, 32, 2], "tanh").to(DEV)
+    x = torch.randn(64, 2, device=DEV)
+    with torch.no_grad():
+        ts = torch.linspace(0, 1, 1025)
+        t_a, s_a = odeint(fused.MLPField(net), x, ts, "dopri5", atol=1e-4, rtol=1e-4)
+        assert "persistent" not in (fused.last_used() or ""), fused.last_used()
+        assert s_a.shape == (1025, 64, 2) and torch.equal(t_a.cpu(), ts)
+        fused.PERSISTENT = False
+        try:
+            _, s_b = odeint(fused.MLPField(net), x, ts, "dopri5", atol=1e-4, rtol=1e-4)
+        finally:
+            fused.PERSISTENT = True
+        assert torch.equal(s_a, s_b)
+        # more than MAX_STEPS attempts inside one launch: shrink the cap instead of building a 4000-step problem
+        old = fused.MAX_STEPS
+        fused.MAX_STEPS = 3
+        try:
+            _, s_c = odeint(fused.MLPField(net), x, torch.linspace(0, 1, 9), "dopri5", atol=1e-4, rtol=1e-4)
+        finally:
+            fused.MAX_STEPS = old
+        _, s_d = odeint(fused.MLPField(net), x, torch.linspace(0, 1, 9), "dopri5", atol=1e-4, rtol=1e-4)
+        assert "persistent" in (fused.last_used() or "")
+        assert_close(s_c, s_d, "host-loop fallback vs persistent kernel", rtol=1e-5)
+
+
+def test_weight_images_follow_in_place_updates_through_data():
+    """`p.data.mul_()` does not bump `_version`: the prepared tensor-core weight images must still follow (they are
+    re-packed at the start of every solve)."""
+    from torchdyn_b200 import fused
+    torch.manual_seed(4)
+    for dims in ([32, 256, 256, 32], [64, 256, 64]):
+        net = build_mlp(dims, "tanh").to(DEV)
+        x = torch.randn(256, dims[0], device=DEV)
+        ts = torch.linspace(0, 1, 5)
+        with torch.no_grad():
+            _, s0 = odeint(fused.MLPField(net), x, ts, "rk4")
+            for p in net.parameters():
+                p.data.mul_(1.5)
+            _, s1 = odeint(fused.MLPField(net), x, ts, "rk4")
+            assert fused.last_used() and "generic" not in fused.last_used()
+            fused.DISABLED = True
+            try:
+                _, s_ref = odeint(lambda t, y: net(y), x, ts, "rk4")
+            finally:
+                fused.DISABLED = False
+        assert not torch.allclose(s0[-1], s1[-1], rtol=1e-3)
+        assert_close(s1[-1], s_ref[-1], f"{dims}: state after an in-place .data update", rtol=2e-5, atol_scale=2e-5)
+
+
+def test_hooked_or_reparametrised_linear_layers_are_not_fused():
+    """A Linear with a forward pre-hook (old-style weight_norm recomputes `.weight` there) must be evaluated by torch."""
+    from torchdyn_b200 import fused
+    torch.manual_seed(5)
+    net = build_mlp([4, 32, 4], "tanh").to(DEV)
+    x = torch.randn(16, 4, device=DEV)
+    with torch.no_grad():
+        odeint(fused.MLPField(net), x, torch.linspace(0, 1, 3), "rk4")
+        assert fused.last_used() is not None
+        h = net[0].register_forward_pre_hook(lambda m, a: None)
+        odeint(fused.MLPField(net), x, torch.linspace(0, 1, 3), "rk4")
+        assert fused.last_used() is None, fused.last_used()
+        h.remove()
+        # the Sequential itself mutated after first use: the cached structure is re-derived
+        net[1] = torch.nn.ELU()
+        odeint(fused.MLPField(net), x, torch.linspace(0, 1, 3), "rk4")
+        assert fused.last_used() is None, fused.last_used()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_state_on_another_device_than_the_current_one():
+    """x on cuda:1 while cuda:0 is the current device (ordinary PyTorch usage): launches must go to x's device."""
+    assert torch.cuda.current_device() == 0
+    torch.manual_seed(6)
+    for dims in ([2, 64, 2], [32, 256, 256, 32]):
+        net0 = build_mlp(dims, "tanh").to("cuda:0")
+        net1 = build_mlp(dims, "tanh", [p.detach().cpu() for p in net0.parameters()], "cuda:1")
+        x = torch.randn(300, dims[0])
+        kw = dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="adjoint")
+        outs = []
+        for net, dev in ((net0, "cuda:0"), (net1, "cuda:1")):
+            m = torchdyn_b200.NeuralODE(net, **kw)
+            xx = x.to(dev).requires_grad_(True)
+            _, sol = m(xx, torch.linspace(0, 1, 2))
+            sol[-1].pow(2).mean().backward()
+            outs.append((sol[-1].detach().cpu(), xx.grad.cpu(), [p.grad.cpu() for p in net.parameters()]))
+        assert torch.cuda.current_device() == 0
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        assert all(torch.equal(a, b) for a, b in zip(outs[0][2], outs[1][2]))

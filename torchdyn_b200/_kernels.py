@@ -87,6 +87,29 @@ def _ptr(t: Optional[Tensor]):
     return None if t is None else t.data_ptr()
 
 
+def _on_own_device(fn):
+    """The C entry points launch on the calling thread's CURRENT device; a state on cuda:1 while cuda:0 is current is
+    ordinary PyTorch usage, so every launching method switches to the instance's device for the duration of the call."""
+    import functools
+
+    @functools.wraps(fn)
+    def guarded(self, *a, **k):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return guarded
+
+
+def _guard_launchers(cls):
+    skip = {"empty_like", "time_tensor"}
+    for name, attr in list(vars(cls).items()):
+        if callable(attr) and not name.startswith("_") and not isinstance(attr, staticmethod) and name not in skip:
+            setattr(cls, name, _on_own_device(attr))
+    return cls
+
+
+@_guard_launchers
 class CudaKernels:
     """One instance per (device, thread).  Owns the reduction scratch (device), its fp64 result and a
     pinned host mirror."""

@@ -33,26 +33,27 @@ class DEFunc(nn.Module):
         self._depth_modules = None
 
     def _inject_depth(self, t):
-        # the reference re-scans named_modules() on every evaluation (defunc.py:63-65); the set of modules
-        # with a `t` attribute is fixed after construction, so scan once.
-        if self._depth_modules is None:
-            object.__setattr__(self, "_depth_modules", [m for _, m in self.vf.named_modules() if hasattr(m, "t")])
-        for m in self._depth_modules:
+        # the reference re-scans named_modules() on every evaluation (defunc.py:63-65); here the list of modules with a
+        # `t` attribute is kept and re-derived whenever the module tree changed (a swapped or added layer)
+        mods = tuple(self.vf.modules()) if isinstance(self.vf, nn.Module) else ()
+        key = tuple(map(id, mods))
+        if self._depth_modules is None or self._depth_modules[0] != key:
+            object.__setattr__(self, "_depth_modules", (key, [m for m in mods if hasattr(m, "t")]))
+        for m in self._depth_modules[1]:
             m.t = t
 
     def forward(self, t: Tensor, x: Tensor, args: Dict = {}) -> Tensor:
         self.nfe += 1
         self._inject_depth(t)
-        if (self.integral_loss is not None) and self.sensitivity == "autograd":
-            x_dyn = x[:, 1:]
-            dlds = self.integral_loss(t, x_dyn)
-            if len(dlds.shape) == 1:
-                dlds = dlds[:, None]
-            x_dyn = self.higher_order_forward(t, x_dyn) if self.order > 1 else self.vf(t, x_dyn)
-            return cat([dlds, x_dyn], 1).to(x_dyn)
-        if self.order > 1:
-            return self.higher_order_forward(t, x)
-        return self.vf(t, x, args=args)
+        carries_cost = self.integral_loss is not None and self.sensitivity == "autograd"
+        if not carries_cost:
+            return self.higher_order_forward(t, x) if self.order > 1 else self.vf(t, x, args=args)
+        # back-propagation through the solver with an integral loss: column 0 of the state accumulates the running cost
+        # g(t, z), the remaining columns z follow the dynamics (reference core/defunc.py:68-77)
+        z = x[:, 1:]
+        running = self.integral_loss(t, z)
+        dz = self.higher_order_forward(t, z) if self.order > 1 else self.vf(t, z)
+        return cat([running[:, None] if running.dim() == 1 else running, dz], 1).to(dz)
 
     def higher_order_forward(self, t: Tensor, x: Tensor, args: Dict = {}) -> Tensor:
         width = x.size(1) // self.order

@@ -75,6 +75,10 @@ class ODEProblem(nn.Module):
     def odeint(self, x: Tensor, t_span: Tensor, save_at: Tensor = (), args={}):
         "Returns Tuple(`t_eval`, `solution`)"
         if self.sensalg == "autograd":
+            if isinstance(t_span, Tensor) and t_span.requires_grad and torch.is_grad_enabled():
+                from warnings import warn
+                warn("torchdyn_b200: gradients with respect to `t_span` are not propagated under sensitivity='autograd' "
+                     "(step sizes are constants of the graph); use sensitivity='adjoint' for dL/dt_span")
             return odeint(self.vf, x, t_span, self.solver, self.atol, self.rtol, interpolator=self.interpolator,
                           save_at=save_at, args=args)
         fn = self._autograd_func()

@@ -99,7 +99,7 @@ def _unwrap_cnf(f):
     return None, []
 
 
-_cache = weakref.WeakKeyDictionary()      # nn.Sequential -> FusedMLP | False (kept off the module: it must stay picklable)
+_cache = weakref.WeakKeyDictionary()      # nn.Sequential -> (ids of its modules, FusedMLP | False); kept off the module: it must stay picklable
 _ACTS = {nn.Tanh: ACT_TANH, nn.Softplus: ACT_SOFTPLUS, nn.ReLU: ACT_RELU}
 
 
@@ -143,6 +143,22 @@ class FusedMLP:
     def _params_key(self):
         return tuple((p.data_ptr(), p._version) for m in self.linears for p in (m.weight, m.bias))
 
+    def begin_solve(self):
+        """Called once per user-level solve / backward: forget the prepared weight images, so that they are re-packed
+        from the live parameters.  ``(data_ptr, _version)`` alone misses in-place updates through ``.data`` (weight
+        clipping, EMA, older optimizers), and re-packing costs a few microseconds next to a solve."""
+        self._key = None
+
+    def _plain(self) -> bool:
+        """Only untouched nn.Linear layers are fused: a forward / pre-forward hook (old-style weight_norm / spectral_norm
+        recompute ``weight`` there) or a non-Parameter weight means torch must evaluate the layer."""
+        for m in self.linears:
+            if m._forward_hooks or m._forward_pre_hooks or m._backward_hooks or m._backward_pre_hooks:
+                return False
+            if not (isinstance(m.weight, nn.Parameter) and isinstance(m.bias, nn.Parameter)):
+                return False
+        return True
+
     def ready(self, kern) -> bool:
         """True if the tensor-core stage kernel can run this net (weight image rebuilt if the parameters changed)."""
         return self._refresh(kern) and self._tc_ok
@@ -183,6 +199,8 @@ class FusedMLP:
         return self._ffma_ws
 
     def _refresh(self, kern) -> bool:
+        if not self._plain():
+            return False
         ps = [p for m in self.linears for p in (m.weight, m.bias)]
         if not all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in ps):
             return False
@@ -207,17 +225,25 @@ class FusedMLP:
         return True
 
 
+def _fused_of(net: nn.Sequential):
+    """FusedMLP of ``net`` (or False), re-derived when the Sequential's module list was mutated after first use."""
+    ids = tuple(id(m) for m in net)
+    hit = _cache.get(net)
+    if hit is not None and hit[0] == ids:
+        return hit[1]
+    try:
+        fm = FusedMLP(net)
+    except ValueError:
+        fm = False
+    _cache[net] = (ids, fm)
+    return fm
+
+
 def _get_fused(f) -> Optional[tuple]:
     net, counters = _unwrap(f)
     if net is None:
         return None
-    fm = _cache.get(net)
-    if fm is None:
-        try:
-            fm = FusedMLP(net)
-        except ValueError:
-            fm = False
-        _cache[net] = fm
+    fm = _fused_of(net)
     return (fm, counters) if fm else None
 
 
@@ -367,13 +393,7 @@ def _get_fused_cnf(f):
     cnf, counters = _unwrap_cnf(f)
     if cnf is None:
         return None
-    fm = _cache.get(cnf.net)
-    if fm is None:
-        try:
-            fm = FusedMLP(cnf.net)
-        except ValueError:
-            fm = False
-        _cache[cnf.net] = fm
+    fm = _fused_of(cnf.net)
     return (cnf, fm, counters) if fm else None
 
 
@@ -385,6 +405,7 @@ def wrap(f, x):
     gc = _get_fused_cnf(f)
     if gc is not None:
         cnf, fm, counters = gc
+        fm.begin_solve()
         kern = _kernels.get(x)
         if getattr(kern, "is_cuda", False) and x.dim() == 2 and x.shape[1] == fm.dims[0] + 1 and fm.ready_ffma(kern) \
                 and kern.cnf_ffma_supported(fm._desc):
@@ -395,6 +416,7 @@ def wrap(f, x):
     if got is None:
         return f
     fm, counters = got
+    fm.begin_solve()
     kern = _kernels.get(x)
     if not getattr(kern, "is_cuda", False) or x.dim() != 2 or x.shape[1] != fm.dims[0]:
         return f
@@ -449,6 +471,7 @@ def adjoint_for(vf, x_shape, device) -> Optional[FusedAdjoint]:
     gc = _get_fused_cnf(vf)
     if gc is not None:
         cnf, fm, counters = gc
+        fm.begin_solve()
         kern = _kernels.get(torch.empty(0, device=device))
         eps = cnf.noise
         ok = (getattr(kern, "is_cuda", False) and x_shape[1] == fm.dims[0] + 1 and fm.ready_ffma(kern)
@@ -462,6 +485,7 @@ def adjoint_for(vf, x_shape, device) -> Optional[FusedAdjoint]:
     fm, counters = got
     if x_shape[1] != fm.dims[0]:
         return None
+    fm.begin_solve()
     kern = _kernels.get(torch.empty(0, device=device))
     if not getattr(kern, "is_cuda", False) or not (fm.ready_ffma(kern) or fm.ready_wide(kern)):
         return None
@@ -476,7 +500,8 @@ def adjoint_for(vf, x_shape, device) -> Optional[FusedAdjoint]:
 # ------------------------------------------------------------------------------------------------------------------
 PERSISTENT = True         # set False to keep the host-driven loop (A/B runs)
 TRACE_CAP = 3 * 4096 + 1
-MAX_STEPS = 4000
+MAX_STEPS = 4000          # attempts one launch may take (its trace buffer holds 4096); longer solves go to the host loop
+MAX_T_SPAN = 1024         # tdyn_mlp_solve keeps t_span in a 4 KB workspace slot
 
 
 def _rk_plan(solver) -> "_lib.RkPlan":
@@ -542,6 +567,8 @@ def try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, s
             return None
     rows, D = x.shape
     n_t = len(ts)
+    if n_t > MAX_T_SPAN:
+        return None
     cap = n_t + (512 if return_all_eval else 0)
     dev = x.device
     y0 = x.clone()
@@ -555,11 +582,11 @@ def try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, s
                    fm.solve_workspace(kern), status, trace, rows, MAX_STEPS, comm)
     st = status.cpu().tolist()
     n_out, n_attempt, nfe, err = st[0], st[1], st[3], st[4]
-    if err == 2:
-        return None                      # more accepted steps than the output buffer holds: let the host loop do it
     if err != 0:
-        raise RuntimeError(f"torchdyn_b200.odeint: adaptive loop did not terminate ({n_attempt} attempts); the error "
-                           "estimate is probably NaN")
+        # 2: more accepted steps than the output buffer holds; 1: more than MAX_STEPS attempts (a legitimately long
+        # solve, or a NaN error estimate).  Either way the host loop redoes the solve from x: it has the reference's
+        # limits and raises on a NaN step size.
+        return None
     for c in inner.counters:
         c.nfe += nfe
     _emit_trace(trace, n_attempt)
@@ -596,7 +623,7 @@ def try_adjoint_interval(dyn, A, t_from, t_to, solver, atol, rtol):
                    fm.solve_workspace(kern), status, trace, rows, MAX_STEPS, comm)
     st = status.cpu().tolist()
     if st[4] != 0:
-        raise RuntimeError(f"torchdyn_b200: adjoint solve did not terminate ({st[1]} attempts)")
+        return None                          # more than MAX_STEPS attempts: the host loop redoes the interval from A
     for c in fa.counters:
         c.nfe += st[3]
     _emit_trace(trace, st[1])
@@ -628,7 +655,7 @@ def try_interp_interval(dyn, A, t_from, t_to, solver, atol, rtol):
                           sp.two_c, sp.three_d, sp.t_dev, fm.solve_workspace(kern), status, trace, rows, MAX_STEPS)
     st = status.cpu().tolist()
     if st[4] != 0:
-        raise RuntimeError(f"torchdyn_b200: interpolated-adjoint solve did not terminate ({st[1]} attempts)")
+        return None                          # more than MAX_STEPS attempts: the host loop redoes the interval from A
     for c in fa.counters:
         c.nfe += st[3]
     _emit_trace(trace, st[1])
@@ -653,6 +680,7 @@ def try_fixed(f, x, ts, sv, solver) -> Optional[List[torch.Tensor]]:
         if got is None:
             return None
         fm, counters = got
+        fm.begin_solve()
     kern = _kernels.get(x)
     if not getattr(kern, "is_cuda", False) or x.shape[1] != fm.dims[0] or not fm.ready(kern):
         return None
