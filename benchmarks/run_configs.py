@@ -144,6 +144,8 @@ def run_cpu(cfg, iters, scale):
     from oracle import erk_oracle as eo
     torch.set_num_threads(os.cpu_count() or 1)
     net, X, t_span, kw, loss_fn, name = build(cfg, torch.device("cpu"), scale)
+    if getattr(net, "noise_dist", None) is not None:      # CNF: NeuralODE samples the Hutchinson noise once per forward
+        net.noise = net.noise_dist.sample((X.shape[0],))
     model = eo.OracleNeuralODE(net, **kw)
 
     def it():

@@ -30,6 +30,7 @@ class KernelTimer:
 
     def __init__(self):
         self.records = []   # (name, start_event, end_event, algorithmic_bytes_or_flops)
+        self.credits = {}   # name -> algorithmic work only known after the launch (persistent solves: NFE from the status)
 
     def summary(self):
         torch.cuda.synchronize()
@@ -39,6 +40,9 @@ class KernelTimer:
             a["launches"] += 1
             a["ms"] += e0.elapsed_time(e1)
             a["work"] += work
+        for name, work in self.credits.items():
+            if name in agg:
+                agg[name]["work"] += work
         return agg
 
 
@@ -48,6 +52,12 @@ _timer: Optional[KernelTimer] = None
 def set_timer(timer: Optional[KernelTimer]):
     global _timer
     _timer = timer
+
+
+def credit_work(name: str, work: float):
+    """Book algorithmic FLOPs of a launch after the fact (the persistent integrators report their NFE in a status word)."""
+    if _timer is not None:
+        _timer.credits[name] = _timer.credits.get(name, 0.0) + float(work)
 
 
 class _Timed:

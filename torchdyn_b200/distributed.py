@@ -19,6 +19,20 @@ from typing import Iterable, List, Optional, Tuple
 import torch
 
 _state = {"enabled": False, "group": None, "symm": None, "epoch": 0, "symm_failed": False, "replicated_from": None}
+_traffic = {"calls": 0, "bytes": 0}      # payload of the collectives issued by this module on this rank (bench.py reports it)
+
+
+def traffic(reset: bool = False):
+    """(number of collectives, payload bytes) this rank issued through this module since the last reset."""
+    out = dict(_traffic)
+    if reset:
+        _traffic["calls"] = _traffic["bytes"] = 0
+    return out
+
+
+def _count(t: torch.Tensor):
+    _traffic["calls"] += 1
+    _traffic["bytes"] += t.numel() * t.element_size()
 
 
 def enable(group=None):
@@ -120,6 +134,7 @@ def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     if _state["enabled"]:
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_state["group"])
+        _count(t)
     return t
 
 
@@ -131,6 +146,7 @@ def reduce_sums(kern, n_sums: int, local_count: int) -> Tuple[List[float], int]:
     import torch.distributed as dist
     kern.red[3].fill_(float(local_count))
     dist.all_reduce(kern.red, op=dist.ReduceOp.SUM, group=_state["group"])
+    _count(kern.red)
     vals = kern.read_reduction(4)
     return vals[:n_sums], int(round(vals[3]))
 
@@ -146,6 +162,7 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], average: bool = Fa
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=_state["group"])
+    _count(flat)
     if average:
         flat /= world_size()
     off = 0

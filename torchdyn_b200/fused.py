@@ -589,6 +589,7 @@ def try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, s
         return None
     for c in inner.counters:
         c.nfe += nfe
+    _kernels.credit_work("mlp_solve", fm.flops_per_row * rows * nfe)
     _emit_trace(trace, n_attempt)
     _last = "persistent fused MLP integrator (tdyn_mlp_solve)" + (", error norm exchanged by NVLink peer stores" if comm else "")
     return t_out[:n_out], out[:n_out]
@@ -626,6 +627,7 @@ def try_adjoint_interval(dyn, A, t_from, t_to, solver, atol, rtol):
         return None                          # more than MAX_STEPS attempts: the host loop redoes the interval from A
     for c in fa.counters:
         c.nfe += st[3]
+    _kernels.credit_work("mlp_solve", 3.0 * fm.flops_per_row * rows * st[3])
     _emit_trace(trace, st[1])
     return y0 if st[5] == 0 else y1
 
@@ -658,6 +660,7 @@ def try_interp_interval(dyn, A, t_from, t_to, solver, atol, rtol):
         return None                          # more than MAX_STEPS attempts: the host loop redoes the interval from A
     for c in fa.counters:
         c.nfe += st[3]
+    _kernels.credit_work("mlp_solve_interp", 3.0 * fm.flops_per_row * rows * st[3])
     _emit_trace(trace, st[1])
     return y0 if st[5] == 0 else y1
 
