@@ -209,11 +209,13 @@ _MAX_FACTOR = torch.tensor([10])  # int64 on purpose: templates.py:25 builds it 
 @torch.no_grad()
 def adapt_step(dt, ratio, order):
     """Step-size controller (utils.py:57-63).  ratio==0 -> x10; ratio<1 lifts min_factor to 1."""
+    # (the reference moves these constants to the state's device in sync_device_dtype, templates.py:32-42)
+    dev = dt.device
     if ratio == 0:
-        return dt * _MAX_FACTOR
-    lo = torch.ones_like(dt) if ratio < 1 else _MIN_FACTOR
-    expo = torch.tensor(order, dtype=dt.dtype).reciprocal()
-    return dt * torch.min(_MAX_FACTOR, torch.max(_SAFETY / ratio ** expo, lo))
+        return dt * _MAX_FACTOR.to(dev)
+    lo = torch.ones_like(dt) if ratio < 1 else _MIN_FACTOR.to(dev)
+    expo = torch.tensor(order, dtype=dt.dtype, device=dev).reciprocal()
+    return dt * torch.min(_MAX_FACTOR.to(dev), torch.max(_SAFETY.to(dev) / ratio ** expo, lo))
 
 
 # --------------------------------------------------------------------------------------
@@ -454,7 +456,7 @@ def _vjp_pack(vf, t, x, lam, with_dt: bool, integral_loss=None):
         if integral_loss:
             dg = torch.autograd.grad(integral_loss(t, x).sum(), x, allow_unused=True, retain_graph=True)[0]
             dlam = dlam - dg
-        dmu = torch.cat([e.flatten() if e is not None else torch.zeros(1) for e in dmu], dim=-1)
+        dmu = torch.cat([e.flatten() if e is not None else torch.zeros(1, device=x.device) for e in dmu], dim=-1)
         if dtt is None:
             dtt = torch.zeros(1).to(t)
         if dtt.dim() == 0:
@@ -490,7 +492,7 @@ def make_adjoint_function(vf, solver, atol, rtol, interpolator, solver_adjoint, 
             n = xT.numel()
             lam_flat = lamT.flatten()
             lam_t = lam_flat @ vf(t_sol[-1], xT).flatten()                   # sensitivity.py:53
-            A = torch.cat([xT.flatten(), lam_flat, torch.zeros(P, dtype=xT.dtype), lam_t[None]])
+            A = torch.cat([xT.flatten(), lam_flat, torch.zeros(P, dtype=xT.dtype, device=xT.device), lam_t[None]])
 
             def aug(t, A):                                                     # sensitivity.py:57-75
                 if t.dim() > 0:
@@ -529,7 +531,7 @@ def make_adjoint_function(vf, solver, atol, rtol, interpolator, solver_adjoint, 
             xT, lamT = sol[-1], g_sol[-1]
             P = _flat_params(vf).numel()
             n = lamT.numel()
-            A = torch.cat([lamT.flatten(), torch.zeros(P, dtype=xT.dtype)])
+            A = torch.cat([lamT.flatten(), torch.zeros(P, dtype=xT.dtype, device=xT.device)])
             spline = NaturalCubicSpline.from_coeffs(natural_cubic_coeffs(sol.permute(1, 0, 2).detach(), t_sol), t_sol)
 
             def aug(t, A):                                                     # sensitivity.py:130-147

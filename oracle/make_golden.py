@@ -190,18 +190,20 @@ def neuralode_cases():
         dims=[64, 256, 64], act="softplus", seed=10, x=torch.randn(128, 64), y=None, t_span=torch.linspace(0, 1, 2),
         loss="sqmean", kw=dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="adjoint", atol_adjoint=1e-4,
                                rtol_adjoint=1e-4))
-    # ACTIVE controller on the tensor-core paths: gain-scaled wide nets, error ratios 0.2-0.9 with rejections.
+    # ACTIVE controller on the tensor-core paths: gain-scaled wide nets whose step sequence is decided by the
+    # controller (ratios 0.15-0.95, rejections at 1.2-3.8) and NOT by rounding noise: tolerances 1e-2 / 1e-3 keep the
+    # embedded error estimates 100-1000x above the fp32 noise of f, the first backward step is clipped at max_factor.
     # (i) the config-2 network class 32-256-256-32 (fused tcgen05 stage kernel forward, layer-wise kernels in the adjoint),
     # (ii) config 3's own shape 128-1024-128 (K = 1024: the accumulator-flush path of tdyn_lin_tc_apply / tdyn_wgrad_tc)
     torch.manual_seed(16)
     cases["act_w256x2_dopri5_adjoint"] = dict(
-        dims=[32, 256, 256, 32], act="tanh", seed=16, gain=3.0, x=torch.randn(256, 32), y=None, t_span=torch.tensor([0.0, 2.0]),
-        loss="sqmean", kw=dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="adjoint", atol_adjoint=1e-4,
-                               rtol_adjoint=1e-4))
+        dims=[32, 256, 256, 32], act="tanh", seed=16, gain=6.0, x=torch.randn(256, 32), y=None, t_span=torch.tensor([0.0, 2.0]),
+        loss="sqmean", kw=dict(solver="dopri5", atol=1e-2, rtol=1e-2, sensitivity="adjoint", atol_adjoint=1e-2,
+                               rtol_adjoint=1e-2))
     torch.manual_seed(17)
     cases["act_w1024_tsit5_interp"] = dict(
-        dims=[128, 1024, 128], act="tanh", seed=17, gain=4.0, x=torch.randn(256, 128), y=None, t_span=torch.tensor([0.0, 2.0]),
-        loss="sq", kw=dict(solver="tsit5", atol=1e-3, rtol=1e-3, sensitivity="interpolated_adjoint"))
+        dims=[128, 1024, 128], act="tanh", seed=17, gain=6.0, x=torch.randn(256, 128), y=None, t_span=torch.tensor([0.0, 2.0]),
+        loss="sqmean", kw=dict(solver="tsit5", atol=1e-3, rtol=1e-3, sensitivity="interpolated_adjoint"))
     return cases
 
 
