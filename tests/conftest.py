@@ -119,5 +119,7 @@ FUNCTIONAL_CASES = ["fn_euler_tspan10", "fn_midpoint_tspan10", "fn_rk4_tspan10",
 # fixtures whose controller is ACTIVE (error ratios ~0.2-0.9, rejections): the GPU must reproduce the step sequence
 ACTIVE_CASES = ["act_dopri5_adjoint", "act_tsit5_interp", "act_tsit5_fn", "act_dopri5_4th_fn",
                 "act_w256x2_dopri5_adjoint", "act_w1024_tsit5_interp"]
+# value tolerance of the active fixtures on the GPU (expanding dynamics amplify the last bits of f; default 2e-4)
+ACTIVE_STATE_RTOL = {"act_w256x2_dopri5_adjoint": 1e-4, "act_w1024_tsit5_interp": 1e-3}
 VDP_CASES = ["vdp_dopri5_adjoint", "vdp_tsit5_adjoint", "vdp_dopri5_interpolated_adjoint",
              "vdp_tsit5_interpolated_adjoint"]

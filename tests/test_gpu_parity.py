@@ -14,7 +14,7 @@ from torchdyn_b200 import _kernels
 from torchdyn_b200._lib import MODE_CHAIN, MODE_INNER
 from torchdyn_b200.numerics import odeint
 from torchdyn_b200.numerics.spline import NaturalCubicSpline
-from conftest import ACTIVE_CASES, FUNCTIONAL_CASES, NEURALODE_CASES, VDP, VDP_CASES, build_mlp, load_golden
+from conftest import ACTIVE_CASES, ACTIVE_STATE_RTOL, FUNCTIONAL_CASES, NEURALODE_CASES, VDP, VDP_CASES, build_mlp, load_golden
 from cpu_kernel_double import CpuKernels
 from oracle import erk_oracle as eo
 from parity_helpers import (assert_close, check_functional_case, check_neuralode_case, run_cnf_case,
@@ -164,15 +164,21 @@ def test_active_controller_step_sequence_identical(name):
     """Fixtures whose error ratios sit at 0.2-0.9 (with rejections): the GPU run must reproduce the reference's
     attempted-step count, accept/reject pattern and t sequence -- no noise-driven fallback allowed."""
     fx = load_golden(name)
-    # these dynamics are expanding (gain 3-4, |x| grows to ~20 over t in [0, 4]): last-bit differences of f are
-    # amplified ~100x along the trajectory, so the STATE is compared at 2e-4; the step sequence is compared below.
+    # these dynamics are expanding (gain 3-6, |x| grows to ~20): last-bit differences of f are amplified ~100x along the
+    # trajectory, so the STATE is compared at 2e-4 (the 128-1024-128 net with gain 6 at solver tolerance 1e-3: at 1e-3);
+    # the step sequence is compared below.
+    rt = ACTIVE_STATE_RTOL.get(name, 2e-4)
     if fx["kind"] == "functional":
         t_eval, sol, traces = run_functional_case(fx, DEV)
-        check_functional_case(fx, t_eval, sol, traces, state_rtol=2e-4, name=name)
+        check_functional_case(fx, t_eval, sol, traces, state_rtol=rt, name=name)
     else:
         out = run_neuralode_case(fx, DEV)
-        check_neuralode_case(fx, out, state_rtol=2e-4, name=name)
+        check_neuralode_case(fx, out, state_rtol=rt, name=name)
         traces = out["traces"]
+    if name.startswith("act_w"):
+        # tensor-core paths: EVERY call (forward and backward) must be strict -- no fallback
+        from parity_helpers import LAST_STRICT_FLAGS
+        assert all(LAST_STRICT_FLAGS) and len(LAST_STRICT_FLAGS) == len(fx["ref"]["traces"]), LAST_STRICT_FLAGS
     # forward solve (first odeint call): identical attempted-step count and accept/reject pattern; step times within
     # 1e-3 (dt = dt*0.9/ratio**0.2 carries the ~1e-4..1e-3 relative noise of the error ratio of f's last bits)
     r, g = fx["ref"]["traces"][0], traces[0]

@@ -54,13 +54,29 @@ constexpr uint32_t kTmemCols = 512;
 enum Bar { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, A_FULL0, A_FULL1, A_FULL2, A_EMPTY0, A_EMPTY1, A_EMPTY2,
            A1_FULL, D1_FULL, D1B_FULL, D2_FULL, D3_FULL, D_FREE, W1B_FULL, W1B_EMPTY, NUM_BARS };
 
+// One PASS = one sweep over all row tiles: build a stage input y = combine(x, k[], coef, mode, dt), optionally store it
+// (the new state / an output time), evaluate the MLP on it and write k_out.  tdyn_mlp_tc_stage launches ONE pass (the
+// descriptor travels in the kernel parameters); tdyn_mlp_tc_solve_fixed launches a whole fixed-step solve, n_steps x
+// n_stages passes read from a table in device memory (rows are independent and every thread re-reads only what it wrote
+// itself, so no grid-wide synchronisation is needed between passes).
+struct PassDesc {
+    const float* x;
+    const float* k[TDYN_MAX_STAGES];    // terms with a zero coefficient are dropped by the host (multi-pass mode)
+    float coef[TDYN_MAX_STAGES];
+    int n_k; int mode; float dt;
+    float* x_store;                     // y -> here as well (solve mode: the state at the start of the step), or NULL
+    float* save;                        // y -> here as well (solve mode: an output time), or NULL
+    float* k_out;
+};
+
 struct Params {
     const uint8_t* wimg;       // 10 x 64 KB stage images
     const float* b1; const float* b2; const float* b3;
-    float* k_out;
-    const float* x;
-    KPtrs k; Coefs coef; int n_k; int mode; float dt;
-    float* x_new; Coefs bsol; int n_sol;
+    PassDesc one;              // single-pass mode (passes == NULL)
+    const PassDesc* passes;    // multi-pass mode: n_pass descriptors in device memory ...
+    const PassDesc* fin;       // ... and the closing combination (no MLP evaluation): final state -> fin->save
+    int n_pass;
+    float* x_new; Coefs bsol; int n_sol;      // single-pass mode only: x + dt*(sum_j bsol_j k_j) in the output epilogue
     int64_t rows; int num_tiles; int act;
 };
 
@@ -145,62 +161,84 @@ struct WorkerCtx {
     uint32_t lane_addr;
 };
 
-// stage input of one tile: y = combine(x, k, coef) for 8 elements of this thread's row -> A1 (hi/lo, swizzled)
-__device__ __forceinline__ void prologue(const Params& P, uint8_t* smem, const WorkerCtx& w, int64_t tile) {
-    const int64_t grow = tile * kTileM + w.row;
-    const bool valid = grow < P.rows;
-    const size_t goff = (size_t)grow * kD + w.sub * 8;
-    float xv[8], y[8];
+// 16-byte global load that is coherent with this thread's own earlier stores (multi-pass mode re-reads what the same
+// thread wrote in an earlier pass): L2-cached, never the non-coherent texture path
+__device__ __forceinline__ float4 ld_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+// y = combine(x, k, coef) for 8 elements of this thread's row, in the reference's rounding order.  The k's are fetched in
+// groups of four with every load of a group issued before the first use (one exposed L2 round trip per group).
+__device__ __forceinline__ void combine_row8(const PassDesc& d, size_t goff, bool valid, float (&y)[8]) {
+    float xv[8];
+    const int n_k = valid ? d.n_k : 0;
+    float4 q[4][2];
     if (valid) {
+        const float4 a = ld_f4(d.x + goff), b = ld_f4(d.x + goff + 4);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(P.x + goff) + i);
-            xv[4 * i] = q.x; xv[4 * i + 1] = q.y; xv[4 * i + 2] = q.z; xv[4 * i + 3] = q.w;
-        }
+        for (int jj = 0; jj < 4; ++jj)
+            if (jj < n_k) { q[jj][0] = ld_f4(d.k[jj] + goff); q[jj][1] = ld_f4(d.k[jj] + goff + 4); }
+        xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
     } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) xv[i] = 0.f;
     }
-    if (P.n_k == 0 || !valid) {
+    if (n_k == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) y[i] = xv[i];
-    } else if (P.mode == TDYN_MODE_CHAIN) {
+        return;
+    }
+    const bool chain = d.mode == TDYN_MODE_CHAIN;
+    float s[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = xv[i];
-        for (int j = 0; j < P.n_k; ++j) {
-            const float da = mul_rn(P.dt, P.coef.c[j]);
+    for (int i = 0; i < 8; ++i) s[i] = xv[i];         // CHAIN: running y; INNER: overwritten by the first product
+    for (int j0 = 0; j0 < n_k; j0 += 4) {
+        if (j0 > 0) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(P.k.p[j] + goff) + i);
-                y[4 * i] = add_rn(y[4 * i], mul_rn(da, q.x));
-                y[4 * i + 1] = add_rn(y[4 * i + 1], mul_rn(da, q.y));
-                y[4 * i + 2] = add_rn(y[4 * i + 2], mul_rn(da, q.z));
-                y[4 * i + 3] = add_rn(y[4 * i + 3], mul_rn(da, q.w));
-            }
-        }
-    } else {
-        float s[8];
-        for (int j = 0; j < P.n_k; ++j) {
-            const float a = P.coef.c[j];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(P.k.p[j] + goff) + i);
-                const float m0 = mul_rn(a, q.x), m1 = mul_rn(a, q.y), m2 = mul_rn(a, q.z), m3 = mul_rn(a, q.w);
-                s[4 * i] = j == 0 ? m0 : add_rn(s[4 * i], m0);
-                s[4 * i + 1] = j == 0 ? m1 : add_rn(s[4 * i + 1], m1);
-                s[4 * i + 2] = j == 0 ? m2 : add_rn(s[4 * i + 2], m2);
-                s[4 * i + 3] = j == 0 ? m3 : add_rn(s[4 * i + 3], m3);
-            }
+            for (int jj = 0; jj < 4; ++jj)
+                if (j0 + jj < n_k) { q[jj][0] = ld_f4(d.k[j0 + jj] + goff); q[jj][1] = ld_f4(d.k[j0 + jj] + goff + 4); }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = add_rn(xv[i], mul_rn(P.dt, s[i]));
+        for (int jj = 0; jj < 4; ++jj) {
+            if (j0 + jj < n_k) {
+                const float c = chain ? mul_rn(d.dt, d.coef[j0 + jj]) : d.coef[j0 + jj];
+                const float kv[8] = {q[jj][0].x, q[jj][0].y, q[jj][0].z, q[jj][0].w, q[jj][1].x, q[jj][1].y, q[jj][1].z, q[jj][1].w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float m = mul_rn(c, kv[i]);
+                    s[i] = (!chain && j0 + jj == 0) ? m : add_rn(s[i], m);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = chain ? s[i] : add_rn(xv[i], mul_rn(d.dt, s[i]));
+}
+
+__device__ __forceinline__ void store_row8(float* dst, size_t goff, const float (&y)[8]) {
+    reinterpret_cast<float4*>(dst + goff)[0] = make_float4(y[0], y[1], y[2], y[3]);
+    reinterpret_cast<float4*>(dst + goff)[1] = make_float4(y[4], y[5], y[6], y[7]);
+}
+
+// stage input of one tile -> A1 (hi/lo, swizzled); solve mode also stores it as the new state / an output
+__device__ __forceinline__ void prologue(const PassDesc& d, int64_t rows, uint8_t* smem, const WorkerCtx& w, int64_t tile) {
+    const int64_t grow = tile * kTileM + w.row;
+    const bool valid = grow < rows;
+    const size_t goff = (size_t)grow * kD + w.sub * 8;
+    float y[8];
+    combine_row8(d, goff, valid, y);
+    if (valid) {
+        if (d.x_store) store_row8(d.x_store, goff, y);
+        if (d.save) store_row8(d.save, goff, y);
     }
     store_split8(smem + kSmemA1, w.row, w.sub, y);
     fence_proxy_async();
 }
 
 template <int ACT>
-__global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params P) {
+__global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_constant__ Params P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t tmem_base_slot;
     // operand tiles need 1024-byte alignment (128B swizzle atoms): align the dynamic window by hand
@@ -235,6 +273,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
     const int my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // work items of this CTA: pass-major, its tiles within a pass (the launcher guarantees my_tiles >= 2 when n_pass > 1:
+    // the stage input of item i + 1 is built while item i is still in flight, so the two must be different tiles)
+    const int n_items = my_tiles * P.n_pass;
     // TMEM map: X = cols [0,256): D1, converted in place to layer 2's A_hi; Y = cols [256,512): D2 -> layer 3's A_hi;
     // D3 = cols [224,256) (layer 2's A_hi is dead once layer 2 has been issued: the tensor pipe executes in order).
     // The NEXT tile's layer 1 is split: columns [0,224) are issued right after this tile's layer 2 (they run under the
@@ -260,10 +301,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                 mbar_expect_tx(bar(W1B_FULL), kW1BBytes);
                 bulk_g2s(sbase + kSmemW1B, P.wimg + (size_t)kWStagesPerTile * kWStage, kW1BBytes, bar(W1B_FULL));
             };
-            if (my_tiles > 0) { load(0); load_w1b(0); }
-            for (int t = 0; t < my_tiles; ++t) {
+            if (n_items > 0) { load(0); load_w1b(0); }
+            for (int t = 0; t < n_items; ++t) {
                 for (int s = 1; s <= 8; ++s) load(s);
-                if (t + 1 < my_tiles) { load(0); load_w1b(t + 1); }
+                if (t + 1 < n_items) { load(0); load_w1b(t + 1); }
                 load(9);
             }
         }
@@ -291,8 +332,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                 tc_commit(bar(W1B_EMPTY));
                 tc_commit(bar(D1B_FULL));
             };
-            if (my_tiles > 0) { layer1a(0); layer1b(0); }
-            for (int t = 0; t < my_tiles; ++t) {
+            if (n_items > 0) { layer1a(0); layer1b(0); }
+            for (int t = 0; t < n_items; ++t) {
                 // ---- layer 2: 8 K-blocks, A_hi = X (in TMEM), A_lo ring -> D2 = Y
                 for (int j = 0; j < kH / kKB; ++j, ++wit, ++ait) {
                     const uint32_t ws = wit & 1, wu = wit >> 1, as = ait % kLoStages, au = ait / kLoStages;
@@ -307,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                 }
                 tc_commit(bar(D2_FULL));
                 // ---- first 224 columns of the next tile's layer 1: tensor work for the layer-2 -> 3 epilogue phase
-                if (t + 1 < my_tiles) layer1a(t + 1);
+                if (t + 1 < n_items) layer1a(t + 1);
                 // ---- layer 3: 8 K-blocks, N = 32, A_hi = Y -> D3 = X[224,256); W3 stage = 8 x [hi 4 KB | lo 4 KB]
                 {
                     const uint32_t ws = wit & 1, wu = wit >> 1;
@@ -327,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                     ++wit;
                 }
                 // ---- the last 32 columns of the next tile's layer 1 overwrite D3: wait until it has been read out
-                if (t + 1 < my_tiles) {
+                if (t + 1 < n_items) {
                     mbar_wait(bar(D_FREE), t & 1);
                     layer1b(t + 1);
                 }
@@ -341,20 +382,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
         w.row = quarter * 32 + lane;                   // row inside the tile == TMEM lane
         w.lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
         uint32_t ait = 0;
-        if (my_tiles > 0) {
-            prologue(P, smem, w, (int64_t)blockIdx.x);
+        auto desc = [&](int pass) -> const PassDesc& { return P.passes ? P.passes[pass] : P.one; };
+        int pass = 0, tl = 0;                          // (pass, local tile index) of the current item
+        if (n_items > 0) {
+            prologue(desc(0), P.rows, smem, w, (int64_t)blockIdx.x);
             mbar_arrive(bar(A1_FULL));
         }
-        for (int t = 0; t < my_tiles; ++t) {
+        for (int t = 0; t < n_items; ++t) {
             const uint32_t tpar = t & 1;
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
-            if (t + 1 < my_tiles && w.sub == 0) {
-                // the next tile's stage-input rows (x and the k's, 128 B each) are consumed by prologue() half a tile
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)tl * gridDim.x;
+            const int npass = tl + 1 < my_tiles ? pass : pass + 1, ntl = tl + 1 < my_tiles ? tl + 1 : 0;   // the next item
+            const int64_t ntile = (int64_t)blockIdx.x + (int64_t)ntl * gridDim.x;
+            if (t + 1 < n_items && w.sub == 0) {
+                // the next item's stage-input rows (x and the k's, 128 B each) are consumed by prologue() half an item
                 // from now: pull them into L2 so that those loads do not pay the DRAM latency
-                const int64_t nrow = (tile + gridDim.x) * kTileM + w.row;
+                const PassDesc& nd = desc(npass);
+                const int64_t nrow = ntile * kTileM + w.row;
                 if (nrow < P.rows) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.x + (size_t)nrow * kD));
-                    for (int j = 0; j < P.n_k; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.k.p[j] + (size_t)nrow * kD));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nd.x + (size_t)nrow * kD));
+                    for (int j = 0; j < nd.n_k; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(nd.k[j] + (size_t)nrow * kD));
                 }
             }
             // ---- two activation epilogues: D1 -> layer-2 operand, D2 -> layer-3 operand
@@ -393,9 +439,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                     mbar_arrive(bar(A_FULL0 + as));
                     if (j + 1 < kH / kKB) tmem_wait8(nxt);
                 }
-                if (layer == 0 && t + 1 < my_tiles) {
-                    // next tile's stage input (A1 is free: this tile's layer 1 has completed)
-                    prologue(P, smem, w, tile + gridDim.x);
+                if (layer == 0 && t + 1 < n_items) {
+                    // next item's stage input (A1 is free: this item's layer 1 has completed)
+                    prologue(desc(npass), P.rows, smem, w, ntile);
                     mbar_arrive(bar(A1_FULL));
                 }
             }
@@ -408,15 +454,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
             tc_fence_before();
             mbar_arrive(bar(D_FREE));
             const int64_t grow = tile * kTileM + w.row;
+            const PassDesc& cd = desc(pass);
             if (grow < P.rows) {
                 const size_t goff = (size_t)grow * kD + w.sub * 8;
                 float o[8];
+                float* k_out = cd.k_out;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const float4 bq = *reinterpret_cast<const float4*>(smem + kSmemBias + (2 * kH + w.sub * 8 + 4 * i) * 4);
                     o[4 * i] = __uint_as_float(ro[4 * i]) + bq.x; o[4 * i + 1] = __uint_as_float(ro[4 * i + 1]) + bq.y;
                     o[4 * i + 2] = __uint_as_float(ro[4 * i + 2]) + bq.z; o[4 * i + 3] = __uint_as_float(ro[4 * i + 3]) + bq.w;
-                    reinterpret_cast<float4*>(P.k_out + goff)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    reinterpret_cast<float4*>(k_out + goff)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                 }
                 if (P.x_new) {
                     // x + dt*(b0*k0 + ... + b_last*k_out)
@@ -428,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                         for (int i = 0; i < 2; ++i) {
                             float4 q;
                             if (last) q = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-                            else q = __ldg(reinterpret_cast<const float4*>(P.k.p[j] + goff) + i);
+                            else q = __ldg(reinterpret_cast<const float4*>(cd.k[j] + goff) + i);
                             const float m0 = mul_rn(b, q.x), m1 = mul_rn(b, q.y), m2 = mul_rn(b, q.z), m3 = mul_rn(b, q.w);
                             s[4 * i] = j == 0 ? m0 : add_rn(s[4 * i], m0);
                             s[4 * i + 1] = j == 0 ? m1 : add_rn(s[4 * i + 1], m1);
@@ -438,11 +486,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const Params 
                     }
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        const float4 xq = __ldg(reinterpret_cast<const float4*>(P.x + goff) + i);
+                        const float4 xq = __ldg(reinterpret_cast<const float4*>(cd.x + goff) + i);
                         reinterpret_cast<float4*>(P.x_new + goff)[i] =
                             make_float4(add_rn(xq.x, mul_rn(P.dt, s[4 * i])), add_rn(xq.y, mul_rn(P.dt, s[4 * i + 1])),
                                         add_rn(xq.z, mul_rn(P.dt, s[4 * i + 2])), add_rn(xq.w, mul_rn(P.dt, s[4 * i + 3])));
                     }
+                }
+            }
+            pass = npass; tl = ntl;
+        }
+        if (P.fin) {
+            // solve mode: the closing combination x_final = x + dt*(sum_j bsol_j k_j) of the last step (no evaluation)
+            for (int i = 0; i < my_tiles; ++i) {
+                const int64_t grow = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTileM + w.row;
+                if (grow < P.rows) {
+                    const size_t goff = (size_t)grow * kD + w.sub * 8;
+                    float y[8];
+                    combine_row8(*P.fin, goff, true, y);
+                    store_row8(P.fin->save, goff, y);
                 }
             }
         }
