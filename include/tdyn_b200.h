@@ -35,7 +35,7 @@ extern "C" {
 #define TDYN_API
 #endif
 
-#define TDYN_ABI_VERSION 9
+#define TDYN_ABI_VERSION 10
 #define TDYN_MAX_STAGES 7
 #define TDYN_MAX_PEERS 8
 
@@ -193,6 +193,21 @@ TDYN_API int tdyn_mlp_tc_prepare(const tdyn_mlp_t* mlp, void* wsplit, void* stre
 TDYN_API int tdyn_mlp_tc_stage(const tdyn_mlp_t* mlp, const void* wsplit, float* k_out, float* y_out,
                       const float* x, const float* const* k, const float* coef, int n_k, int mode, float dt,
                       float* x_new, const float* bsol, int n_sol, int64_t rows, void* stream);
+
+/* K2 (persistent form). A whole FIXED-STEP solve of the same MLP class -- the loop of numerics/odeint.py:411-445 around
+ * RungeKutta4.step / Euler.step / Midpoint.step (numerics/solvers/ode.py:61-104) -- in ONE launch: every CTA walks
+ * n_steps x n_stages passes over its own row tiles (rows are independent and each thread re-reads only what it wrote, so
+ * there is no grid-wide synchronisation); the solution update x + dt*(sum_j bsol_j k_j) of a step is folded into the
+ * first stage input of the next one, terms whose tableau coefficient is exactly 0 are not loaded (they add +-0).
+ * `plan`: the stepper (n_err == 0).  `dts[n_steps]`, `save_slot[n_steps + 1]`: HOST arrays -- the step sizes (fp32, from the
+ * accumulated t as in odeint.py:431-434) and, per time point t_s, the row of `out` the state is saved to or -1 (slot of
+ * t_0 is ignored: the caller owns x; the final state must be saved).  `xw` [rows*32] and `k` [n_stages*rows*32] are
+ * scratch, `workspace` = tdyn_mlp_tc_solve_workspace_bytes(n_steps, n_stages) bytes of device memory. */
+TDYN_API int tdyn_mlp_tc_solve_supported(const tdyn_mlp_t* mlp, int64_t rows);
+TDYN_API int64_t tdyn_mlp_tc_solve_workspace_bytes(int n_steps, int n_stages);
+TDYN_API int tdyn_mlp_tc_solve_fixed(const tdyn_mlp_t* mlp, const void* wsplit, const tdyn_rk_plan_t* plan, const float* x_in,
+                                     float* xw, float* k, float* out, const float* dts, const int* save_slot, int n_steps,
+                                     int64_t rows, void* workspace, void* stream);
 
 /* ---- Layer-wise tensor-core kernels for wide MLP vector fields (any widths that are multiples of 32; output widths
  * <= 128 or multiples of 128, <= 2048): BASELINE configs[2] (128-1024-128) and the adjoint of the 32-256-256-32 class.

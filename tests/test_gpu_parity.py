@@ -783,3 +783,32 @@ def test_state_on_another_device_than_the_current_one():
         assert torch.cuda.current_device() == 0
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
         assert all(torch.equal(a, b) for a, b in zip(outs[0][2], outs[1][2]))
+
+
+@pytest.mark.parametrize("solver,rows,n_t", [("rk4", 1000, 21), ("rk4", 19001, 6), ("euler", 300, 9), ("midpoint", 777, 5)])
+def test_mlp_tc_solve_fixed_is_bit_identical_to_the_per_stage_kernel(solver, rows, n_t):
+    """The one-launch fixed-step integrator (tdyn_mlp_tc_solve_fixed: all steps x stages in one persistent kernel, the
+    solution update folded into the next step's first stage input, zero tableau coefficients not loaded) against one
+    tdyn_mlp_tc_stage launch per stage: same arithmetic in the same order, so the saved states are bit-identical."""
+    from torchdyn_b200 import fused
+    torch.manual_seed(8)
+    net = build_mlp([32, 256, 256, 32], "tanh").to(DEV)
+    x = torch.randn(rows, 32, device=DEV)
+    ts = torch.linspace(0, 1, n_t)
+    res = {}
+    for save in ("all", "some", "last"):
+        kw = {} if save == "all" else dict(save_at=ts[[1, n_t // 2, n_t - 1]] if save == "some" else ts[-1:])
+        for flag in (True, False):
+            fused.SOLVE_KERNEL = flag
+            try:
+                with torch.no_grad(), warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    t_eval, sol = odeint(fused.MLPField(net), x, ts, solver, **kw)
+            finally:
+                fused.SOLVE_KERNEL = True
+            assert ("tdyn_mlp_tc_solve_fixed" in fused.last_used()) == flag, fused.last_used()
+            res[(save, flag)] = (t_eval, sol)
+        a, b = res[(save, True)], res[(save, False)]
+        assert torch.equal(a[0], b[0]) and a[1].shape == b[1].shape
+        assert torch.equal(a[1], b[1]), f"{solver} save={save}: max diff {float((a[1] - b[1]).abs().max()):.3e}"
+    assert torch.equal(res[("all", True)][1][-1], res[("last", True)][1][-1])

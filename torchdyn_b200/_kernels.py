@@ -246,6 +246,22 @@ class CudaKernels:
         _lib.check(rc, "tdyn_mlp_tc_stage")
         _launches += 1
 
+    def mlp_tc_solve_supported(self, desc, rows: int) -> bool:
+        return bool(self.lib.tdyn_mlp_tc_solve_supported(C.byref(desc), int(rows)))
+
+    def mlp_tc_solve_fixed(self, desc, img: Tensor, plan, x: Tensor, xw: Tensor, k: Tensor, out: Tensor, dts, save_slot,
+                           n_stages: int, flops_per_row: float):
+        """Whole fixed-step solve in one launch (tdyn_mlp_tc_solve_fixed); dts / save_slot are host numpy arrays."""
+        global _launches
+        rows, n_steps = x.shape[0], int(dts.size)
+        ws = torch.empty(int(self.lib.tdyn_mlp_tc_solve_workspace_bytes(n_steps, n_stages)), dtype=torch.uint8, device=self.device)
+        with _Timed("mlp_tc_solve", flops_per_row * rows * n_steps * n_stages):
+            rc = self.lib.tdyn_mlp_tc_solve_fixed(C.byref(desc), img.data_ptr(), C.byref(plan), x.data_ptr(), xw.data_ptr(),
+                                                  k.data_ptr(), out.data_ptr(), dts.ctypes.data, save_slot.ctypes.data, n_steps,
+                                                  rows, ws.data_ptr(), self._stream())
+        _lib.check(rc, "tdyn_mlp_tc_solve_fixed")
+        _launches += 1
+
     # ---- layer-wise tensor-core kernels for wide MLPs (tdyn_lin_tc_*, tdyn_wgrad_tc)
     def lin_tc_supported(self, n_out: int, k_in: int) -> bool:
         return bool(self.lib.tdyn_lin_tc_supported(int(n_out), int(k_in)))

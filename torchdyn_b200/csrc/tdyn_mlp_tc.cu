@@ -24,6 +24,7 @@
 // Algorithmic work: 163 840 FLOP per sample-NFE (issued as 1 TF32 + 2 bf16 FLOPs = 4 bf16-equivalents).  HBM traffic is negligible (128-256 B per
 // sample-NFE), the bound is the tensor pipe with the activation epilogue (512 tanh per sample-NFE) next.
 #include <cuda_bf16.h>
+#include <vector>
 #include "tdyn_tc_ptx.cuh"
 
 namespace tdyn {
@@ -488,8 +489,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
                     for (int i = 0; i < 2; ++i) {
                         const float4 xq = __ldg(reinterpret_cast<const float4*>(cd.x + goff) + i);
                         reinterpret_cast<float4*>(P.x_new + goff)[i] =
-                            make_float4(add_rn(xq.x, mul_rn(P.dt, s[4 * i])), add_rn(xq.y, mul_rn(P.dt, s[4 * i + 1])),
-                                        add_rn(xq.z, mul_rn(P.dt, s[4 * i + 2])), add_rn(xq.w, mul_rn(P.dt, s[4 * i + 3])));
+                            make_float4(add_rn(xq.x, mul_rn(cd.dt, s[4 * i])), add_rn(xq.y, mul_rn(cd.dt, s[4 * i + 1])),
+                                        add_rn(xq.z, mul_rn(cd.dt, s[4 * i + 2])), add_rn(xq.w, mul_rn(cd.dt, s[4 * i + 3])));
                     }
                 }
             }
@@ -573,33 +574,7 @@ int tdyn_mlp_tc_prepare(const tdyn_mlp_t* m, void* wsplit, void* stream) {
     return 0;
 }
 
-int tdyn_mlp_tc_stage(const tdyn_mlp_t* m, const void* wsplit, float* k_out, float* y_out, const float* x,
-                      const float* const* k, const float* coef, int n_k, int mode, float dt, float* x_new,
-                      const float* bsol, int n_sol, int64_t rows, void* stream) {
-    TDYN_REQUIRE(tdyn_mlp_tc_supported(m), "tdyn_mlp_tc_stage: unsupported MLP shape (need 32-256-256-32)");
-    TDYN_REQUIRE(wsplit && k_out && x, "tdyn_mlp_tc_stage: null argument");
-    TDYN_REQUIRE(y_out == nullptr, "tdyn_mlp_tc_stage: y_out is not produced by this kernel (pass NULL)");
-    TDYN_REQUIRE(n_k >= 0 && n_k <= TDYN_MAX_STAGES && n_sol >= 0 && n_sol <= TDYN_MAX_STAGES, "tdyn_mlp_tc_stage: bad n_k / n_sol");
-    TDYN_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)k_out & 15) == 0 && (!x_new || ((uintptr_t)x_new & 15) == 0),
-                 "tdyn_mlp_tc_stage: state pointers must be 16-byte aligned");
-    if (rows <= 0) return 0;
-    tc::Params P{};
-    P.wimg = (const uint8_t*)wsplit;
-    P.b1 = m->b[0]; P.b2 = m->b[1]; P.b3 = m->b[2];
-    P.k_out = k_out; P.x = x; P.n_k = n_k; P.mode = mode; P.dt = dt;
-    const int need_k = x_new ? (n_sol - 1 > n_k ? n_sol - 1 : n_k) : n_k;
-    for (int j = 0; j < need_k; ++j) {
-        TDYN_REQUIRE(k && k[j] && ((uintptr_t)k[j] & 15) == 0, "tdyn_mlp_tc_stage: k[%d] null or misaligned", j);
-        P.k.p[j] = k[j];
-    }
-    for (int j = 0; j < n_k; ++j) P.coef.c[j] = coef[j];
-    P.x_new = x_new; P.n_sol = x_new ? n_sol : 0;
-    for (int j = 0; j < P.n_sol; ++j) P.bsol.c[j] = bsol[j];
-    P.rows = rows;
-    P.num_tiles = (int)((rows + tc::kTileM - 1) / tc::kTileM);
-    P.act = m->act;
-    const int grid = P.num_tiles < kNumSMs ? P.num_tiles : kNumSMs;
-    cudaStream_t st = (cudaStream_t)stream;
+static int launch_tc(const tdyn_mlp_t* m, tc::Params& P, int grid, cudaStream_t st) {
     static thread_local unsigned long long seen = 0;
     if (first_use_on_device(seen)) {
         TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
@@ -613,6 +588,109 @@ int tdyn_mlp_tc_stage(const tdyn_mlp_t* m, const void* wsplit, float* k_out, flo
     }
     TDYN_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+int tdyn_mlp_tc_stage(const tdyn_mlp_t* m, const void* wsplit, float* k_out, float* y_out, const float* x,
+                      const float* const* k, const float* coef, int n_k, int mode, float dt, float* x_new,
+                      const float* bsol, int n_sol, int64_t rows, void* stream) {
+    TDYN_REQUIRE(tdyn_mlp_tc_supported(m), "tdyn_mlp_tc_stage: unsupported MLP shape (need 32-256-256-32)");
+    TDYN_REQUIRE(wsplit && k_out && x, "tdyn_mlp_tc_stage: null argument");
+    TDYN_REQUIRE(y_out == nullptr, "tdyn_mlp_tc_stage: y_out is not produced by this kernel (pass NULL)");
+    TDYN_REQUIRE(n_k >= 0 && n_k <= TDYN_MAX_STAGES && n_sol >= 0 && n_sol <= TDYN_MAX_STAGES, "tdyn_mlp_tc_stage: bad n_k / n_sol");
+    TDYN_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)k_out & 15) == 0 && (!x_new || ((uintptr_t)x_new & 15) == 0),
+                 "tdyn_mlp_tc_stage: state pointers must be 16-byte aligned");
+    if (rows <= 0) return 0;
+    tc::Params P{};
+    P.wimg = (const uint8_t*)wsplit;
+    P.b1 = m->b[0]; P.b2 = m->b[1]; P.b3 = m->b[2];
+    P.one.k_out = k_out; P.one.x = x; P.one.n_k = n_k; P.one.mode = mode; P.one.dt = dt;
+    const int need_k = x_new ? (n_sol - 1 > n_k ? n_sol - 1 : n_k) : n_k;
+    for (int j = 0; j < need_k; ++j) {
+        TDYN_REQUIRE(k && k[j] && ((uintptr_t)k[j] & 15) == 0, "tdyn_mlp_tc_stage: k[%d] null or misaligned", j);
+        P.one.k[j] = k[j];
+    }
+    for (int j = 0; j < n_k; ++j) P.one.coef[j] = coef[j];
+    P.n_pass = 1;
+    P.x_new = x_new; P.n_sol = x_new ? n_sol : 0;
+    for (int j = 0; j < P.n_sol; ++j) P.bsol.c[j] = bsol[j];
+    P.rows = rows;
+    P.num_tiles = (int)((rows + tc::kTileM - 1) / tc::kTileM);
+    P.act = m->act;
+    const int grid = P.num_tiles < kNumSMs ? P.num_tiles : kNumSMs;
+    return launch_tc(m, P, grid, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------- whole fixed-step solve
+int tdyn_mlp_tc_solve_supported(const tdyn_mlp_t* m, int64_t rows) {
+    // every CTA must own at least two row tiles (the stage input of the next work item is built while the current one is
+    // in flight: they must be different tiles)
+    return tdyn_mlp_tc_supported(m) && rows > 2 * tc::kTileM;
+}
+
+int64_t tdyn_mlp_tc_solve_workspace_bytes(int n_steps, int n_stages) {
+    if (n_steps <= 0 || n_stages <= 0 || n_stages > TDYN_MAX_STAGES) return 0;
+    return (int64_t)sizeof(tc::PassDesc) * ((int64_t)n_steps * n_stages + 1);
+}
+
+int tdyn_mlp_tc_solve_fixed(const tdyn_mlp_t* m, const void* wsplit, const tdyn_rk_plan_t* plan, const float* x_in, float* xw,
+                            float* k, float* out, const float* dts, const int* save_slot, int n_steps, int64_t rows,
+                            void* workspace, void* stream) {
+    TDYN_REQUIRE(m && plan && wsplit && x_in && xw && k && out && dts && save_slot && workspace, "tdyn_mlp_tc_solve_fixed: null argument");
+    TDYN_REQUIRE(tdyn_mlp_tc_solve_supported(m, rows), "tdyn_mlp_tc_solve_fixed: unsupported MLP shape or too few rows");
+    TDYN_REQUIRE(plan->n_err == 0 && plan->n_extra >= 0 && plan->n_extra <= 6 && plan->n_sol >= 1 && plan->n_sol <= plan->n_extra + 1,
+                 "tdyn_mlp_tc_solve_fixed: need a fixed-step plan");
+    TDYN_REQUIRE(n_steps >= 1, "tdyn_mlp_tc_solve_fixed: n_steps must be positive");
+    TDYN_REQUIRE(save_slot[n_steps] >= 0, "tdyn_mlp_tc_solve_fixed: the final state must have an output slot");
+    TDYN_REQUIRE((((uintptr_t)x_in | (uintptr_t)xw | (uintptr_t)k | (uintptr_t)out | (uintptr_t)workspace) & 15) == 0,
+                 "tdyn_mlp_tc_solve_fixed: pointers must be 16-byte aligned");
+    const int n_stage = plan->n_extra + 1;
+    const size_t n_state = (size_t)rows * tc::kD;
+    // the solution update x + dt*(sum_j bsol_j k_j) of step s is folded into the first stage input of step s + 1 (and into
+    // the closing combination); terms with an exactly zero coefficient are dropped (they add +-0)
+    auto fill_update = [&](tc::PassDesc& d, float dt) {
+        d.x = xw; d.n_k = 0; d.dt = dt;
+        d.mode = plan->n_sol > 1 ? TDYN_MODE_INNER : TDYN_MODE_CHAIN;
+        for (int j = 0; j < plan->n_sol; ++j)
+            if (plan->bsol[j] != 0.f) { d.k[d.n_k] = k + (size_t)j * n_state; d.coef[d.n_k] = plan->bsol[j]; ++d.n_k; }
+    };
+    std::vector<tc::PassDesc> tab((size_t)n_steps * n_stage + 1);
+    for (int s = 0; s < n_steps; ++s) {
+        for (int g = 0; g < n_stage; ++g) {
+            tc::PassDesc& d = tab[(size_t)s * n_stage + g];
+            memset(&d, 0, sizeof(d));
+            if (g == 0) {
+                if (s == 0) { d.x = x_in; d.n_k = 0; d.mode = TDYN_MODE_CHAIN; d.dt = 0.f; }
+                else fill_update(d, dts[s - 1]);
+                d.x_store = xw;
+                d.save = (s > 0 && save_slot[s] >= 0) ? out + (size_t)save_slot[s] * n_state : nullptr;
+            } else {
+                d.x = xw; d.mode = plan->mode[g - 1]; d.dt = dts[s];
+                TDYN_REQUIRE(plan->nk[g - 1] >= 0 && plan->nk[g - 1] <= g, "tdyn_mlp_tc_solve_fixed: stage %d combines later stages", g);
+                for (int j = 0; j < plan->nk[g - 1]; ++j)
+                    if (plan->a[g - 1][j] != 0.f) { d.k[d.n_k] = k + (size_t)j * n_state; d.coef[d.n_k] = plan->a[g - 1][j]; ++d.n_k; }
+            }
+            d.k_out = k + (size_t)g * n_state;
+        }
+    }
+    tc::PassDesc& fin = tab.back();
+    memset(&fin, 0, sizeof(fin));
+    fill_update(fin, dts[n_steps - 1]);
+    fin.save = out + (size_t)save_slot[n_steps] * n_state;
+    cudaStream_t st = (cudaStream_t)stream;
+    // (pageable source: the copy is staged before the call returns, so `tab` may go out of scope)
+    TDYN_CHECK_CUDA(cudaMemcpyAsync(workspace, tab.data(), sizeof(tc::PassDesc) * tab.size(), cudaMemcpyHostToDevice, st));
+    tc::Params P{};
+    P.wimg = (const uint8_t*)wsplit;
+    P.b1 = m->b[0]; P.b2 = m->b[1]; P.b3 = m->b[2];
+    P.passes = (const tc::PassDesc*)workspace;
+    P.fin = P.passes + (tab.size() - 1);
+    P.n_pass = n_steps * n_stage;
+    P.rows = rows;
+    P.num_tiles = (int)((rows + tc::kTileM - 1) / tc::kTileM);
+    P.act = m->act;
+    int grid = P.num_tiles / 2;
+    if (grid > kNumSMs) grid = kNumSMs;
+    return launch_tc(m, P, grid, st);
 }
 
 }  // extern "C"

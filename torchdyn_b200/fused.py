@@ -499,6 +499,7 @@ def adjoint_for(vf, x_shape, device) -> Optional[FusedAdjoint]:
 # persistent solver: a whole adaptive odeint call in one cooperative kernel (tdyn_mlp_solve)
 # ------------------------------------------------------------------------------------------------------------------
 PERSISTENT = True         # set False to keep the host-driven loop (A/B runs)
+SOLVE_KERNEL = True       # fixed-step solves of the 32-256-256-32 class: one launch per solve (False: one per stage)
 TRACE_CAP = 3 * 4096 + 1
 MAX_STEPS = 4000          # attempts one launch may take (its trace buffer holds 4096); longer solves go to the host loop
 MAX_T_SPAN = 1024         # tdyn_mlp_solve keeps t_span in a 4 KB workspace slot
@@ -690,6 +691,29 @@ def try_fixed(f, x, ts, sv, solver) -> Optional[List[torch.Tensor]]:
     x = x if x.is_contiguous() else x.contiguous()
     p = solver.plan()
     n_stage = len(p.stages) + 1
+    if SOLVE_KERNEL and x.data_ptr() % 16 == 0 and kern.mlp_tc_solve_supported(fm._desc, x.shape[0]):
+        # the whole solve in ONE launch: dt and the saved time points follow the reference's loop (odeint.py:420-434)
+        n_steps = len(ts) - 1
+        dts, slot = np.empty(n_steps, dtype=np.float32), np.full(n_steps + 1, -1, dtype=np.int32)
+        t, dt, n_saved = f32(ts[0]), f32(ts[1] - ts[0]), 0
+        first = bool(_isclose_count(t, sv))
+        for step in range(1, len(ts)):
+            dts[step - 1] = dt
+            t = f32(t + dt)
+            if _isclose_count(t, sv):
+                slot[step] = n_saved
+                n_saved += 1
+            if step < len(ts) - 1:
+                dt = f32(ts[step + 1] - t)
+        if slot[n_steps] >= 0:
+            out = torch.empty(n_saved, *x.shape, dtype=torch.float32, device=x.device)       # returned to the caller: fresh
+            xw, kbuf = fm.scratch(("solve_fixed", x.shape[0], n_stage, x.device.index), lambda: (
+                torch.empty_like(x), torch.empty(n_stage, *x.shape, dtype=torch.float32, device=x.device)))
+            kern.mlp_tc_solve_fixed(fm._desc, fm._img, _rk_plan(solver), x, xw, kbuf, out, dts, slot, n_stage, fm.flops_per_row)
+            for c in counters:
+                c.nfe += n_stage * n_steps
+            _last = "persistent fused tcgen05 split-precision (TF32 + bf16 corrections) fixed-step integrator (tdyn_mlp_tc_solve_fixed)"
+            return ([x] if first else []) + list(out.unbind(0))
     ks = [torch.empty_like(x) for _ in range(n_stage)]
     t, dt = f32(ts[0]), f32(ts[1] - ts[0])
     sol = [x] if _isclose_count(t, sv) else []
