@@ -56,31 +56,44 @@ enum Bar { W_FULL0 = 0, W_FULL1, W_EMPTY0, W_EMPTY1, A_FULL0, A_FULL1, A_FULL2, 
            A1_FULL, D1_FULL, D1B_FULL, D2_FULL, D3_FULL, D_FREE, W1B_FULL, W1B_EMPTY, NUM_BARS };
 
 // One PASS = one sweep over all row tiles: build a stage input y = combine(x, k[], coef, mode, dt), optionally store it
-// (the new state / an output time), evaluate the MLP on it and write k_out.  tdyn_mlp_tc_stage launches ONE pass (the
-// descriptor travels in the kernel parameters); tdyn_mlp_tc_solve_fixed launches a whole fixed-step solve, n_steps x
-// n_stages passes read from a table in device memory (rows are independent and every thread re-reads only what it wrote
-// itself, so no grid-wide synchronisation is needed between passes).
-struct PassDesc {
-    const float* x;
-    const float* k[TDYN_MAX_STAGES];    // terms with a zero coefficient are dropped by the host (multi-pass mode)
+// (the new state / an output time), evaluate the MLP on it and write the stage derivative.  tdyn_mlp_tc_stage launches ONE
+// pass; tdyn_mlp_tc_solve_fixed launches a whole fixed-step solve = n_steps x n_stage passes (rows are independent and
+// every thread re-reads only what it wrote itself, so no grid-wide synchronisation is needed between passes).
+// Everything that describes a pass lives in the kernel parameters (constant bank: no load latency in the prologue); only
+// the per-step dt and output slot come from two small device arrays.
+struct StagePlan {                      // one stage input: which stage derivatives, which coefficients
+    int n_k; int mode;
+    int kidx[TDYN_MAX_STAGES];          // indices into Params::kp (terms with a zero coefficient dropped in solve mode)
     float coef[TDYN_MAX_STAGES];
-    int n_k; int mode; float dt;
-    float* x_store;                     // y -> here as well (solve mode: the state at the start of the step), or NULL
-    float* save;                        // y -> here as well (solve mode: an output time), or NULL
-    float* k_out;
 };
+constexpr int kUpd = TDYN_MAX_STAGES;   // st[kUpd]: the solution update x + dt*(sum_j bsol_j k_j)
 
 struct Params {
     const uint8_t* wimg;       // 10 x 64 KB stage images
     const float* b1; const float* b2; const float* b3;
-    PassDesc one;              // single-pass mode (passes == NULL)
-    const PassDesc* passes;    // multi-pass mode: n_pass descriptors in device memory ...
-    const PassDesc* fin;       // ... and the closing combination (no MLP evaluation): final state -> fin->save
-    int n_pass;
-    float* x_new; Coefs bsol; int n_sol;      // single-pass mode only: x + dt*(sum_j bsol_j k_j) in the output epilogue
+    StagePlan st[TDYN_MAX_STAGES + 2];        // st[g]: input of stage g; st[kUpd]: update; st[kUpd + 1]: empty (n_k = 0)
+    const float* kp[TDYN_MAX_STAGES];         // stage-derivative buffers (stage mode: the caller's k pointers)
+    const float* x_in;         // the caller's state (stage mode: x of this launch; solve mode: read by the very first pass)
+    float* xw;                 // solve mode: working copy of the state (written by the first stage of every step)
+    float* k_out0;             // stage mode: output
+    float* out;                // solve mode: [n_saved][rows*32]
+    const float* dts;          // solve mode: dt of every step (device)
+    const int* slots;          // solve mode: output slot of every time point t_s, s = 0..n_steps (device; -1 = not saved)
+    unsigned long long n_state;
+    float dt0;                 // stage mode: dt
+    int n_stage, n_steps;      // stage mode: 1, 1
+    int solve;                 // 0: stage mode, 1: solve mode
+    float* x_new; Coefs bsol; int n_sol;      // stage mode only: x + dt*(sum_j bsol_j k_j) in the output epilogue
     int64_t rows; int num_tiles; int act;
 };
 
+// what a work item needs beyond the constant-bank plan
+struct Item {
+    int g;           // stage index (k_out = kp[g]); the plan is st[g], or st[kUpd] for g == 0 (st[kUpd + 1], empty, for the
+                     // very first pass, which reads Params::x_in); g == 0 also stores the stage input into Params::xw
+    int slot;        // ... and into this output slot (-1: none)
+    float dt;
+};
 
 // act(acc + bias); for tanh `bias` is the pre-scaled value (see the bias staging in the kernel)
 template <int ACT>
@@ -164,23 +177,22 @@ struct WorkerCtx {
 
 // 16-byte global load that is coherent with this thread's own earlier stores (multi-pass mode re-reads what the same
 // thread wrote in an earlier pass): L2-cached, never the non-coherent texture path
-__device__ __forceinline__ float4 ld_f4(const float* p) {
-    float4 v;
-    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-    return v;
-}
+// (every re-read is separated from the store it depends on by mbarrier waits, which order it for the compiler as well)
+__device__ __forceinline__ float4 ld_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 // y = combine(x, k, coef) for 8 elements of this thread's row, in the reference's rounding order.  The k's are fetched in
 // groups of four with every load of a group issued before the first use (one exposed L2 round trip per group).
-__device__ __forceinline__ void combine_row8(const PassDesc& d, size_t goff, bool valid, float (&y)[8]) {
+__device__ __forceinline__ void combine_row8(const Params& P, int si, const float* x, float dt, size_t goff, bool valid,
+                                             float (&y)[8]) {
     float xv[8];
-    const int n_k = valid ? d.n_k : 0;
+    const StagePlan& sp = P.st[si];
+    const int n_k = valid ? sp.n_k : 0;
     float4 q[4][2];
     if (valid) {
-        const float4 a = ld_f4(d.x + goff), b = ld_f4(d.x + goff + 4);
+        const float4 a = ld_f4(x + goff), b = ld_f4(x + goff + 4);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj)
-            if (jj < n_k) { q[jj][0] = ld_f4(d.k[jj] + goff); q[jj][1] = ld_f4(d.k[jj] + goff + 4); }
+            if (jj < n_k) { const float* kp = P.kp[sp.kidx[jj]] + goff; q[jj][0] = ld_f4(kp); q[jj][1] = ld_f4(kp + 4); }
         xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
     } else {
 #pragma unroll
@@ -191,7 +203,7 @@ __device__ __forceinline__ void combine_row8(const PassDesc& d, size_t goff, boo
         for (int i = 0; i < 8; ++i) y[i] = xv[i];
         return;
     }
-    const bool chain = d.mode == TDYN_MODE_CHAIN;
+    const bool chain = sp.mode == TDYN_MODE_CHAIN;
     float s[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = xv[i];         // CHAIN: running y; INNER: overwritten by the first product
@@ -199,12 +211,12 @@ __device__ __forceinline__ void combine_row8(const PassDesc& d, size_t goff, boo
         if (j0 > 0) {
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
-                if (j0 + jj < n_k) { q[jj][0] = ld_f4(d.k[j0 + jj] + goff); q[jj][1] = ld_f4(d.k[j0 + jj] + goff + 4); }
+                if (j0 + jj < n_k) { const float* kp = P.kp[sp.kidx[j0 + jj]] + goff; q[jj][0] = ld_f4(kp); q[jj][1] = ld_f4(kp + 4); }
         }
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             if (j0 + jj < n_k) {
-                const float c = chain ? mul_rn(d.dt, d.coef[j0 + jj]) : d.coef[j0 + jj];
+                const float c = chain ? mul_rn(dt, sp.coef[j0 + jj]) : sp.coef[j0 + jj];
                 const float kv[8] = {q[jj][0].x, q[jj][0].y, q[jj][0].z, q[jj][0].w, q[jj][1].x, q[jj][1].y, q[jj][1].z, q[jj][1].w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -215,7 +227,7 @@ __device__ __forceinline__ void combine_row8(const PassDesc& d, size_t goff, boo
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = chain ? s[i] : add_rn(xv[i], mul_rn(d.dt, s[i]));
+    for (int i = 0; i < 8; ++i) y[i] = chain ? s[i] : add_rn(xv[i], mul_rn(dt, s[i]));
 }
 
 __device__ __forceinline__ void store_row8(float* dst, size_t goff, const float (&y)[8]) {
@@ -223,16 +235,37 @@ __device__ __forceinline__ void store_row8(float* dst, size_t goff, const float 
     reinterpret_cast<float4*>(dst + goff)[1] = make_float4(y[4], y[5], y[6], y[7]);
 }
 
+// the work item of pass `pass` (solve mode: step = pass / n_stage, stage = pass % n_stage)
+__device__ __forceinline__ Item make_item(const Params& P, int pass) {
+    Item it;
+    it.slot = -1;
+    if (!P.solve) { it.g = 0; it.dt = P.dt0; return it; }
+    const int s = pass / P.n_stage, g = pass - s * P.n_stage;
+    it.g = g;
+    if (g == 0) {
+        it.dt = s > 0 ? __ldg(P.dts + s - 1) : 0.f;
+        if (s > 0) it.slot = __ldg(P.slots + s);
+    } else {
+        it.dt = __ldg(P.dts + s);
+    }
+    return it;
+}
+__device__ __forceinline__ int plan_index(const Params& P, const Item& it, bool first_pass) {
+    return !P.solve ? 0 : (it.g > 0 ? it.g : (first_pass ? kUpd + 1 : kUpd));
+}
+
 // stage input of one tile -> A1 (hi/lo, swizzled); solve mode also stores it as the new state / an output
-__device__ __forceinline__ void prologue(const PassDesc& d, int64_t rows, uint8_t* smem, const WorkerCtx& w, int64_t tile) {
+__device__ __forceinline__ void prologue(const Params& P, const Item& it, bool first_pass, uint8_t* smem, const WorkerCtx& w,
+                                         int64_t tile) {
     const int64_t grow = tile * kTileM + w.row;
-    const bool valid = grow < rows;
+    const bool valid = grow < P.rows;
     const size_t goff = (size_t)grow * kD + w.sub * 8;
     float y[8];
-    combine_row8(d, goff, valid, y);
-    if (valid) {
-        if (d.x_store) store_row8(d.x_store, goff, y);
-        if (d.save) store_row8(d.save, goff, y);
+    // (the very first pass of a solve copies the caller's state: no stage derivatives exist yet)
+    combine_row8(P, plan_index(P, it, first_pass), (first_pass || !P.solve) ? P.x_in : P.xw, it.dt, goff, valid, y);
+    if (valid && P.solve && it.g == 0) {
+        store_row8(P.xw, goff, y);
+        if (it.slot >= 0) store_row8(P.out + (size_t)it.slot * P.n_state, goff, y);
     }
     store_split8(smem + kSmemA1, w.row, w.sub, y);
     fence_proxy_async();
@@ -276,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
     const int my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     // work items of this CTA: pass-major, its tiles within a pass (the launcher guarantees my_tiles >= 2 when n_pass > 1:
     // the stage input of item i + 1 is built while item i is still in flight, so the two must be different tiles)
-    const int n_items = my_tiles * P.n_pass;
+    const int n_items = my_tiles * P.n_stage * P.n_steps;
     // TMEM map: X = cols [0,256): D1, converted in place to layer 2's A_hi; Y = cols [256,512): D2 -> layer 3's A_hi;
     // D3 = cols [224,256) (layer 2's A_hi is dead once layer 2 has been issued: the tensor pipe executes in order).
     // The NEXT tile's layer 1 is split: columns [0,224) are issued right after this tile's layer 2 (they run under the
@@ -383,10 +416,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
         w.row = quarter * 32 + lane;                   // row inside the tile == TMEM lane
         w.lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
         uint32_t ait = 0;
-        auto desc = [&](int pass) -> const PassDesc& { return P.passes ? P.passes[pass] : P.one; };
         int pass = 0, tl = 0;                          // (pass, local tile index) of the current item
+        Item cur = make_item(P, 0);
         if (n_items > 0) {
-            prologue(desc(0), P.rows, smem, w, (int64_t)blockIdx.x);
+            prologue(P, cur, true, smem, w, (int64_t)blockIdx.x);
             mbar_arrive(bar(A1_FULL));
         }
         for (int t = 0; t < n_items; ++t) {
@@ -394,14 +427,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)tl * gridDim.x;
             const int npass = tl + 1 < my_tiles ? pass : pass + 1, ntl = tl + 1 < my_tiles ? tl + 1 : 0;   // the next item
             const int64_t ntile = (int64_t)blockIdx.x + (int64_t)ntl * gridDim.x;
+            const Item nxt = (t + 1 < n_items && npass != pass) ? make_item(P, npass) : cur;
             if (t + 1 < n_items && w.sub == 0) {
                 // the next item's stage-input rows (x and the k's, 128 B each) are consumed by prologue() half an item
                 // from now: pull them into L2 so that those loads do not pay the DRAM latency
-                const PassDesc& nd = desc(npass);
                 const int64_t nrow = ntile * kTileM + w.row;
                 if (nrow < P.rows) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nd.x + (size_t)nrow * kD));
-                    for (int j = 0; j < nd.n_k; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(nd.k[j] + (size_t)nrow * kD));
+                    const StagePlan& np = P.st[plan_index(P, nxt, npass == 0)];
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(((npass == 0 || !P.solve) ? P.x_in : P.xw) + (size_t)nrow * kD));
+                    for (int j = 0; j < np.n_k; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.kp[np.kidx[j]] + (size_t)nrow * kD));
                 }
             }
             // ---- two activation epilogues: D1 -> layer-2 operand, D2 -> layer-3 operand
@@ -442,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
                 }
                 if (layer == 0 && t + 1 < n_items) {
                     // next item's stage input (A1 is free: this item's layer 1 has completed)
-                    prologue(desc(npass), P.rows, smem, w, ntile);
+                    prologue(P, nxt, npass == 0, smem, w, ntile);
                     mbar_arrive(bar(A1_FULL));
                 }
             }
@@ -455,11 +489,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
             tc_fence_before();
             mbar_arrive(bar(D_FREE));
             const int64_t grow = tile * kTileM + w.row;
-            const PassDesc& cd = desc(pass);
             if (grow < P.rows) {
                 const size_t goff = (size_t)grow * kD + w.sub * 8;
                 float o[8];
-                float* k_out = cd.k_out;
+                float* k_out = P.solve ? const_cast<float*>(P.kp[cur.g]) : P.k_out0;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const float4 bq = *reinterpret_cast<const float4*>(smem + kSmemBias + (2 * kH + w.sub * 8 + 4 * i) * 4);
@@ -477,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
                         for (int i = 0; i < 2; ++i) {
                             float4 q;
                             if (last) q = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-                            else q = __ldg(reinterpret_cast<const float4*>(cd.k[j] + goff) + i);
+                            else q = __ldg(reinterpret_cast<const float4*>(P.kp[j] + goff) + i);
                             const float m0 = mul_rn(b, q.x), m1 = mul_rn(b, q.y), m2 = mul_rn(b, q.z), m3 = mul_rn(b, q.w);
                             s[4 * i] = j == 0 ? m0 : add_rn(s[4 * i], m0);
                             s[4 * i + 1] = j == 0 ? m1 : add_rn(s[4 * i + 1], m1);
@@ -487,24 +520,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
                     }
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        const float4 xq = __ldg(reinterpret_cast<const float4*>(cd.x + goff) + i);
+                        const float4 xq = __ldg(reinterpret_cast<const float4*>(P.x_in + goff) + i);
                         reinterpret_cast<float4*>(P.x_new + goff)[i] =
-                            make_float4(add_rn(xq.x, mul_rn(cd.dt, s[4 * i])), add_rn(xq.y, mul_rn(cd.dt, s[4 * i + 1])),
-                                        add_rn(xq.z, mul_rn(cd.dt, s[4 * i + 2])), add_rn(xq.w, mul_rn(cd.dt, s[4 * i + 3])));
+                            make_float4(add_rn(xq.x, mul_rn(P.dt0, s[4 * i])), add_rn(xq.y, mul_rn(P.dt0, s[4 * i + 1])),
+                                        add_rn(xq.z, mul_rn(P.dt0, s[4 * i + 2])), add_rn(xq.w, mul_rn(P.dt0, s[4 * i + 3])));
                     }
                 }
             }
-            pass = npass; tl = ntl;
+            pass = npass; tl = ntl; cur = nxt;
         }
-        if (P.fin) {
+        if (P.solve) {
             // solve mode: the closing combination x_final = x + dt*(sum_j bsol_j k_j) of the last step (no evaluation)
             for (int i = 0; i < my_tiles; ++i) {
                 const int64_t grow = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTileM + w.row;
                 if (grow < P.rows) {
                     const size_t goff = (size_t)grow * kD + w.sub * 8;
                     float y[8];
-                    combine_row8(*P.fin, goff, true, y);
-                    store_row8(P.fin->save, goff, y);
+                    combine_row8(P, kUpd, P.xw, __ldg(P.dts + P.n_steps - 1), goff, true, y);
+                    store_row8(P.out + (size_t)__ldg(P.slots + P.n_steps) * P.n_state, goff, y);
                 }
             }
         }
@@ -603,14 +636,15 @@ int tdyn_mlp_tc_stage(const tdyn_mlp_t* m, const void* wsplit, float* k_out, flo
     tc::Params P{};
     P.wimg = (const uint8_t*)wsplit;
     P.b1 = m->b[0]; P.b2 = m->b[1]; P.b3 = m->b[2];
-    P.one.k_out = k_out; P.one.x = x; P.one.n_k = n_k; P.one.mode = mode; P.one.dt = dt;
+    P.k_out0 = k_out; P.x_in = x; P.dt0 = dt;
+    P.st[0].n_k = n_k; P.st[0].mode = mode;
     const int need_k = x_new ? (n_sol - 1 > n_k ? n_sol - 1 : n_k) : n_k;
     for (int j = 0; j < need_k; ++j) {
         TDYN_REQUIRE(k && k[j] && ((uintptr_t)k[j] & 15) == 0, "tdyn_mlp_tc_stage: k[%d] null or misaligned", j);
-        P.one.k[j] = k[j];
+        P.kp[j] = k[j];
     }
-    for (int j = 0; j < n_k; ++j) P.one.coef[j] = coef[j];
-    P.n_pass = 1;
+    for (int j = 0; j < n_k; ++j) { P.st[0].coef[j] = coef[j]; P.st[0].kidx[j] = j; }
+    P.n_stage = 1; P.n_steps = 1; P.solve = 0;
     P.x_new = x_new; P.n_sol = x_new ? n_sol : 0;
     for (int j = 0; j < P.n_sol; ++j) P.bsol.c[j] = bsol[j];
     P.rows = rows;
@@ -629,7 +663,7 @@ int tdyn_mlp_tc_solve_supported(const tdyn_mlp_t* m, int64_t rows) {
 
 int64_t tdyn_mlp_tc_solve_workspace_bytes(int n_steps, int n_stages) {
     if (n_steps <= 0 || n_stages <= 0 || n_stages > TDYN_MAX_STAGES) return 0;
-    return (int64_t)sizeof(tc::PassDesc) * ((int64_t)n_steps * n_stages + 1);
+    return (int64_t)(((size_t)n_steps * 4 + 15) / 16 * 16 + ((size_t)n_steps + 1) * 4);       // dts | slots
 }
 
 int tdyn_mlp_tc_solve_fixed(const tdyn_mlp_t* m, const void* wsplit, const tdyn_rk_plan_t* plan, const float* x_in, float* xw,
@@ -645,46 +679,31 @@ int tdyn_mlp_tc_solve_fixed(const tdyn_mlp_t* m, const void* wsplit, const tdyn_
                  "tdyn_mlp_tc_solve_fixed: pointers must be 16-byte aligned");
     const int n_stage = plan->n_extra + 1;
     const size_t n_state = (size_t)rows * tc::kD;
-    // the solution update x + dt*(sum_j bsol_j k_j) of step s is folded into the first stage input of step s + 1 (and into
-    // the closing combination); terms with an exactly zero coefficient are dropped (they add +-0)
-    auto fill_update = [&](tc::PassDesc& d, float dt) {
-        d.x = xw; d.n_k = 0; d.dt = dt;
-        d.mode = plan->n_sol > 1 ? TDYN_MODE_INNER : TDYN_MODE_CHAIN;
-        for (int j = 0; j < plan->n_sol; ++j)
-            if (plan->bsol[j] != 0.f) { d.k[d.n_k] = k + (size_t)j * n_state; d.coef[d.n_k] = plan->bsol[j]; ++d.n_k; }
-    };
-    std::vector<tc::PassDesc> tab((size_t)n_steps * n_stage + 1);
-    for (int s = 0; s < n_steps; ++s) {
-        for (int g = 0; g < n_stage; ++g) {
-            tc::PassDesc& d = tab[(size_t)s * n_stage + g];
-            memset(&d, 0, sizeof(d));
-            if (g == 0) {
-                if (s == 0) { d.x = x_in; d.n_k = 0; d.mode = TDYN_MODE_CHAIN; d.dt = 0.f; }
-                else fill_update(d, dts[s - 1]);
-                d.x_store = xw;
-                d.save = (s > 0 && save_slot[s] >= 0) ? out + (size_t)save_slot[s] * n_state : nullptr;
-            } else {
-                d.x = xw; d.mode = plan->mode[g - 1]; d.dt = dts[s];
-                TDYN_REQUIRE(plan->nk[g - 1] >= 0 && plan->nk[g - 1] <= g, "tdyn_mlp_tc_solve_fixed: stage %d combines later stages", g);
-                for (int j = 0; j < plan->nk[g - 1]; ++j)
-                    if (plan->a[g - 1][j] != 0.f) { d.k[d.n_k] = k + (size_t)j * n_state; d.coef[d.n_k] = plan->a[g - 1][j]; ++d.n_k; }
-            }
-            d.k_out = k + (size_t)g * n_state;
-        }
-    }
-    tc::PassDesc& fin = tab.back();
-    memset(&fin, 0, sizeof(fin));
-    fill_update(fin, dts[n_steps - 1]);
-    fin.save = out + (size_t)save_slot[n_steps] * n_state;
-    cudaStream_t st = (cudaStream_t)stream;
-    // (pageable source: the copy is staged before the call returns, so `tab` may go out of scope)
-    TDYN_CHECK_CUDA(cudaMemcpyAsync(workspace, tab.data(), sizeof(tc::PassDesc) * tab.size(), cudaMemcpyHostToDevice, st));
     tc::Params P{};
+    // terms with an exactly zero coefficient are dropped (they add +-0); the solution update x + dt*(sum_j bsol_j k_j) of
+    // step s is the first stage input of step s + 1 (and the closing combination after the last step)
+    auto fill = [&](tc::StagePlan& sp, int mode, int n, const float* c) {
+        sp.n_k = 0; sp.mode = mode;
+        for (int j = 0; j < n; ++j)
+            if (c[j] != 0.f) { sp.kidx[sp.n_k] = j; sp.coef[sp.n_k] = c[j]; ++sp.n_k; }
+    };
+    for (int g = 1; g < n_stage; ++g) {
+        TDYN_REQUIRE(plan->nk[g - 1] >= 0 && plan->nk[g - 1] <= g, "tdyn_mlp_tc_solve_fixed: stage %d combines later stages", g);
+        fill(P.st[g], plan->mode[g - 1], plan->nk[g - 1], plan->a[g - 1]);
+    }
+    fill(P.st[tc::kUpd], plan->n_sol > 1 ? TDYN_MODE_INNER : TDYN_MODE_CHAIN, plan->n_sol, plan->bsol);
+    for (int g = 0; g < n_stage; ++g) P.kp[g] = k + (size_t)g * n_state;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)workspace;
+    const size_t off_slots = ((size_t)n_steps * 4 + 15) / 16 * 16;
+    // (pageable sources: the copies are staged before the calls return)
+    TDYN_CHECK_CUDA(cudaMemcpyAsync(ws, dts, sizeof(float) * (size_t)n_steps, cudaMemcpyHostToDevice, st));
+    TDYN_CHECK_CUDA(cudaMemcpyAsync(ws + off_slots, save_slot, sizeof(int) * ((size_t)n_steps + 1), cudaMemcpyHostToDevice, st));
     P.wimg = (const uint8_t*)wsplit;
     P.b1 = m->b[0]; P.b2 = m->b[1]; P.b3 = m->b[2];
-    P.passes = (const tc::PassDesc*)workspace;
-    P.fin = P.passes + (tab.size() - 1);
-    P.n_pass = n_steps * n_stage;
+    P.x_in = x_in; P.xw = xw; P.out = out;
+    P.dts = (const float*)ws; P.slots = (const int*)(ws + off_slots);
+    P.n_state = n_state; P.n_stage = n_stage; P.n_steps = n_steps; P.solve = 1;
     P.rows = rows;
     P.num_tiles = (int)((rows + tc::kTileM - 1) / tc::kTileM);
     P.act = m->act;
