@@ -35,7 +35,7 @@ extern "C" {
 #define TDYN_API
 #endif
 
-#define TDYN_ABI_VERSION 10
+#define TDYN_ABI_VERSION 11
 #define TDYN_MAX_STAGES 7
 #define TDYN_MAX_PEERS 8
 
@@ -229,6 +229,36 @@ TDYN_API int tdyn_lin_tc_apply(const void* img, int n_out, int k_in, const float
 TDYN_API int64_t tdyn_wgrad_tc_workspace_bytes(int n_out, int k_in, int64_t rows);
 TDYN_API int tdyn_wgrad_tc(const float* g, int n_out, const float* in, int k_in, float* dw, float* db, float scale,
                   void* ws, int64_t ws_bytes, int64_t rows, void* stream);
+
+/* ---- Device-side adaptive loop for an OPAQUE vector field.  The accept/reject loop of the reference's
+ * _adaptive_odeint (numerics/odeint.py:351-407: clamp to T / next output time, attempt, error ratio, accept, output
+ * bookkeeping, adapt_step of numerics/utils.py:57-63) as a CUDA-graph conditional WHILE node: the body -- one attempted
+ * step -- is captured by the caller (tdyn_loop_begin, [tdyn_rk_combine_dev, f] x stages, tdyn_rk_finish_dev,
+ * tdyn_loop_end, tdyn_loop_commit on a capturing stream; f's own kernels are captured by PyTorch) and handed to
+ * tdyn_graph_while_create, which clones it into `while (*keep_going) body;`, instantiates it and returns the executable
+ * graph: one tdyn_graph_launch per odeint call, no host synchronisation per step.
+ * Controller state: `cf` (tdyn_loop_ctrl_sizes floats) and `ci` (ints), device arrays the caller initialises:
+ *   cf: [0] t, [1] dt, [2] T, [3] dt_keep, [4] dt of the current attempt (what *_dev kernels read), [5] error ratio,
+ *       [6] safety, [7] min_factor, [8] max_factor, [10..15] c_i, [16..21] stage times t + c_i*dt (1-element views for f)
+ *   ci: [0] ck (next output time), [1] ck_flag, [2] n_eval, [3] n_attempt, [4] n_accept, [5] n_out, [6] out_cap,
+ *       [7] return_all_eval, [8] keep_going, [9] accept, [10] output slot of this step or -1, [11] status (0 ok, 1 max
+ *       steps / NaN dt, 2 output buffer full), [12] max_steps, [13] order, [14] number of stage times, [15] trace_cap
+ * `t_eval`: device array of the n_eval output times after t0; `t_out` / `out`: [out_cap] times and states;
+ * `trace` (optional): [1 + 3*attempts] = dt0, then (t, dt, ratio) per attempt. */
+TDYN_API int tdyn_loop_ctrl_sizes(int* n_float, int* n_int);
+TDYN_API int tdyn_rk_combine_dev(float* y, const float* x, const float* const* k, const float* coef, int n_k, int mode,
+                                 const float* dt_dev, int64_t n, void* stream);
+TDYN_API int tdyn_rk_finish_dev(float* x_new, float* err_out, const float* x, const float* const* k, const float* bsol,
+                                int n_sol, const float* berr, int n_err, const float* dt_dev, float atol, float rtol, int64_t n,
+                                int64_t norm_n, double* sumsq_out, void* workspace, void* stream);
+TDYN_API int tdyn_loop_begin(float* cf, int* ci, const float* t_eval, void* stream);
+TDYN_API int tdyn_loop_end(float* cf, int* ci, const double* sumsq, int64_t norm_count, const float* t_eval, float* t_out,
+                           float* trace, void* stream);
+TDYN_API int tdyn_loop_commit(const int* ci, float* x, const float* x_new, float* k1, const float* k_last, float* out,
+                              int64_t n, void* stream);
+TDYN_API int tdyn_graph_while_create(void* body_graph, const int* keep_going, void** exec_out);
+TDYN_API int tdyn_graph_launch(void* exec, void* stream);
+TDYN_API int tdyn_graph_destroy(void* exec);
 
 #ifdef __cplusplus
 }

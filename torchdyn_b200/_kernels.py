@@ -182,6 +182,52 @@ class CudaKernels:
         _lib.check(rc, "tdyn_rk_finish")
         _launches += 1
 
+    # -- device-side loop (CUDA-graph WHILE, numerics/graph_loop.py): dt comes from the controller block on the device
+    def combine_dev(self, y: Tensor, x: Optional[Tensor], ks: List[Tensor], coefs: Sequence[float], mode: int, dt_dev: int):
+        global _launches
+        rc = self.lib.tdyn_rk_combine_dev(y.data_ptr(), _ptr(x), _pp(ks), _fp(coefs), len(ks), mode, dt_dev, y.numel(),
+                                          self._stream())
+        _lib.check(rc, "tdyn_rk_combine_dev")
+        _launches += 1
+        return y
+
+    def finish_dev(self, x_new: Tensor, x: Tensor, ks: List[Tensor], bsol, berr, dt_dev: int, atol: float, rtol: float,
+                   norm_n: int):
+        global _launches
+        rc = self.lib.tdyn_rk_finish_dev(x_new.data_ptr(), None, x.data_ptr(), _pp(ks), _fp(bsol), len(bsol), _fp(berr),
+                                         len(berr), dt_dev, float(atol), float(rtol), x.numel(), int(norm_n),
+                                         self.red.data_ptr(), self.ws.data_ptr(), self._stream())
+        _lib.check(rc, "tdyn_rk_finish_dev")
+        _launches += 1
+
+    def loop_begin(self, cf: Tensor, ci: Tensor, t_eval: Tensor):
+        global _launches
+        _lib.check(self.lib.tdyn_loop_begin(cf.data_ptr(), ci.data_ptr(), t_eval.data_ptr(), self._stream()), "tdyn_loop_begin")
+        _launches += 1
+
+    def loop_end(self, cf: Tensor, ci: Tensor, norm_count: int, t_eval: Tensor, t_out: Tensor, trace: Optional[Tensor]):
+        global _launches
+        _lib.check(self.lib.tdyn_loop_end(cf.data_ptr(), ci.data_ptr(), self.red.data_ptr(), int(norm_count), t_eval.data_ptr(),
+                                          t_out.data_ptr(), _ptr(trace), self._stream()), "tdyn_loop_end")
+        _launches += 1
+
+    def loop_commit(self, ci: Tensor, x: Tensor, x_new: Tensor, k1: Tensor, k_last: Tensor, out: Tensor):
+        global _launches
+        _lib.check(self.lib.tdyn_loop_commit(ci.data_ptr(), x.data_ptr(), x_new.data_ptr(), k1.data_ptr(), k_last.data_ptr(),
+                                             out.data_ptr(), x.numel(), self._stream()), "tdyn_loop_commit")
+        _launches += 1
+
+    def graph_while_create(self, raw_graph: int, keep_going_ptr: int) -> int:
+        h = C.c_void_p()
+        _lib.check(self.lib.tdyn_graph_while_create(raw_graph, keep_going_ptr, C.byref(h)), "tdyn_graph_while_create")
+        return h.value
+
+    def graph_launch(self, exec_handle: int):
+        _lib.check(self.lib.tdyn_graph_launch(exec_handle, self._stream()), "tdyn_graph_launch")
+
+    def graph_destroy(self, exec_handle: int):
+        self.lib.tdyn_graph_destroy(exec_handle)
+
     def init_norms(self, x0: Tensor, f0: Tensor, f1: Optional[Tensor], atol: float, rtol: float):
         """Launch K9; sums land in ``self.red[0:3]``."""
         global _launches

@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdyn_b200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_STAGES = 7
 MAX_LAYERS = 4
 MODE_CHAIN, MODE_INNER = 0, 1
@@ -97,6 +97,17 @@ SIGNATURES = {
     "tdyn_lin_tc_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_int, C.c_float, C.c_int64, C.c_void_p]),
     "tdyn_wgrad_tc_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int64]),
+    "tdyn_loop_ctrl_sizes": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "tdyn_rk_combine_dev": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp, c_float_p, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                      C.c_void_p]),
+    "tdyn_rk_finish_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_void_pp, c_float_p, C.c_int, c_float_p, C.c_int,
+                                     C.c_void_p, C.c_float, C.c_float, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tdyn_loop_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tdyn_loop_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tdyn_loop_commit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tdyn_graph_while_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tdyn_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tdyn_graph_destroy": (C.c_int, [C.c_void_p]),
     "tdyn_wgrad_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                 C.c_int64, C.c_int64, C.c_void_p]),
 }

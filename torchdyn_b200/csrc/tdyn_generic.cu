@@ -36,7 +36,9 @@ __device__ __forceinline__ float& comp(float4& v, int c) { return reinterpret_ca
 // ------------------------------------------------------------------------------------------ K5
 template <int NK, int MODE>
 __global__ void __launch_bounds__(kThreads) rk_combine_kernel(float* __restrict__ y, const float* __restrict__ x,
-                                                              KPtrs k, Coefs a, float dt, int64_t n, int vec) {
+                                                              KPtrs k, Coefs a, float dt, const float* dt_dev,
+                                                              int64_t n, int vec) {
+    if (dt_dev) dt = __ldg(dt_dev);          // device-side loop: the step size is decided by the controller kernel
     Coefs da;
 #pragma unroll
     for (int j = 0; j < NK; ++j) da.c[j] = mul_rn(dt, a.c[j]);
@@ -72,12 +74,12 @@ __global__ void __launch_bounds__(kThreads) rk_combine_kernel(float* __restrict_
 }
 
 template <int MODE>
-static int launch_combine(int n_k, float* y, const float* x, const KPtrs& k, const Coefs& a, float dt, int64_t n,
-                          int vec, cudaStream_t st) {
+static int launch_combine(int n_k, float* y, const float* x, const KPtrs& k, const Coefs& a, float dt, const float* dt_dev,
+                          int64_t n, int vec, cudaStream_t st) {
     const int grid = grid_for(vec ? (n >> 2) + 3 : n);
 #define TDYN_CASE(NK)                                                                          \
     case NK:                                                                                   \
-        rk_combine_kernel<NK, MODE><<<grid, kThreads, 0, st>>>(y, x, k, a, dt, n, vec);        \
+        rk_combine_kernel<NK, MODE><<<grid, kThreads, 0, st>>>(y, x, k, a, dt, dt_dev, n, vec); \
         break;
     switch (n_k) {
         TDYN_CASE(1) TDYN_CASE(2) TDYN_CASE(3) TDYN_CASE(4) TDYN_CASE(5) TDYN_CASE(6) TDYN_CASE(7)
@@ -172,8 +174,9 @@ __device__ __forceinline__ float finish1(float x, const float (&kv)[TDYN_MAX_STA
 }
 
 __global__ void __launch_bounds__(kThreads) rk_finish_kernel(float* __restrict__ x_new, float* __restrict__ err_out,
-                                                             const float* __restrict__ x, FinishArgs A, int64_t n,
-                                                             int64_t norm_n, int vec, ReduceWs* ws, double* out) {
+                                                             const float* __restrict__ x, FinishArgs A, const float* dt_dev,
+                                                             int64_t n, int64_t norm_n, int vec, ReduceWs* ws, double* out) {
+    if (dt_dev) A.dt = __ldg(dt_dev);
     const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     double acc[1] = {0.0};
@@ -376,8 +379,8 @@ int tdyn_version(void) { return TDYN_ABI_VERSION; }
 const char* tdyn_last_error(void) { return g_err; }
 int64_t tdyn_reduce_workspace_bytes(void) { return (int64_t)sizeof(ReduceWs); }
 
-int tdyn_rk_combine(float* y, const float* x, const float* const* k, const float* coef, int n_k, int mode, float dt,
-                    int64_t n, void* stream) {
+static int rk_combine_impl(float* y, const float* x, const float* const* k, const float* coef, int n_k, int mode, float dt,
+                           const float* dt_dev, int64_t n, void* stream) {
     TDYN_REQUIRE(y && k && coef, "tdyn_rk_combine: null argument");
     TDYN_REQUIRE(n_k >= 1 && n_k <= TDYN_MAX_STAGES, "tdyn_rk_combine: n_k=%d out of range 1..7", n_k);
     TDYN_REQUIRE(mode == TDYN_MODE_CHAIN || mode == TDYN_MODE_INNER, "tdyn_rk_combine: bad mode %d", mode);
@@ -393,13 +396,24 @@ int tdyn_rk_combine(float* y, const float* x, const float* const* k, const float
         vec = vec && aligned16(k[j]);
     }
     cudaStream_t st = (cudaStream_t)stream;
-    return mode == TDYN_MODE_CHAIN ? launch_combine<TDYN_MODE_CHAIN>(n_k, y, x, kp, a, dt, n, vec, st)
-                                   : launch_combine<TDYN_MODE_INNER>(n_k, y, x, kp, a, dt, n, vec, st);
+    return mode == TDYN_MODE_CHAIN ? launch_combine<TDYN_MODE_CHAIN>(n_k, y, x, kp, a, dt, dt_dev, n, vec, st)
+                                   : launch_combine<TDYN_MODE_INNER>(n_k, y, x, kp, a, dt, dt_dev, n, vec, st);
 }
 
-int tdyn_rk_finish(float* x_new, float* err_out, const float* x, const float* const* k, const float* bsol, int n_sol,
-                   const float* berr, int n_err, float dt, float atol, float rtol, int64_t n, int64_t norm_n,
-                   double* sumsq_out, void* workspace, void* stream) {
+int tdyn_rk_combine(float* y, const float* x, const float* const* k, const float* coef, int n_k, int mode, float dt,
+                    int64_t n, void* stream) {
+    return rk_combine_impl(y, x, k, coef, n_k, mode, dt, nullptr, n, stream);
+}
+
+int tdyn_rk_combine_dev(float* y, const float* x, const float* const* k, const float* coef, int n_k, int mode,
+                        const float* dt_dev, int64_t n, void* stream) {
+    TDYN_REQUIRE(dt_dev, "tdyn_rk_combine_dev: dt_dev is null");
+    return rk_combine_impl(y, x, k, coef, n_k, mode, 0.f, dt_dev, n, stream);
+}
+
+static int rk_finish_impl(float* x_new, float* err_out, const float* x, const float* const* k, const float* bsol, int n_sol,
+                          const float* berr, int n_err, float dt, const float* dt_dev, float atol, float rtol, int64_t n,
+                          int64_t norm_n, double* sumsq_out, void* workspace, void* stream) {
     TDYN_REQUIRE(x_new && x && k && bsol && berr && sumsq_out && workspace, "tdyn_rk_finish: null argument");
     TDYN_REQUIRE(n_sol >= 1 && n_sol <= TDYN_MAX_STAGES && n_err >= 1 && n_err <= TDYN_MAX_STAGES,
                  "tdyn_rk_finish: n_sol=%d n_err=%d out of range", n_sol, n_err);
@@ -417,10 +431,25 @@ int tdyn_rk_finish(float* x_new, float* err_out, const float* x, const float* co
     for (int j = 0; j < n_err; ++j) A.berr.c[j] = berr[j];
     A.n_sol = n_sol; A.n_err = n_err; A.dt = dt; A.atol = atol; A.rtol = rtol;
     const int grid = grid_for(vec ? (n >> 2) + 3 : n);
-    rk_finish_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x_new, err_out, x, A, n, norm_n, vec,
+    rk_finish_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x_new, err_out, x, A, dt_dev, n, norm_n, vec,
                                                                  (ReduceWs*)workspace, sumsq_out);
     TDYN_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+int tdyn_rk_finish(float* x_new, float* err_out, const float* x, const float* const* k, const float* bsol, int n_sol,
+                   const float* berr, int n_err, float dt, float atol, float rtol, int64_t n, int64_t norm_n,
+                   double* sumsq_out, void* workspace, void* stream) {
+    return rk_finish_impl(x_new, err_out, x, k, bsol, n_sol, berr, n_err, dt, nullptr, atol, rtol, n, norm_n, sumsq_out,
+                          workspace, stream);
+}
+
+int tdyn_rk_finish_dev(float* x_new, float* err_out, const float* x, const float* const* k, const float* bsol, int n_sol,
+                       const float* berr, int n_err, const float* dt_dev, float atol, float rtol, int64_t n, int64_t norm_n,
+                       double* sumsq_out, void* workspace, void* stream) {
+    TDYN_REQUIRE(dt_dev, "tdyn_rk_finish_dev: dt_dev is null");
+    return rk_finish_impl(x_new, err_out, x, k, bsol, n_sol, berr, n_err, 0.f, dt_dev, atol, rtol, n, norm_n, sumsq_out,
+                          workspace, stream);
 }
 
 int tdyn_init_norms(const float* x0, const float* f0, const float* f1, float atol, float rtol, int64_t n, double* out3,

@@ -108,6 +108,14 @@ def odeint(f: Callable, x: Tensor, t_span: Union[List, Tensor], solver: Union[st
             kern = _kernels.get(x)
             k1 = call_vf(kern, f_, t0, x)
             dt = init_step(f, k1, x, t0, solver.order, atol, rtol)      # un-negated f: reference quirk
+            from . import graph_loop
+            if graph_loop.ENABLED and isinstance(x, Tensor) and x.is_cuda:
+                # opaque f: the whole accept / reject loop as one CUDA-graph launch (no host sync per step)
+                done = graph_loop.try_device_loop(f, f_, k1, x, dt, ts, solver, atol, rtol, interpolator, return_all_eval, seminorm)
+                if done is not None:
+                    if len(save_at) > 0:
+                        warn("Setting save_at has no effect on adaptive-step methods")
+                    return done
         else:
             t0_t = torch.full((), float(t0), dtype=x.dtype, device=x.device)
             k1 = f_(t0_t, x)

@@ -54,7 +54,7 @@ def _vjp(vf, t, x, lam, integral_loss):
         dmu = torch.cat([e.flatten() if e is not None else torch.zeros(1, dtype=x.dtype, device=x.device) for e in dmu],
                         dim=-1)
         if dt_ is None:
-            dt_ = torch.zeros(1).to(t)
+            dt_ = torch.zeros(1, dtype=t.dtype, device=t.device)
         if dt_.dim() == 0:
             dt_ = dt_.unsqueeze(0)
     return dx.detach(), dlam, dmu, dt_
