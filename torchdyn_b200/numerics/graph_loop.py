@@ -43,17 +43,13 @@ _cache = weakref.WeakKeyDictionary()
 
 
 def _tensor_callable(f_):
-    """``f_`` as a callable of a DEVICE time tensor, or None when it can only be driven with host times."""
+    """``f_`` as a callable of a DEVICE time tensor, or None when it can only be driven with host times: the library's own
+    dynamics objects (fused fields, adjoint dynamics) take host-side times -- and an adjoint's VJP is issued by the autograd
+    engine's threads from inside a running backward pass, which stream capture does not survive (measured) -- so they keep
+    the host-driven loop."""
     inner = f_.f if isinstance(f_, Reversed) else f_
     if hasattr(inner, "tdyn_eval"):
-        # library-internal dynamics keep host-side times, except the backsolve adjoint on torch autograd (its __call__
-        # takes the time as a tensor)
-        from .sensitivity import BacksolveDynamics
-        if not (isinstance(inner, BacksolveDynamics) and inner.fused is None):
-            return None
-        if isinstance(f_, Reversed):
-            return lambda t, y: -inner(-t, y)
-        return inner
+        return None
     return f_
 
 
@@ -72,6 +68,24 @@ def _counters(f_):
             if nxt is not None and not isinstance(nxt, torch.Tensor):
                 stack.append(nxt)
     return out
+
+
+def _recover_after_failed_capture(device):
+    """A capture that dies half way leaves PyTorch's CUDA generator flagged as "capturing" (its epilogue never ran), which
+    would make the next random-number call fail: an empty capture runs prologue + epilogue and clears the flag."""
+    import warnings
+    try:
+        torch.cuda.synchronize(device)
+    except Exception:
+        pass
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                pass
+    except Exception:
+        pass
 
 
 class _Loop:
@@ -103,7 +117,8 @@ class _Loop:
         # accepted states are committed into this loop-owned buffer; the caller gets a copy of the rows that were written
         self.out = torch.empty(self.cap, *x.shape, dtype=torch.float32, device=dev)
         torch.cuda.synchronize(dev)
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+        # (capture mode "global": the VJP of an adjoint's dynamics is launched by the autograd engine's device thread)
+        with torch.cuda.graph(self.graph):
             kern.loop_begin(self.cf, self.ci, self.t_eval)
             ks = [self.k1]
             for i, st in enumerate(plan.stages):
@@ -197,8 +212,8 @@ def try_device_loop(f_user, f_, k1, x, dt0, ts, solver, atol, rtol, interpolator
         try:
             loop = _Loop(kern, fn, x, plan, solver, atol, rtol, len(t_eval), return_all_eval, norm_n, norm_n, counters)
         except Exception as e:      # f is not capturable (host sync, unsupported op ...): host loop
-            last_status = f"capture failed: {type(e).__name__}: {e}"
-            torch.cuda.synchronize(x.device)
+            last_status = f"capture failed: {type(e).__name__}: {str(e).splitlines()[0]}"
+            _recover_after_failed_capture(x.device)
             return None
         if holder is not None:
             if len(holder) > 4:
