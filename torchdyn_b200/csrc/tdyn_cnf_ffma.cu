@@ -25,13 +25,19 @@ using namespace ffma;
 // dst[k][r] = sum_n W[n][k] * src[n][r]  (W^T src), optionally times act'(h[k][r])
 template <int ACT>
 __device__ __forceinline__ void matvec_t(const Net& net, const float* w_s, int l, const float* src, float* dst, const float* h_for_deriv) {
-    const int K = net.dims[l], N = net.dims[l + 1];
+    const int K = net.dims[l], N = net.dims[l + 1], ld = w_ld(K);
+    if ((K & 3) == 0) {
+        gemm_kn_4x4(N, K, w_s + net.w_off[l], ld, src, dst, [&](float v, int k, int r) {
+            return h_for_deriv ? v * act_bwd<ACT>(h_for_deriv[k * kLd + r]) : v;
+        });
+        return;
+    }
     for (int i = threadIdx.x; i < kRG * K; i += kThreads) {
         const int g = i / K, k = i - g * K;
         const float* wc = w_s + net.w_off[l] + k;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int nn = 0; nn < N; ++nn) {
-            const float w = wc[nn * (K + 1)];
+            const float w = wc[nn * ld];
             const float4 sv = *reinterpret_cast<const float4*>(src + nn * kLd + 4 * g);
             acc.x = fmaf(w, sv.x, acc.x); acc.y = fmaf(w, sv.y, acc.y); acc.z = fmaf(w, sv.z, acc.z); acc.w = fmaf(w, sv.w, acc.w);
         }
@@ -45,10 +51,15 @@ __device__ __forceinline__ void matvec_t(const Net& net, const float* w_s, int l
 
 // dst[n][r] = sum_k W[n][k] * src[k][r]  (W src, no bias)
 __device__ __forceinline__ void matvec(const Net& net, const float* w_s, int l, const float* src, float* dst) {
-    const int K = net.dims[l], N = net.dims[l + 1];
+    const int K = net.dims[l], N = net.dims[l + 1], ld = w_ld(K);
+    if (((N | K) & 3) == 0) {
+        // (threads 256..: the outer product of the same phase runs on threads 0..255)
+        gemm_nk_4x4(N, K, w_s + net.w_off[l], ld, nullptr, src, dst, [](float v, int, int) { return v; }, 256);
+        return;
+    }
     for (int i = threadIdx.x; i < kRG * N; i += kThreads) {
         const int g = i / N, n = i - g * N;
-        const float* wr = w_s + net.w_off[l] + n * (K + 1);
+        const float* wr = w_s + net.w_off[l] + n * ld;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int k = 0; k < K; ++k) {
             const float w = wr[k];

@@ -14,13 +14,18 @@ constexpr int kLd = kRows + 4;       // row stride of the feature-major tiles: 3
 constexpr int kMaxWidth = 128;
 constexpr int kMaxGrid = 148 * 2;
 
+// Row stride of a weight matrix [N][K] in shared memory: a multiple of 4 floats (rows are 16-byte aligned, so four
+// consecutive k of one neuron are one LDS.128) and = 4 mod 8, so that 8 consecutive rows start in 8 distinct 16-byte bank
+// groups (lanes that read the same k-quad of consecutive neurons do not conflict).
+__host__ __device__ __forceinline__ int w_ld(int K) { return ((K + 3) & ~3) + 4; }
+
 struct Net {
     int L;
     int dims[TDYN_MAX_LAYERS + 1];
     int act;
     const float* w[TDYN_MAX_LAYERS];
     const float* b[TDYN_MAX_LAYERS];
-    int w_off[TDYN_MAX_LAYERS];      // float offsets into the shared weight area ([N][K+1])
+    int w_off[TDYN_MAX_LAYERS];      // float offsets into the shared weight area ([N][w_ld(K)])
     int b_off[TDYN_MAX_LAYERS];
     int p_off[TDYN_MAX_LAYERS];      // float offsets of layer l's (weight, bias) block in the flat parameter vector
     int h_off[TDYN_MAX_LAYERS + 1];  // float offsets of h_l ([dims[l]][kLd]) in the activation area
@@ -52,7 +57,8 @@ __device__ __forceinline__ float act_bwd2(float h) {
 __device__ __forceinline__ void load_weights(const Net& net, float* w_s) {
     for (int l = 0; l < net.L; ++l) {
         const int K = net.dims[l], N = net.dims[l + 1];
-        for (int i = threadIdx.x; i < N * K; i += kThreads) w_s[net.w_off[l] + (i / K) * (K + 1) + (i % K)] = __ldg(net.w[l] + i);
+        const int ld = w_ld(K);
+        for (int i = threadIdx.x; i < N * K; i += kThreads) w_s[net.w_off[l] + (i / K) * ld + (i % K)] = __ldg(net.w[l] + i);
         for (int i = threadIdx.x; i < N; i += kThreads) w_s[net.b_off[l] + i] = __ldg(net.b[l] + i);
     }
 }
@@ -73,27 +79,116 @@ __device__ __forceinline__ void store_tile(float* __restrict__ dst, const float*
     }
 }
 
+// `t0`: the thread that takes item 0.  Independent pieces of one phase (parameter gradient / input gradient / bias
+// gradient) start at different threads, so that they run on different warps at the same time instead of one after the
+// other on the first warps.
+// ---- register-tiled GEMM pieces.  A thread owns a 4 x 4 block (4 rows of the tile x 4 features), so one LDS.128 of
+// weights and one of activations feed 16 FFMA (the first version owned 4 x 1: two LDS per 4 FFMA, shared-memory bound at
+// ~1/10 of the FP32 rate).  Feature ownership is interleaved (feature = group + i * n_groups) where the lanes of a warp
+// read different weight rows, consecutive where they read one row: all weight / activation reads are conflict-free
+// (w_ld, kLd).  Summation order per output element is unchanged (ascending contraction index): same bits as before.
+
+// out[n][r] = epi(bias[n] + sum_k W[n][k] * in[k][r]) for N % 4 == 0, K % 4 == 0
+template <class Epi>
+__device__ __forceinline__ void gemm_nk_4x4(int N, int K, const float* __restrict__ W, int ld, const float* __restrict__ bias,
+                                            const float* __restrict__ in, float* __restrict__ out, Epi&& epi, int t0 = 0) {
+    const int NQ = N >> 2;
+    for (int item = (threadIdx.x + kThreads - t0) % kThreads; item < kRG * NQ; item += kThreads) {
+        const int ng = item % NQ, rg = item / NQ;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float bv = bias ? bias[ng + NQ * i] : 0.f;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[i][r] = bv;
+        }
+        const float* w0 = W + ng * ld;
+        const float* h0 = in + 4 * rg;
+        for (int k = 0; k < K; k += 4) {
+            float4 w[4], h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const float4*>(w0 + (NQ * i) * ld + k);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = *reinterpret_cast<const float4*>(h0 + (k + j) * kLd);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float wv[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[i][0] = fmaf(wv[j], h[j].x, acc[i][0]); acc[i][1] = fmaf(wv[j], h[j].y, acc[i][1]);
+                    acc[i][2] = fmaf(wv[j], h[j].z, acc[i][2]); acc[i][3] = fmaf(wv[j], h[j].w, acc[i][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int n = ng + NQ * i;
+            *reinterpret_cast<float4*>(out + n * kLd + 4 * rg) =
+                make_float4(epi(acc[i][0], n, 4 * rg), epi(acc[i][1], n, 4 * rg + 1), epi(acc[i][2], n, 4 * rg + 2), epi(acc[i][3], n, 4 * rg + 3));
+        }
+    }
+}
+
+// out[k][r] = epi(sum_n W[n][k] * in[n][r]) for K % 4 == 0 (any N)
+template <class Epi>
+__device__ __forceinline__ void gemm_kn_4x4(int N, int K, const float* __restrict__ W, int ld, const float* __restrict__ in,
+                                            float* __restrict__ out, Epi&& epi, int t0 = 0) {
+    const int KQ = K >> 2;
+    for (int item = (threadIdx.x + kThreads - t0) % kThreads; item < kRG * KQ; item += kThreads) {
+        const int kg = item % KQ, rg = item / KQ;
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[j][r] = 0.f;
+        const float* w0 = W + 4 * kg;
+        const float* d0 = in + 4 * rg;
+#pragma unroll 4
+        for (int n = 0; n < N; ++n) {
+            const float4 w = *reinterpret_cast<const float4*>(w0 + n * ld);
+            const float4 d = *reinterpret_cast<const float4*>(d0 + n * kLd);
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[j][0] = fmaf(wv[j], d.x, acc[j][0]); acc[j][1] = fmaf(wv[j], d.y, acc[j][1]);
+                acc[j][2] = fmaf(wv[j], d.z, acc[j][2]); acc[j][3] = fmaf(wv[j], d.w, acc[j][3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = 4 * kg + j;
+            *reinterpret_cast<float4*>(out + k * kLd + 4 * rg) =
+                make_float4(epi(acc[j][0], k, 4 * rg), epi(acc[j][1], k, 4 * rg + 1), epi(acc[j][2], k, 4 * rg + 2), epi(acc[j][3], k, 4 * rg + 3));
+        }
+    }
+}
+
 // forward through all layers for the tile in h_s[h_off[0]]; leaves every h_l in shared memory
 template <int ACT>
 __device__ __forceinline__ void forward_tile(const Net& net, const float* w_s, float* h_s) {
     for (int l = 0; l < net.L; ++l) {
-        const int K = net.dims[l], N = net.dims[l + 1];
+        const int K = net.dims[l], N = net.dims[l + 1], ld = w_ld(K);
         const float* hin = h_s + net.h_off[l];
         float* hout = h_s + net.h_off[l + 1];
         const bool last = l == net.L - 1;
-        for (int i = threadIdx.x; i < kRG * N; i += kThreads) {
-            const int g = i / N, n = i % N;
-            const float* wr = w_s + net.w_off[l] + n * (K + 1);
-            const float bias = w_s[net.b_off[l] + n];
-            float4 acc = make_float4(bias, bias, bias, bias);
-            for (int k = 0; k < K; ++k) {
-                const float w = wr[k];
-                const float4 hv = *reinterpret_cast<const float4*>(hin + k * kLd + 4 * g);
-                acc.x = fmaf(w, hv.x, acc.x); acc.y = fmaf(w, hv.y, acc.y);
-                acc.z = fmaf(w, hv.z, acc.z); acc.w = fmaf(w, hv.w, acc.w);
+        if (((N | K) & 3) == 0) {
+            gemm_nk_4x4(N, K, w_s + net.w_off[l], ld, w_s + net.b_off[l], hin, hout,
+                        [&](float v, int, int) { return last ? v : act_fwd<ACT>(v); });
+        } else {
+            for (int i = threadIdx.x; i < kRG * N; i += kThreads) {
+                const int g = i / N, n = i % N;
+                const float* wr = w_s + net.w_off[l] + n * ld;
+                const float bias = w_s[net.b_off[l] + n];
+                float4 acc = make_float4(bias, bias, bias, bias);
+                for (int k = 0; k < K; ++k) {
+                    const float w = wr[k];
+                    const float4 hv = *reinterpret_cast<const float4*>(hin + k * kLd + 4 * g);
+                    acc.x = fmaf(w, hv.x, acc.x); acc.y = fmaf(w, hv.y, acc.y);
+                    acc.z = fmaf(w, hv.z, acc.z); acc.w = fmaf(w, hv.w, acc.w);
+                }
+                if (!last) { acc.x = act_fwd<ACT>(acc.x); acc.y = act_fwd<ACT>(acc.y); acc.z = act_fwd<ACT>(acc.z); acc.w = act_fwd<ACT>(acc.w); }
+                *reinterpret_cast<float4*>(hout + n * kLd + 4 * g) = acc;
             }
-            if (!last) { acc.x = act_fwd<ACT>(acc.x); acc.y = act_fwd<ACT>(acc.y); acc.z = act_fwd<ACT>(acc.z); acc.w = act_fwd<ACT>(acc.w); }
-            *reinterpret_cast<float4*>(hout + n * kLd + 4 * g) = acc;
         }
         __syncthreads();
     }
@@ -108,7 +203,34 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float s)
 // warp broadcasts -- 5 LDS.128 per 16 FFMA per row group.
 template <class GAcc>
 __device__ __forceinline__ void outer_tile(int N, int K, const float* A, const float* B, int base, GAcc&& gacc) {
-    if ((N & 3) == 0) {
+    if (((N | K) & 3) == 0) {
+        // 4 n x 4 k per thread, both interleaved (n = ng + i*N/4, k = kg + j*K/4), lanes over kg: 8 LDS.128 per 64 FFMA
+        const int NQ = N >> 2, KQ = K >> 2;
+        for (int item = threadIdx.x; item < NQ * KQ; item += kThreads) {
+            const int kg = item % KQ, ng = item / KQ;
+            float sacc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sacc[i][j] = 0.f;
+#pragma unroll 2
+            for (int q = 0; q < kRG; ++q) {
+                float4 a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(A + (ng + NQ * i) * kLd + 4 * q);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(B + (kg + KQ * j) * kLd + 4 * q);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sacc[i][j] = dot4(a[i], b[j], sacc[i][j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gacc(base + (ng + NQ * i) * K + kg + KQ * j, sacc[i][j]);
+        }
+    } else if ((N & 3) == 0) {
         for (int i = threadIdx.x; i < (N >> 2) * K; i += kThreads) {
             const int nb = i / K, k = i - nb * K;
             const float* a0 = A + (4 * nb) * kLd;
@@ -152,19 +274,30 @@ __device__ __forceinline__ float* backward_tile(const Net& net, const float* w_s
         const float* hin = h_s + net.h_off[l];
         const int po = net.p_off[l];
         outer_tile(N, K, dcur, hin, po, gacc);
-        for (int nn = threadIdx.x; nn < N; nn += kThreads) {
+        for (int nn = (threadIdx.x + kThreads - 384) % kThreads; nn < N; nn += kThreads) {
             float s = 0.f;
 #pragma unroll
             for (int r = 0; r < kRows; ++r) s += dcur[nn * kLd + r];
             gacc(po + N * K + nn, s);
         }
         // dgrad: delta_prev[k][r] = (sum_n delta[n][r] * W[n][k]) * act'(h_l[k][r])   (no act' into the input layer)
+        const int ld = w_ld(K);
+        if ((K & 3) == 0) {
+            const float* zb = zbar ? zbar + net.h_off[l] : nullptr;
+            gemm_kn_4x4(N, K, w_s + net.w_off[l], ld, dcur, dnxt, [&](float v, int k, int r) {
+                if (l > 0) {
+                    v *= act_bwd<ACT>(hin[k * kLd + r]);
+                    if (zb) v += zb[k * kLd + r];
+                }
+                return v;
+            }, 256);       // (outer_tile occupies threads 0..255 for a 64 x 64 layer, the bias gradient 384..)
+        } else
         for (int i = threadIdx.x; i < kRG * K; i += kThreads) {
             const int g = i / K, k = i - g * K;
             const float* wc = w_s + net.w_off[l] + k;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int nn = 0; nn < N; ++nn) {
-                const float w = wc[nn * (K + 1)];
+                const float w = wc[nn * ld];
                 const float4 dv = *reinterpret_cast<const float4*>(dcur + nn * kLd + 4 * g);
                 acc.x = fmaf(w, dv.x, acc.x); acc.y = fmaf(w, dv.y, acc.y);
                 acc.z = fmaf(w, dv.z, acc.z); acc.w = fmaf(w, dv.w, acc.w);
@@ -271,7 +404,7 @@ inline int make_net(const tdyn_mlp_t* m, Net& net, const char* who) {
         TDYN_REQUIRE(m->w[l] && m->b[l], "%s: null weight/bias", who);
         net.w[l] = m->w[l]; net.b[l] = m->b[l];
         const int K = net.dims[l], N = net.dims[l + 1];
-        net.w_off[l] = woff; woff += N * (K + 1);
+        net.w_off[l] = woff; woff += N * w_ld(K);
         net.b_off[l] = woff; woff += N;
         net.p_off[l] = poff; poff += N * K + N;
     }
