@@ -812,3 +812,45 @@ def test_mlp_tc_solve_fixed_is_bit_identical_to_the_per_stage_kernel(solver, row
         assert torch.equal(a[0], b[0]) and a[1].shape == b[1].shape
         assert torch.equal(a[1], b[1]), f"{solver} save={save}: max diff {float((a[1] - b[1]).abs().max()):.3e}"
     assert torch.equal(res[("all", True)][1][-1], res[("last", True)][1][-1])
+
+
+@pytest.mark.parametrize("name", ["il_dopri5_adjoint", "il_tsit5_interp"])
+def test_integral_loss_runs_on_the_fused_adjoint(name):
+    """integral_loss with both adjoints (reference sensitivity.py:67-69, 141-143): f, its VJP and the parameter gradient stay
+    in the fused kernel, only -dg/dx of the user's running cost is a torch call; values against the executed reference."""
+    fx = load_golden(name)
+    timer = _kernels.KernelTimer()
+    _kernels.set_timer(timer)
+    try:
+        out = run_neuralode_case(fx, DEV)
+    finally:
+        _kernels.set_timer(None)
+    check_neuralode_case(fx, out, name=name)
+    names = {r[0] for r in timer.records}
+    assert "mlp_ffma_adjoint" in names, names
+
+
+def test_hypersolvers_on_gpu_match_the_oracle_formula():
+    """HyperEuler / HyperMidpoint / HyperRungeKutta4 (reference numerics/solvers/hyper.py:17-47) on the GPU: the base step on
+    this library's kernels, the learned correction dt**(p+1) * g(t, x) a torch call; against the oracle's base step with
+    the same correction added by hand on the CPU."""
+    from torchdyn_b200.numerics.solvers import HyperEuler, HyperMidpoint, HyperRungeKutta4
+    torch.manual_seed(5)
+    f_net, g_net = build_mlp([3, 8, 3], "tanh"), build_mlp([3, 8, 3], "tanh")
+    x0 = torch.randn(6, 3)
+    t_span = torch.linspace(0, 1, 6)
+    f_gpu, g_gpu = build_mlp([3, 8, 3], "tanh", list(f_net.parameters()), DEV), build_mlp([3, 8, 3], "tanh", list(g_net.parameters()), DEV)
+    for cls, sname, order in ((HyperEuler, "euler", 1), (HyperMidpoint, "midpoint", 2), (HyperRungeKutta4, "rk4", 4)):
+        with torch.no_grad():
+            n0 = _kernels.launches()
+            _, sol = odeint(lambda t, x: f_gpu(x), x0.to(DEV), t_span, cls(lambda t, x: g_gpu(x)))
+            assert _kernels.launches() > n0
+            tab = eo.Tableau(sname)
+            x, t, dt = x0, t_span[0], t_span[1] - t_span[0]
+            for i in range(1, len(t_span)):
+                _, xn, _, _ = eo.rk_step(tab, lambda t, x: f_net(x), x, t, dt)
+                x = xn + dt ** (order + 1) * g_net(x)
+                t = t + dt
+                if i < len(t_span) - 1:
+                    dt = t_span[i + 1] - t
+        assert_close(sol[-1], x, f"hyper {sname}", rtol=1e-5, atol_scale=2e-6)

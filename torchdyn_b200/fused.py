@@ -148,6 +148,7 @@ class FusedMLP:
         from the live parameters.  ``(data_ptr, _version)`` alone misses in-place updates through ``.data`` (weight
         clipping, EMA, older optimizers), and re-packing costs a few microseconds next to a solve."""
         self._key = None
+        self._fresh = False
 
     def _plain(self) -> bool:
         """Only untouched nn.Linear layers are fused: a forward / pre-forward hook (old-style weight_norm / spectral_norm
@@ -199,6 +200,14 @@ class FusedMLP:
         return self._ffma_ws
 
     def _refresh(self, kern) -> bool:
+        # within one solve (between two begin_solve calls) the first check stands: this runs once per f evaluation
+        if self.__dict__.get("_fresh") and self._fresh_dev == kern.device:
+            return self._fresh_ok
+        ok = self._refresh_now(kern)
+        self._fresh, self._fresh_dev, self._fresh_ok = True, kern.device, ok
+        return ok
+
+    def _refresh_now(self, kern) -> bool:
         if not self._plain():
             return False
         ps = [p for m in self.linears for p in (m.weight, m.bias)]
@@ -603,6 +612,8 @@ def try_adjoint_interval(dyn, A, t_from, t_to, solver, atol, rtol):
     fa = getattr(dyn, "fused", None)
     if DISABLED or not PERSISTENT or not isinstance(fa, FusedAdjoint) or not _solver_ok(solver) or not A.is_contiguous():
         return None
+    if getattr(dyn, "integral_loss", None) is not None:
+        return None       # the -dg/dx term of an integral loss is a torch call: host-driven loop around the fused adjoint
     fm, kern = fa.fm, fa.kern
     if not kern.mlp_solve_supported(fm._desc, True):
         return None
@@ -641,7 +652,7 @@ def try_interp_interval(dyn, A, t_from, t_to, solver, atol, rtol):
     sp = getattr(dyn, "spline", None)
     if DISABLED or not PERSISTENT or not isinstance(fa, FusedAdjoint) or _dist.is_enabled() or not _solver_ok(solver) or not A.is_contiguous():
         return None
-    if not all(hasattr(sp, a) for a in ("sol", "kd", "two_c", "three_d", "t")):
+    if not all(hasattr(sp, a) for a in ("sol", "kd", "two_c", "three_d", "t")) or getattr(dyn, "integral_loss", None) is not None:
         return None
     fm, kern = fa.fm, fa.kern
     if not kern.mlp_solve_supported(fm._desc, True):

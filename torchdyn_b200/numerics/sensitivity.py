@@ -60,6 +60,14 @@ def _vjp(vf, t, x, lam, integral_loss):
     return dx.detach(), dlam, dmu, dt_
 
 
+def _integral_grad(integral_loss, t, x):
+    """dg/dx of the running cost g(t, x) (reference sensitivity.py:68, :142)."""
+    with torch.set_grad_enabled(True):
+        x = x.detach().requires_grad_(True)
+        dg = torch.autograd.grad(integral_loss(t, x).sum(), x, allow_unused=True)[0]
+    return torch.zeros_like(x) if dg is None else dg
+
+
 class BacksolveDynamics:
     """d/dt [x, lam, mu, lam_t] for the backsolve adjoint on the flat vector A (sensitivity.py:57-75)."""
 
@@ -67,7 +75,7 @@ class BacksolveDynamics:
         self.vf, self.x_shape, self.lam_shape, self.P, self.integral_loss = vf, x_shape, lam_shape, n_params, integral_loss
         self.n = int(np.prod(x_shape))
         self.fused = None
-        if integral_loss is None and device is not None and tuple(x_shape) == tuple(lam_shape):
+        if device is not None and tuple(x_shape) == tuple(lam_shape):
             from .. import fused
             self.fused = fused.adjoint_for(vf, tuple(x_shape), device)
 
@@ -81,6 +89,10 @@ class BacksolveDynamics:
         out = torch.empty_like(A)
         out[-1:].zero_()
         self.fused(A[:n], A[n:2 * n], out[:n], out[n:2 * n], out[2 * n:2 * n + P], self.x_shape[0], sign)
+        if self.integral_loss:
+            # integral loss: the co-state dynamics gain -dg/dx (sensitivity.py:67-69); g is a user callable, so its
+            # gradient is a torch call, added to the fused kernel's output
+            out[n:2 * n].sub_(_integral_grad(self.integral_loss, _time(t_host, A), A[:n].reshape(self.x_shape)).flatten(), alpha=sign)
         return out
 
     def __call__(self, t, A):
@@ -99,7 +111,7 @@ class InterpDynamics:
         self.vf, self.spline, self.lam_shape, self.P, self.integral_loss = vf, spline, lam_shape, n_params, integral_loss
         self.n = int(np.prod(lam_shape))
         self.fused = None
-        if integral_loss is None and device is not None:
+        if device is not None:
             from .. import fused
             self.fused = fused.adjoint_for(vf, tuple(lam_shape), device)
 
@@ -111,6 +123,8 @@ class InterpDynamics:
             # f(x) itself is not part of [dlam, dmu]: kernels that can skip it take None
             scratch = None if getattr(self.fused, "f_optional", False) else torch.empty_like(x)
             self.fused(x, A[:n], scratch, out[:n], out[n:n + P], self.lam_shape[0], sign)
+            if self.integral_loss:      # -dg/dx on the co-state (sensitivity.py:141-143)
+                out[:n].sub_(_integral_grad(self.integral_loss, _time(t_host, A), x.reshape(self.lam_shape)).flatten(), alpha=sign)
         else:
             out = self._eval_torch(t_host, A, x)
             out = out if sign == 1.0 else -out
