@@ -35,7 +35,7 @@ extern "C" {
 #define TDYN_API
 #endif
 
-#define TDYN_ABI_VERSION 11
+#define TDYN_ABI_VERSION 12
 #define TDYN_MAX_STAGES 7
 #define TDYN_MAX_PEERS 8
 
@@ -259,6 +259,16 @@ TDYN_API int tdyn_loop_commit(const int* ci, float* x, const float* x_new, float
 TDYN_API int tdyn_graph_while_create(void* body_graph, const int* keep_going, void** exec_out);
 TDYN_API int tdyn_graph_launch(void* exec, void* stream);
 TDYN_API int tdyn_graph_destroy(void* exec);
+
+/* ---- In-kernel all-reduce(SUM) over the GPUs of one box through peer-mapped (symmetric) memory (NVLink / NVSwitch):
+ * the exchange step of the sharded solves -- the d(mu)/dt block of every stage of the sharded interpolated adjoint
+ * (numerics/sensitivity.py:124,152 puts mu inside the error norm) and the partial sums of squares of the host-driven
+ * adaptive loops (numerics/utils.py:33-34 over a sharded batch).  `comm->peer[r]` = rank r's exchange buffer of
+ * tdyn_peer_allreduce_buffer_bytes(slot_bytes) bytes (zero-initialised once), `comm->epoch` = a call counter that is equal
+ * on all ranks and increases by one per call.  One launch per GPU: all-gather by direct peer stores, per-rank release
+ * flags, fixed-order sum (deterministic).  `vec` (n floats or doubles) is reduced in place. */
+TDYN_API int64_t tdyn_peer_allreduce_buffer_bytes(int64_t slot_bytes);
+TDYN_API int tdyn_peer_allreduce(const tdyn_comm_t* comm, void* vec, int64_t n, int is_double, int64_t slot_bytes, void* stream);
 
 #ifdef __cplusplus
 }

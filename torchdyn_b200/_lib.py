@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdyn_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 MAX_STAGES = 7
 MAX_LAYERS = 4
 MODE_CHAIN, MODE_INNER = 0, 1
@@ -108,6 +108,8 @@ SIGNATURES = {
     "tdyn_graph_while_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "tdyn_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tdyn_graph_destroy": (C.c_int, [C.c_void_p]),
+    "tdyn_peer_allreduce_buffer_bytes": (C.c_int64, [C.c_int64]),
+    "tdyn_peer_allreduce": (C.c_int, [C.POINTER(Comm), C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p]),
     "tdyn_wgrad_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                 C.c_int64, C.c_int64, C.c_void_p]),
 }

@@ -19,14 +19,17 @@ from typing import Iterable, List, Optional, Tuple
 import torch
 
 _state = {"enabled": False, "group": None, "symm": None, "epoch": 0, "symm_failed": False, "replicated_from": None}
-_traffic = {"calls": 0, "bytes": 0}      # payload of the collectives issued by this module on this rank (bench.py reports it)
+_traffic = {"calls": 0, "bytes": 0, "peer_calls": 0, "peer_bytes": 0}   # collectives issued by this module on this rank
+                                                                          # (NCCL calls / in-kernel NVLink exchanges)
+PEER_ALLREDUCE = True     # all-reduce small vectors inside one kernel per GPU over peer-mapped memory (False: NCCL)
 
 
 def traffic(reset: bool = False):
     """(number of collectives, payload bytes) this rank issued through this module since the last reset."""
     out = dict(_traffic)
     if reset:
-        _traffic["calls"] = _traffic["bytes"] = 0
+        for k in _traffic:
+            _traffic[k] = 0
     return out
 
 
@@ -129,9 +132,54 @@ def local_norm_count(count: int) -> int:
     return min(int(count), rf)
 
 
+def _peer_allreduce_(t: torch.Tensor) -> bool:
+    """In-place sum over ranks by ``tdyn_peer_allreduce`` (one kernel per GPU: all-gather by NVLink peer stores, flags,
+    fixed-order sum).  False when unavailable (no peer-mapped memory, more than 8 ranks, unsupported tensor)."""
+    if not PEER_ALLREDUCE or _state.get("ar_failed") or not (t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.float64)):
+        return False
+    import ctypes as C
+    import torch.distributed as dist
+    from . import _lib
+    nbytes = t.numel() * t.element_size()
+    ar = _state.get("ar")
+    if ar is None or nbytes > ar["slot_bytes"]:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            lib = _lib.load()
+            group = _state["group"] if _state["group"] is not None else dist.group.WORLD
+            slot = max(2 << 20, (nbytes + (1 << 20) - 1) >> 20 << 20)          # collective: every rank computes the same size
+            buf = symm_mem.empty(int(lib.tdyn_peer_allreduce_buffer_bytes(slot)), dtype=torch.uint8, device=t.device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, group)
+            torch.cuda.synchronize(t.device)
+            dist.barrier(group)
+            if hdl.world_size > 8:
+                raise RuntimeError("more than 8 ranks")
+            ar = _state["ar"] = {"buf": buf, "hdl": hdl, "ptrs": [int(p) for p in hdl.buffer_ptrs], "slot_bytes": slot, "seq": 0}
+        except Exception as e:
+            import warnings
+            warnings.warn(f"torchdyn_b200: peer-memory all-reduce unavailable ({e}); using NCCL")
+            _state["ar_failed"] = True
+            return False
+    ar["seq"] += 1
+    c = _lib.Comm()
+    c.world, c.rank, c.epoch = ar["hdl"].world_size, ar["hdl"].rank, ar["seq"]
+    for r, p in enumerate(ar["ptrs"]):
+        c.peer[r] = p
+    with torch.cuda.device(t.device):
+        rc = _lib.load().tdyn_peer_allreduce(C.byref(c), t.data_ptr(), t.numel(), int(t.dtype == torch.float64), ar["slot_bytes"],
+                                             torch.cuda.current_stream(t.device).cuda_stream)
+    _lib.check(rc, "tdyn_peer_allreduce")
+    _traffic["peer_calls"] += 1
+    _traffic["peer_bytes"] += nbytes
+    return True
+
+
 def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     """In-place sum over ranks (no-op when sharding is off)."""
     if _state["enabled"]:
+        if _peer_allreduce_(t):
+            return t
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_state["group"])
         _count(t)
@@ -145,8 +193,9 @@ def reduce_sums(kern, n_sums: int, local_count: int) -> Tuple[List[float], int]:
         return kern.read_reduction(n_sums), int(local_count)
     import torch.distributed as dist
     kern.red[3].fill_(float(local_count))
-    dist.all_reduce(kern.red, op=dist.ReduceOp.SUM, group=_state["group"])
-    _count(kern.red)
+    if not _peer_allreduce_(kern.red):
+        dist.all_reduce(kern.red, op=dist.ReduceOp.SUM, group=_state["group"])
+        _count(kern.red)
     vals = kern.read_reduction(4)
     return vals[:n_sums], int(round(vals[3]))
 
