@@ -342,7 +342,7 @@ def sharded_configs(dev, rank, world, iters=3):
         ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         tr = tdist.traffic(reset=True)
-        return float(ms), nfe, tr["calls"] / iters, tr["bytes"] / iters
+        return float(ms), nfe, {k: v / iters for k, v in tr.items()}
 
     def training(net, shard, B_global, kw, label, collective):
         def step():
@@ -355,18 +355,22 @@ def sharded_configs(dev, rank, world, iters=3):
             tdist.allreduce_gradients(net.parameters())
             tdist.disable()
             return float(model.vf.nfe)
-        ms, nfe, calls, nbytes = timed(step)
+        ms, nfe, tr = timed(step)
         return {"workload": label, "global_batch": B_global, "rows_per_gpu": shard.shape[0], "nfe_per_iter": nfe,
                 "ms_per_iter": ms, "sample_nfe_per_s": B_global * nfe / (ms * 1e-3), "sharding": collective,
-                "collectives_per_iter": calls, "collective_payload_bytes_per_iter_per_rank": nbytes, "path": fused.last_used()}
+                "nvlink_peer_exchanges_per_iter": tr["peer_calls"], "nvlink_peer_payload_bytes_per_iter_per_rank": tr["peer_bytes"],
+                "nccl_collectives_per_iter": tr["calls"], "nccl_payload_bytes_per_iter_per_rank": tr["bytes"],
+                "path": fused.last_used()}
 
     # ---- config 3 (tsit5 + interpolated adjoint, 128-1024-128): strong (262 144 rows in total) and weak (per GPU)
     torch.manual_seed(0)
     net3 = nn.Sequential(nn.Linear(128, 1024), nn.Tanh(), nn.Linear(1024, 128)).to(dev)
     kw3 = dict(solver="tsit5", sensitivity="interpolated_adjoint")
     coll3 = (f"batch rows x{world}; per attempted step an all-reduce(SUM) of 4 fp64 (global RMS error norm: sum of squares + "
-             "counts), per adjoint stage an all-reduce(SUM) of d(mu)/dt (263 296 fp32: mu sits inside the interpolated "
-             "adjoint's norm), one gradient all-reduce(SUM) per iteration; NCCL over NVLink")
+             "counts) and per adjoint stage an all-reduce(SUM) of d(mu)/dt (263 296 fp32: mu sits inside the interpolated "
+             "adjoint's norm), both by tdyn_peer_allreduce = ONE kernel per GPU that all-gathers by direct NVLink peer "
+             "stores into every rank's exchange buffer, releases per-rank flags and adds in rank order (deterministic, no "
+             "NCCL call); one gradient all-reduce(SUM) per iteration through NCCL")
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     rows = 262144 // world
     out["c3_strong"] = training(net3, torch.randn(rows, 128, generator=g, device=dev), 262144, kw3,
@@ -380,7 +384,8 @@ def sharded_configs(dev, rank, world, iters=3):
     net2 = make_net(dev)
     kw2 = dict(solver="dopri5", atol=1e-4, rtol=1e-4, sensitivity="adjoint", atol_adjoint=1e-4, rtol_adjoint=1e-4)
     coll2 = (f"batch rows x{world}; per attempted step (forward and adjoint) an all-reduce(SUM) of 4 fp64 (global RMS error "
-             "norm / seminorm), one gradient all-reduce(SUM) of 82 464 fp32 per iteration; NCCL over NVLink")
+             "norm / seminorm) by tdyn_peer_allreduce (in-kernel NVLink peer stores + flags, fixed-order sum), one gradient "
+             "all-reduce(SUM) of 82 464 fp32 per iteration through NCCL")
     out["c2a_weak"] = training(net2, torch.randn(262144, 32, generator=g, device=dev), 262144 * world, kw2,
                                "c2a dopri5 1e-4 + backsolve adjoint, MLP 32-256-256-32, 262144 rows per GPU (weak scaling)", coll2)
     del net2
@@ -406,7 +411,7 @@ def sharded_configs(dev, rank, world, iters=3):
         tdist.disable()
         attempts[0] = len(tr[0]["t"]) if tr else 0
         return float(fld.nfe - n0)
-    ms, nfe, _, _ = timed(solve)
+    ms, nfe, _ = timed(solve)
     path = fused.last_used() or ""
     out["dopri5_persistent_weak"] = {
         "workload": "dopri5 1e-5 forward, MLP 8-64-8 (gain 2), 262144 rows per GPU, whole solve in ONE persistent kernel per GPU",
@@ -426,7 +431,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help=argparse.SUPPRESS)
-    ap.add_argument("--configs", default="1,2a,3,4", help="configs block: comma-separated of 1,2a,3,4,5 or 'none'")
+    ap.add_argument("--configs", default="1,2a,3,4,5", help="configs block: comma-separated of 1,2a,3,4,5 or 'none'")
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-eager-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--force-generic", action="store_true", help="keep f a torch call (generic kernels only)")
