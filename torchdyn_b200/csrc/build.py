@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libtdyn_b200.so")
 SOURCES = ["tdyn_generic.cu", "tdyn_mlp_tc.cu", "tdyn_mlp_ffma.cu", "tdyn_mlp_solve.cu", "tdyn_cnf_ffma.cu", "tdyn_wide_tc.cu", "tdyn_graph_loop.cu", "tdyn_peer.cu"]
 HEADERS = ["tdyn_common.cuh", "tdyn_mlp_ffma.cuh", "tdyn_tc_ptx.cuh", os.path.join("..", "..", "include", "tdyn_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+NVCC_FLAGS = (["-DTDYN_FFMA_FEAT_TILE=" + os.environ["TDYN_FFMA_FEAT_TILE"]] if os.environ.get("TDYN_FFMA_FEAT_TILE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--fmad=true",  # parity-critical code uses explicit __f*_rn intrinsics; the MLP dot products may fuse
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -13,6 +13,10 @@ constexpr int kLd = kRows + 4;       // row stride of the feature-major tiles: 3
                                      // (an unpadded stride of 8 x 16 B would be 8-way conflicted)
 constexpr int kMaxWidth = 128;
 constexpr int kMaxGrid = 148 * 2;
+#ifndef TDYN_FFMA_FEAT_TILE
+#define TDYN_FFMA_FEAT_TILE 2
+#endif
+constexpr int kFeatTile = TDYN_FFMA_FEAT_TILE;      // features per thread in the register-tiled GEMM pieces (x 4 rows)
 
 // Row stride of a weight matrix [N][K] in shared memory: a multiple of 4 floats (rows are 16-byte aligned, so four
 // consecutive k of one neuron are one LDS.128) and = 4 mod 8, so that 8 consecutive rows start in 8 distinct 16-byte bank
@@ -82,22 +86,23 @@ __device__ __forceinline__ void store_tile(float* __restrict__ dst, const float*
 // `t0`: the thread that takes item 0.  Independent pieces of one phase (parameter gradient / input gradient / bias
 // gradient) start at different threads, so that they run on different warps at the same time instead of one after the
 // other on the first warps.
-// ---- register-tiled GEMM pieces.  A thread owns a 4 x 4 block (4 rows of the tile x 4 features), so one LDS.128 of
-// weights and one of activations feed 16 FFMA (the first version owned 4 x 1: two LDS per 4 FFMA, shared-memory bound at
-// ~1/10 of the FP32 rate).  Feature ownership is interleaved (feature = group + i * n_groups) where the lanes of a warp
+// ---- register-tiled GEMM pieces.  A thread owns a block of 4 rows of the tile x kFeatTile features and steps the
+// contraction four at a time: kFeatTile + 4 LDS.128 feed 16 * kFeatTile FFMA (the first version owned 4 x 1: two LDS per 4
+// FFMA, shared-memory bound at ~1/10 of the FP32 rate).  Measured on config 4 / the 2-64-64-64-2 persistent solve:
+// kFeatTile = 4 (128 busy threads per 64-wide layer) 14.7 / 9.05 ms, kFeatTile = 2 (256 busy threads) 14.3 / 7.9 ms.  Feature ownership is interleaved (feature = group + i * n_groups) where the lanes of a warp
 // read different weight rows, consecutive where they read one row: all weight / activation reads are conflict-free
 // (w_ld, kLd).  Summation order per output element is unchanged (ascending contraction index): same bits as before.
 
 // out[n][r] = epi(bias[n] + sum_k W[n][k] * in[k][r]) for N % 4 == 0, K % 4 == 0
-template <class Epi>
+template <int NT = kFeatTile, class Epi>
 __device__ __forceinline__ void gemm_nk_4x4(int N, int K, const float* __restrict__ W, int ld, const float* __restrict__ bias,
                                             const float* __restrict__ in, float* __restrict__ out, Epi&& epi, int t0 = 0) {
-    const int NQ = N >> 2;
+    const int NQ = N / NT;
     for (int item = (threadIdx.x + kThreads - t0) % kThreads; item < kRG * NQ; item += kThreads) {
         const int ng = item % NQ, rg = item / NQ;
-        float acc[4][4];
+        float acc[NT][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NT; ++i) {
             const float bv = bias ? bias[ng + NQ * i] : 0.f;
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[i][r] = bv;
@@ -105,13 +110,13 @@ __device__ __forceinline__ void gemm_nk_4x4(int N, int K, const float* __restric
         const float* w0 = W + ng * ld;
         const float* h0 = in + 4 * rg;
         for (int k = 0; k < K; k += 4) {
-            float4 w[4], h[4];
+            float4 w[NT], h[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const float4*>(w0 + (NQ * i) * ld + k);
+            for (int i = 0; i < NT; ++i) w[i] = *reinterpret_cast<const float4*>(w0 + (NQ * i) * ld + k);
 #pragma unroll
             for (int j = 0; j < 4; ++j) h[j] = *reinterpret_cast<const float4*>(h0 + (k + j) * kLd);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < NT; ++i) {
                 const float wv[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -121,7 +126,7 @@ __device__ __forceinline__ void gemm_nk_4x4(int N, int K, const float* __restric
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NT; ++i) {
             const int n = ng + NQ * i;
             *reinterpret_cast<float4*>(out + n * kLd + 4 * rg) =
                 make_float4(epi(acc[i][0], n, 4 * rg), epi(acc[i][1], n, 4 * rg + 1), epi(acc[i][2], n, 4 * rg + 2), epi(acc[i][3], n, 4 * rg + 3));
@@ -130,33 +135,34 @@ __device__ __forceinline__ void gemm_nk_4x4(int N, int K, const float* __restric
 }
 
 // out[k][r] = epi(sum_n W[n][k] * in[n][r]) for K % 4 == 0 (any N)
-template <class Epi>
+template <int KT = kFeatTile, class Epi>
 __device__ __forceinline__ void gemm_kn_4x4(int N, int K, const float* __restrict__ W, int ld, const float* __restrict__ in,
                                             float* __restrict__ out, Epi&& epi, int t0 = 0) {
-    const int KQ = K >> 2;
+    const int KQ = K / KT;
     for (int item = (threadIdx.x + kThreads - t0) % kThreads; item < kRG * KQ; item += kThreads) {
         const int kg = item % KQ, rg = item / KQ;
-        float acc[4][4];
+        float acc[KT][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < KT; ++j)
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[j][r] = 0.f;
-        const float* w0 = W + 4 * kg;
+        const float* w0 = W + KT * kg;
         const float* d0 = in + 4 * rg;
 #pragma unroll 4
         for (int n = 0; n < N; ++n) {
-            const float4 w = *reinterpret_cast<const float4*>(w0 + n * ld);
+            float wv[KT];
+            if (KT == 4) { const float4 w = *reinterpret_cast<const float4*>(w0 + n * ld); wv[0] = w.x; wv[1] = w.y; wv[KT - 2] = w.z; wv[KT - 1] = w.w; }
+            else { const float2 w = *reinterpret_cast<const float2*>(w0 + n * ld); wv[0] = w.x; wv[1] = w.y; }
             const float4 d = *reinterpret_cast<const float4*>(d0 + n * kLd);
-            const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < KT; ++j) {
                 acc[j][0] = fmaf(wv[j], d.x, acc[j][0]); acc[j][1] = fmaf(wv[j], d.y, acc[j][1]);
                 acc[j][2] = fmaf(wv[j], d.z, acc[j][2]); acc[j][3] = fmaf(wv[j], d.w, acc[j][3]);
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = 4 * kg + j;
+        for (int j = 0; j < KT; ++j) {
+            const int k = KT * kg + j;
             *reinterpret_cast<float4*>(out + k * kLd + 4 * rg) =
                 make_float4(epi(acc[j][0], k, 4 * rg), epi(acc[j][1], k, 4 * rg + 1), epi(acc[j][2], k, 4 * rg + 2), epi(acc[j][3], k, 4 * rg + 3));
         }
