@@ -35,7 +35,7 @@ extern "C" {
 #define TDYN_API
 #endif
 
-#define TDYN_ABI_VERSION 12
+#define TDYN_ABI_VERSION 13
 #define TDYN_MAX_STAGES 7
 #define TDYN_MAX_PEERS 8
 
@@ -193,6 +193,12 @@ TDYN_API int tdyn_mlp_tc_prepare(const tdyn_mlp_t* mlp, void* wsplit, void* stre
 TDYN_API int tdyn_mlp_tc_stage(const tdyn_mlp_t* mlp, const void* wsplit, float* k_out, float* y_out,
                       const float* x, const float* const* k, const float* coef, int n_k, int mode, float dt,
                       float* x_new, const float* bsol, int n_sol, int64_t rows, void* stream);
+
+/* K2, forward with the hidden activations kept: out = scale * f(x), a1 / a2 = the two hidden activations [rows, 256] --
+ * the forward half of the adjoint dynamics (numerics/sensitivity.py:62-66: `dx = vf(t, x)` under autograd keeps the
+ * activations for the VJP); `scale` folds the negation of the reversed-time field. */
+TDYN_API int tdyn_mlp_tc_forward_save(const tdyn_mlp_t* mlp, const void* wsplit, float* out, const float* x, float scale,
+                                      float* a1, float* a2, int64_t rows, void* stream);
 
 /* K2 (persistent form). A whole FIXED-STEP solve of the same MLP class -- the loop of numerics/odeint.py:411-445 around
  * RungeKutta4.step / Euler.step / Midpoint.step (numerics/solvers/ode.py:61-104) -- in ONE launch: every CTA walks

@@ -292,6 +292,17 @@ class CudaKernels:
         _lib.check(rc, "tdyn_mlp_tc_stage")
         _launches += 1
 
+    def mlp_tc_forward_save(self, desc, img: Tensor, out: Tensor, x: Tensor, scale: float, a1: Tensor, a2: Tensor,
+                            flops_per_row: float):
+        """out = scale * f(x) with both hidden activations written out (forward half of the adjoint dynamics)."""
+        global _launches
+        rows = x.numel() // 32
+        with _Timed("mlp_tc_stage", flops_per_row * rows):
+            rc = self.lib.tdyn_mlp_tc_forward_save(C.byref(desc), img.data_ptr(), out.data_ptr(), x.data_ptr(), float(scale),
+                                                   a1.data_ptr(), a2.data_ptr(), rows, self._stream())
+        _lib.check(rc, "tdyn_mlp_tc_forward_save")
+        _launches += 1
+
     def mlp_tc_solve_supported(self, desc, rows: int) -> bool:
         return bool(self.lib.tdyn_mlp_tc_solve_supported(C.byref(desc), int(rows)))
 

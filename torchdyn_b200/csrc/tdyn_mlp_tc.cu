@@ -84,6 +84,9 @@ struct Params {
     int n_stage, n_steps;      // stage mode: 1, 1
     int solve;                 // 0: stage mode, 1: solve mode
     float* x_new; Coefs bsol; int n_sol;      // stage mode only: x + dt*(sum_j bsol_j k_j) in the output epilogue
+    float* act_out[2];         // stage mode only: the hidden activations a1, a2 ([rows][256]) are also written here (the
+                               // adjoint's input / parameter gradients need them), or NULL
+    float out_scale;           // k_out = out_scale * f(y)  (1 except for the reversed-time field of an adjoint)
     int64_t rows; int num_tiles; int act;
 };
 
@@ -271,7 +274,9 @@ __device__ __forceinline__ void prologue(const Params& P, const Item& it, bool f
     fence_proxy_async();
 }
 
-template <int ACT>
+// SAVE: also write the hidden activations (and scale the output) -- the adjoint's forward half; a separate instantiation so
+// that the integration kernels carry none of it (registers are at the limit of 576 threads per SM)
+template <int ACT, bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_constant__ Params P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t tmem_base_slot;
@@ -425,6 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
         for (int t = 0; t < n_items; ++t) {
             const uint32_t tpar = t & 1;
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)tl * gridDim.x;
+            const int64_t grow_cur = SAVE ? tile * kTileM + w.row : 0;
             const int npass = tl + 1 < my_tiles ? pass : pass + 1, ntl = tl + 1 < my_tiles ? tl + 1 : 0;   // the next item
             const int64_t ntile = (int64_t)blockIdx.x + (int64_t)ntl * gridDim.x;
             const Item nxt = (t + 1 < n_items && npass != pass) ? make_item(P, npass) : cur;
@@ -466,6 +472,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
                     v[2] = activate_biased<ACT>(__uint_as_float(cur[2]), b0.z); v[3] = activate_biased<ACT>(__uint_as_float(cur[3]), b0.w);
                     v[4] = activate_biased<ACT>(__uint_as_float(cur[4]), b1.x); v[5] = activate_biased<ACT>(__uint_as_float(cur[5]), b1.y);
                     v[6] = activate_biased<ACT>(__uint_as_float(cur[6]), b1.z); v[7] = activate_biased<ACT>(__uint_as_float(cur[7]), b1.w);
+                    if (SAVE && grow_cur < P.rows) {
+                        float4* dst = reinterpret_cast<float4*>(P.act_out[layer] + (size_t)grow_cur * kH + j * kKB + w.sub * 8);
+                        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    }
                     const uint32_t as = ait % kLoStages, au = ait / kLoStages;
                     mbar_wait(bar(A_EMPTY0 + as), (au & 1) ^ 1);
                     store_split8_tmem(src + (uint32_t)(j * kKB), smem + kSmemLoRing + as * kATile, w.row, w.sub, v);
@@ -496,8 +507,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const float4 bq = *reinterpret_cast<const float4*>(smem + kSmemBias + (2 * kH + w.sub * 8 + 4 * i) * 4);
-                    o[4 * i] = __uint_as_float(ro[4 * i]) + bq.x; o[4 * i + 1] = __uint_as_float(ro[4 * i + 1]) + bq.y;
-                    o[4 * i + 2] = __uint_as_float(ro[4 * i + 2]) + bq.z; o[4 * i + 3] = __uint_as_float(ro[4 * i + 3]) + bq.w;
+                    const float sc = SAVE ? P.out_scale : 1.f;
+                    o[4 * i] = sc * (__uint_as_float(ro[4 * i]) + bq.x); o[4 * i + 1] = sc * (__uint_as_float(ro[4 * i + 1]) + bq.y);
+                    o[4 * i + 2] = sc * (__uint_as_float(ro[4 * i + 2]) + bq.z); o[4 * i + 3] = sc * (__uint_as_float(ro[4 * i + 3]) + bq.w);
                     reinterpret_cast<float4*>(k_out + goff)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                 }
                 if (P.x_new) {
@@ -587,6 +599,26 @@ __global__ void prepare_weights_kernel(const float* __restrict__ w1, const float
 
 using namespace tdyn;
 
+template <bool SAVE>
+static int launch_tc_t(const tdyn_mlp_t* m, tc::Params& P, int grid, cudaStream_t st) {
+    static thread_local unsigned long long seen = 0;
+    if (first_use_on_device(seen)) {
+        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_TANH, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
+        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_SOFTPLUS, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
+        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_RELU, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
+    }
+    switch (m->act) {
+        case TDYN_ACT_TANH: tc::mlp_tc_stage_kernel<TDYN_ACT_TANH, SAVE><<<grid, tc::kThreads, tc::kSmemTotal, st>>>(P); break;
+        case TDYN_ACT_SOFTPLUS: tc::mlp_tc_stage_kernel<TDYN_ACT_SOFTPLUS, SAVE><<<grid, tc::kThreads, tc::kSmemTotal, st>>>(P); break;
+        default: tc::mlp_tc_stage_kernel<TDYN_ACT_RELU, SAVE><<<grid, tc::kThreads, tc::kSmemTotal, st>>>(P); break;
+    }
+    TDYN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+static int launch_tc(const tdyn_mlp_t* m, tc::Params& P, int grid, cudaStream_t st) {
+    return P.act_out[0] ? launch_tc_t<true>(m, P, grid, st) : launch_tc_t<false>(m, P, grid, st);
+}
+
 extern "C" {
 
 int tdyn_mlp_tc_supported(const tdyn_mlp_t* m) {
@@ -603,22 +635,6 @@ int tdyn_mlp_tc_prepare(const tdyn_mlp_t* m, void* wsplit, void* stream) {
     TDYN_REQUIRE(tdyn_mlp_tc_supported(m), "tdyn_mlp_tc_prepare: unsupported MLP shape (need 32-256-256-32)");
     TDYN_REQUIRE(wsplit && ((uintptr_t)wsplit & 15) == 0, "tdyn_mlp_tc_prepare: wsplit must be 16-byte aligned");
     tc::prepare_weights_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(m->w[0], m->w[1], m->w[2], (uint8_t*)wsplit);
-    TDYN_CHECK_CUDA(cudaGetLastError());
-    return 0;
-}
-
-static int launch_tc(const tdyn_mlp_t* m, tc::Params& P, int grid, cudaStream_t st) {
-    static thread_local unsigned long long seen = 0;
-    if (first_use_on_device(seen)) {
-        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
-        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_SOFTPLUS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
-        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
-    }
-    switch (m->act) {
-        case TDYN_ACT_TANH: tc::mlp_tc_stage_kernel<TDYN_ACT_TANH><<<grid, tc::kThreads, tc::kSmemTotal, st>>>(P); break;
-        case TDYN_ACT_SOFTPLUS: tc::mlp_tc_stage_kernel<TDYN_ACT_SOFTPLUS><<<grid, tc::kThreads, tc::kSmemTotal, st>>>(P); break;
-        default: tc::mlp_tc_stage_kernel<TDYN_ACT_RELU><<<grid, tc::kThreads, tc::kSmemTotal, st>>>(P); break;
-    }
     TDYN_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -644,9 +660,30 @@ int tdyn_mlp_tc_stage(const tdyn_mlp_t* m, const void* wsplit, float* k_out, flo
         P.kp[j] = k[j];
     }
     for (int j = 0; j < n_k; ++j) { P.st[0].coef[j] = coef[j]; P.st[0].kidx[j] = j; }
-    P.n_stage = 1; P.n_steps = 1; P.solve = 0;
+    P.n_stage = 1; P.n_steps = 1; P.solve = 0; P.out_scale = 1.f;
     P.x_new = x_new; P.n_sol = x_new ? n_sol : 0;
     for (int j = 0; j < P.n_sol; ++j) P.bsol.c[j] = bsol[j];
+    P.rows = rows;
+    P.num_tiles = (int)((rows + tc::kTileM - 1) / tc::kTileM);
+    P.act = m->act;
+    const int grid = P.num_tiles < kNumSMs ? P.num_tiles : kNumSMs;
+    return launch_tc(m, P, grid, (cudaStream_t)stream);
+}
+
+int tdyn_mlp_tc_forward_save(const tdyn_mlp_t* m, const void* wsplit, float* out, const float* x, float scale, float* a1,
+                             float* a2, int64_t rows, void* stream) {
+    TDYN_REQUIRE(tdyn_mlp_tc_supported(m), "tdyn_mlp_tc_forward_save: unsupported MLP shape (need 32-256-256-32)");
+    TDYN_REQUIRE(wsplit && out && x && a1 && a2, "tdyn_mlp_tc_forward_save: null argument");
+    TDYN_REQUIRE((((uintptr_t)x | (uintptr_t)out | (uintptr_t)a1 | (uintptr_t)a2) & 15) == 0,
+                 "tdyn_mlp_tc_forward_save: pointers must be 16-byte aligned");
+    if (rows <= 0) return 0;
+    tc::Params P{};
+    P.wimg = (const uint8_t*)wsplit;
+    P.b1 = m->b[0]; P.b2 = m->b[1]; P.b3 = m->b[2];
+    P.k_out0 = out; P.x_in = x; P.dt0 = 0.f;
+    P.st[0].n_k = 0; P.st[0].mode = TDYN_MODE_CHAIN;
+    P.n_stage = 1; P.n_steps = 1; P.solve = 0; P.out_scale = scale;
+    P.act_out[0] = a1; P.act_out[1] = a2;
     P.rows = rows;
     P.num_tiles = (int)((rows + tc::kTileM - 1) / tc::kTileM);
     P.act = m->act;
@@ -703,7 +740,7 @@ int tdyn_mlp_tc_solve_fixed(const tdyn_mlp_t* m, const void* wsplit, const tdyn_
     P.b1 = m->b[0]; P.b2 = m->b[1]; P.b3 = m->b[2];
     P.x_in = x_in; P.xw = xw; P.out = out;
     P.dts = (const float*)ws; P.slots = (const int*)(ws + off_slots);
-    P.n_state = n_state; P.n_stage = n_stage; P.n_steps = n_steps; P.solve = 1;
+    P.n_state = n_state; P.n_stage = n_stage; P.n_steps = n_steps; P.solve = 1; P.out_scale = 1.f;
     P.rows = rows;
     P.num_tiles = (int)((rows + tc::kTileM - 1) / tc::kTileM);
     P.act = m->act;
