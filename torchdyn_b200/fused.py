@@ -302,14 +302,15 @@ def wide_forward(fm: "FusedMLP", kern, y, out, sign: float = 1.0):
     (skipped when ``out`` is None: the interpolated adjoint does not need f itself)."""
     imgs, dims, rows = fm.wide_images(kern), fm.dims, y.numel() // fm.dims[0]
     L = len(fm.linears)
-    if out is not None and fm.ready(kern) and rows > 0:
+    if fm.ready(kern) and rows > 0:
         # the 32-256-256-32 class: ONE launch of the fused stage kernel, hidden activations written out on the way
+        # (also when the caller does not need f itself: the same kernel, so the same activations to the last bit)
         ya = _aligned(y)
-        o = out if out.data_ptr() % 16 == 0 else torch.empty(rows, dims[-1], dtype=torch.float32, device=y.device)
+        o = out if out is not None and out.data_ptr() % 16 == 0 else torch.empty(rows, dims[-1], dtype=torch.float32, device=y.device)
         a1 = torch.empty(rows, dims[1], dtype=torch.float32, device=y.device)
         a2 = torch.empty(rows, dims[2], dtype=torch.float32, device=y.device)
         kern.mlp_tc_forward_save(fm._desc, fm._img, o, ya, sign, a1, a2, fm.flops_per_row)
-        if o is not out:
+        if out is not None and o is not out:
             out.view(-1).copy_(o.view(-1))
         return [a1, a2]
     h, saved = _aligned(y), []
