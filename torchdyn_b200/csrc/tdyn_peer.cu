@@ -15,13 +15,28 @@ namespace peer {
 
 constexpr int kThreads = 256;
 constexpr int kMaxBlocks = 64;          // all blocks must be co-resident: they wait for one another's peers
-constexpr size_t kHeader = 1024;        // flags[2][TDYN_MAX_PEERS] (u32) | ticket | error
+constexpr size_t kHeader = 1024;        // flags | tickets | error
 
 struct Header {
-    unsigned int flag[2][TDYN_MAX_PEERS];
+    unsigned int flag[2][TDYN_MAX_PEERS];       // one-shot: data of rank q has landed; two-shot: rank q's input is published
+    unsigned int flag2[2][TDYN_MAX_PEERS];      // two-shot: rank q has written its chunk of the result everywhere
     unsigned int ticket;
+    unsigned int ticket2;
     unsigned int error;
 };
+
+__device__ __forceinline__ bool wait_flags(const unsigned int* flags, int world, unsigned int seq) {
+    for (int q = 0; q < world; ++q) {
+        unsigned int seen = 0;
+        for (long long spin = 0; spin < (1ll << 26); ++spin) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags + q) : "memory");
+            if (seen == seq) break;
+            __nanosleep(32);
+        }
+        if (seen != seq) return false;
+    }
+    return true;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) allreduce_kernel(tdyn_comm_t comm, T* __restrict__ vec, int64_t n, int64_t cap_bytes) {
@@ -83,6 +98,73 @@ __global__ void __launch_bounds__(kThreads) allreduce_kernel(tdyn_comm_t comm, T
     }
 }
 
+// Two-shot variant for larger vectors (reduce-scatter by peer LOADS + all-gather by peer STORES): every rank publishes
+// its vector in its own buffer, reduces ONE chunk of the index range over all ranks' published vectors (fixed rank order)
+// and stores that chunk of the result into every rank's result area: 2 x (world-1)/world of the payload crosses NVLink per
+// GPU instead of (world-1) x.  Buffer: header | in[2 parities][slot] | res[2 parities][slot].
+template <typename T>
+__global__ void __launch_bounds__(kThreads) allreduce2_kernel(tdyn_comm_t comm, T* __restrict__ vec, int64_t n, int64_t slot_bytes) {
+    const unsigned int seq = comm.epoch;
+    const int par = seq & 1;
+    const int world = comm.world, rank = comm.rank;
+    __shared__ bool last, ok;
+    auto in_of = [&](int r) { return reinterpret_cast<T*>((uint8_t*)comm.peer[r] + kHeader + (size_t)par * slot_bytes); };
+    auto res_of = [&](int r) { return reinterpret_cast<T*>((uint8_t*)comm.peer[r] + kHeader + (size_t)(2 + par) * slot_bytes); };
+    Header* mine = reinterpret_cast<Header*>(comm.peer[rank]);
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x, stride = (int64_t)gridDim.x * kThreads;
+    // ---- 1. publish the own vector (local copy), then tell every peer
+    T* my_in = in_of(rank);
+    for (int64_t i = tid; i < n; i += stride) my_in[i] = vec[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&mine->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        mine->ticket = 0u;
+        __threadfence_system();
+        for (int r = 0; r < world; ++r)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&reinterpret_cast<Header*>(comm.peer[r])->flag[par][rank]), "r"(seq) : "memory");
+    }
+    if (threadIdx.x == 0) ok = wait_flags(mine->flag[par], world, seq);
+    __syncthreads();
+    if (ok) {
+        // ---- 2. reduce the own chunk over all ranks (peer loads, rank order), scatter the result to every rank
+        const int64_t chunk = ((n + world - 1) / world + 3) & ~(int64_t)3;
+        const int64_t lo = chunk * rank, hi = lo + chunk < n ? lo + chunk : n;
+        for (int64_t i = lo + tid; i < hi; i += stride) {
+            T v[TDYN_MAX_PEERS];
+#pragma unroll
+            for (int q = 0; q < TDYN_MAX_PEERS; ++q)          // all peer loads in flight before the first add
+                if (q < world) v[q] = *(volatile const T*)(in_of(q) + i);
+            T sv = v[0];
+#pragma unroll
+            for (int q = 1; q < TDYN_MAX_PEERS; ++q)
+                if (q < world) sv += v[q];
+            for (int r = 0; r < world; ++r) res_of(r)[i] = sv;
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&mine->ticket2, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        mine->ticket2 = 0u;
+        __threadfence_system();
+        for (int r = 0; r < world; ++r)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&reinterpret_cast<Header*>(comm.peer[r])->flag2[par][rank]), "r"(seq) : "memory");
+    }
+    // ---- 3. wait for every rank's chunk, copy the result out
+    if (threadIdx.x == 0) ok = ok && wait_flags(mine->flag2[par], world, seq);
+    __syncthreads();
+    if (!ok) {
+        if (threadIdx.x == 0) mine->error = 1u;
+        for (int64_t i = tid; i < n; i += stride) vec[i] = (T)__int_as_float(0x7fc00000);
+        return;
+    }
+    const T* my_res = res_of(rank);
+    for (int64_t i = tid; i < n; i += stride) vec[i] = *(volatile const T*)(my_res + i);
+}
+
 }  // namespace peer
 }  // namespace tdyn
 
@@ -92,6 +174,7 @@ extern "C" {
 
 int64_t tdyn_peer_allreduce_buffer_bytes(int64_t slot_bytes) {
     if (slot_bytes <= 0) return 0;
+    // one-shot layout (2 parities x TDYN_MAX_PEERS slots) covers the two-shot layout (2 in + 2 result areas) as well
     return (int64_t)peer::kHeader + 2 * (int64_t)TDYN_MAX_PEERS * ((slot_bytes + 15) / 16 * 16);
 }
 
@@ -105,7 +188,11 @@ int tdyn_peer_allreduce(const tdyn_comm_t* comm, void* vec, int64_t n, int is_do
     int64_t blocks = (n + peer::kThreads - 1) / peer::kThreads;
     if (blocks > peer::kMaxBlocks) blocks = peer::kMaxBlocks;
     cudaStream_t st = (cudaStream_t)stream;
-    if (is_double) peer::allreduce_kernel<double><<<(int)blocks, peer::kThreads, 0, st>>>(*comm, (double*)vec, n, slot_bytes);
+    const bool two_shot = comm->world > 2 && n * (is_double ? 8 : 4) > 32768;      // large payloads: 2(w-1)/w instead of (w-1) x the bytes
+    if (two_shot) {
+        if (is_double) peer::allreduce2_kernel<double><<<(int)blocks, peer::kThreads, 0, st>>>(*comm, (double*)vec, n, slot_bytes);
+        else peer::allreduce2_kernel<float><<<(int)blocks, peer::kThreads, 0, st>>>(*comm, (float*)vec, n, slot_bytes);
+    } else if (is_double) peer::allreduce_kernel<double><<<(int)blocks, peer::kThreads, 0, st>>>(*comm, (double*)vec, n, slot_bytes);
     else peer::allreduce_kernel<float><<<(int)blocks, peer::kThreads, 0, st>>>(*comm, (float*)vec, n, slot_bytes);
     TDYN_CHECK_CUDA(cudaGetLastError());
     return 0;
