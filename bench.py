@@ -367,10 +367,10 @@ def sharded_configs(dev, rank, world, iters=3):
     net3 = nn.Sequential(nn.Linear(128, 1024), nn.Tanh(), nn.Linear(1024, 128)).to(dev)
     kw3 = dict(solver="tsit5", sensitivity="interpolated_adjoint")
     coll3 = (f"batch rows x{world}; per attempted step an all-reduce(SUM) of 4 fp64 (global RMS error norm: sum of squares + "
-             "counts) and per adjoint stage an all-reduce(SUM) of d(mu)/dt (263 296 fp32: mu sits inside the interpolated "
-             "adjoint's norm), both by tdyn_peer_allreduce = ONE kernel per GPU that all-gathers by direct NVLink peer "
-             "stores into every rank's exchange buffer, releases per-rank flags and adds in rank order (deterministic, no "
-             "NCCL call); one gradient all-reduce(SUM) per iteration through NCCL")
+             "counts) by tdyn_peer_allreduce = ONE kernel per GPU that all-gathers by direct NVLink peer stores into every "
+             "rank's exchange buffer, releases per-rank flags and adds in rank order (deterministic, no NCCL call); per "
+             "adjoint stage an NCCL all-reduce(SUM) of d(mu)/dt (263 296 fp32: mu sits inside the interpolated adjoint's "
+             "norm; the NVSwitch reduces it faster than peer stores do); one gradient all-reduce(SUM) per iteration (NCCL)")
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     rows = 262144 // world
     out["c3_strong"] = training(net3, torch.randn(rows, 128, generator=g, device=dev), 262144, kw3,

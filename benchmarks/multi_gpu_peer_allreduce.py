@@ -23,6 +23,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     from torchdyn_b200 import distributed as tdist
     tdist.enable()
+    tdist.PEER_MAX_BYTES = 1 << 30          # measure the peer kernels at every size (the library sends > 32 KB to NCCL)
     out = {"world": world}
     for label, n, dtype in (("dmu_263296_f32", 263296, torch.float32), ("sums_4_f64", 4, torch.float64), ("odd_100003_f32", 100003, torch.float32)):
         g = torch.Generator(device=dev).manual_seed(7 + rank)

@@ -98,6 +98,13 @@ __global__ void __launch_bounds__(kThreads) allreduce_kernel(tdyn_comm_t comm, T
     }
 }
 
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 ld_vol4(const float4* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 // Two-shot variant for larger vectors (reduce-scatter by peer LOADS + all-gather by peer STORES): every rank publishes
 // its vector in its own buffer, reduces ONE chunk of the index range over all ranks' published vectors (fixed rank order)
 // and stores that chunk of the result into every rank's result area: 2 x (world-1)/world of the payload crosses NVLink per
@@ -112,9 +119,13 @@ __global__ void __launch_bounds__(kThreads) allreduce2_kernel(tdyn_comm_t comm, 
     auto res_of = [&](int r) { return reinterpret_cast<T*>((uint8_t*)comm.peer[r] + kHeader + (size_t)(2 + par) * slot_bytes); };
     Header* mine = reinterpret_cast<Header*>(comm.peer[rank]);
     const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x, stride = (int64_t)gridDim.x * kThreads;
+    // (fp32 vectors whose address is 16-byte aligned move as float4: 16-byte NVLink transactions)
+    const bool v4 = sizeof(T) == 4 && (((uintptr_t)vec) & 15) == 0;
+    const int64_t n4 = v4 ? n >> 2 : 0;
     // ---- 1. publish the own vector (local copy), then tell every peer
     T* my_in = in_of(rank);
-    for (int64_t i = tid; i < n; i += stride) my_in[i] = vec[i];
+    for (int64_t i = tid; i < n4; i += stride) reinterpret_cast<float4*>(my_in)[i] = reinterpret_cast<const float4*>(vec)[i];
+    for (int64_t i = 4 * n4 + tid; i < n; i += stride) my_in[i] = vec[i];
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) last = atomicAdd(&mine->ticket, 1u) == gridDim.x - 1;
@@ -131,7 +142,19 @@ __global__ void __launch_bounds__(kThreads) allreduce2_kernel(tdyn_comm_t comm, 
         // ---- 2. reduce the own chunk over all ranks (peer loads, rank order), scatter the result to every rank
         const int64_t chunk = ((n + world - 1) / world + 3) & ~(int64_t)3;
         const int64_t lo = chunk * rank, hi = lo + chunk < n ? lo + chunk : n;
-        for (int64_t i = lo + tid; i < hi; i += stride) {
+        const int64_t hi4 = v4 ? (hi > lo ? lo + ((hi - lo) & ~(int64_t)3) : lo) : lo;       // chunk starts are multiples of 4
+        for (int64_t i = (lo >> 2) + tid; i < (hi4 >> 2); i += stride) {
+            float4 v[TDYN_MAX_PEERS];
+#pragma unroll
+            for (int q = 0; q < TDYN_MAX_PEERS; ++q)
+                if (q < world) v[q] = ld_vol4(reinterpret_cast<const float4*>(in_of(q)) + i);
+            float4 sv = v[0];
+#pragma unroll
+            for (int q = 1; q < TDYN_MAX_PEERS; ++q)
+                if (q < world) sv = add4(sv, v[q]);
+            for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(res_of(r))[i] = sv;
+        }
+        for (int64_t i = hi4 + tid; i < hi; i += stride) {
             T v[TDYN_MAX_PEERS];
 #pragma unroll
             for (int q = 0; q < TDYN_MAX_PEERS; ++q)          // all peer loads in flight before the first add
@@ -162,7 +185,8 @@ __global__ void __launch_bounds__(kThreads) allreduce2_kernel(tdyn_comm_t comm, 
         return;
     }
     const T* my_res = res_of(rank);
-    for (int64_t i = tid; i < n; i += stride) vec[i] = *(volatile const T*)(my_res + i);
+    for (int64_t i = tid; i < n4; i += stride) reinterpret_cast<float4*>(vec)[i] = ld_vol4(reinterpret_cast<const float4*>(my_res) + i);
+    for (int64_t i = 4 * n4 + tid; i < n; i += stride) vec[i] = *(volatile const T*)(my_res + i);
 }
 
 }  // namespace peer

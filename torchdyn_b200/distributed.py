@@ -22,6 +22,9 @@ _state = {"enabled": False, "group": None, "symm": None, "epoch": 0, "symm_faile
 _traffic = {"calls": 0, "bytes": 0, "peer_calls": 0, "peer_bytes": 0}   # collectives issued by this module on this rank
                                                                           # (NCCL calls / in-kernel NVLink exchanges)
 PEER_ALLREDUCE = True     # all-reduce small vectors inside one kernel per GPU over peer-mapped memory (False: NCCL)
+PEER_MAX_BYTES = 32768    # larger payloads go to NCCL: measured on 4 / 8 B200 (benchmarks/multi_gpu_peer_allreduce.py), 4 doubles
+                          # take 15 / 25 us in the peer kernel vs 19 / 34 us in NCCL, but 1 MB takes 37 / 59 us vs 20 / 29 us
+                          # (NCCL reduces inside the NVSwitch; the peer kernel's flag handshakes cost ~15 us per phase)
 
 
 def traffic(reset: bool = False):
@@ -141,6 +144,8 @@ def _peer_allreduce_(t: torch.Tensor) -> bool:
     import torch.distributed as dist
     from . import _lib
     nbytes = t.numel() * t.element_size()
+    if nbytes > PEER_MAX_BYTES:
+        return False
     ar = _state.get("ar")
     if ar is None or nbytes > ar["slot_bytes"]:
         try:
