@@ -35,7 +35,7 @@ extern "C" {
 #define TDYN_API
 #endif
 
-#define TDYN_ABI_VERSION 13
+#define TDYN_ABI_VERSION 14
 #define TDYN_MAX_STAGES 7
 #define TDYN_MAX_PEERS 8
 
@@ -199,6 +199,15 @@ TDYN_API int tdyn_mlp_tc_stage(const tdyn_mlp_t* mlp, const void* wsplit, float*
  * activations for the VJP); `scale` folds the negation of the reversed-time field. */
 TDYN_API int tdyn_mlp_tc_forward_save(const tdyn_mlp_t* mlp, const void* wsplit, float* out, const float* x, float scale,
                                       float* a1, float* a2, int64_t rows, void* stream);
+
+/* K2, input-gradient chain of the same MLP class in one launch (the input half of the VJP `grad(dx, x, -lambda)`,
+ * numerics/sensitivity.py:62-66): with the TRANSPOSED network `mlp_t` (w[0] = W3^T [256,32], w[1] = W2^T [256,256],
+ * w[2] = W1^T [32,256], zero biases; `wsplit_t` = its prepared image)
+ *   d2 = (g W3) * act'(a2),  d1 = (d2 W2) * act'(a1),  out = scale * (d1 W1)
+ * where a1 / a2 are the hidden activations saved by tdyn_mlp_tc_forward_save; d2 / d1 ([rows, 256]) are written out for
+ * the parameter gradients (tdyn_wgrad_tc). */
+TDYN_API int tdyn_mlp_tc_dgrad(const tdyn_mlp_t* mlp_t, const void* wsplit_t, float* out, const float* g, float scale,
+                               const float* a2, const float* a1, float* d2, float* d1, int64_t rows, void* stream);
 
 /* K2 (persistent form). A whole FIXED-STEP solve of the same MLP class -- the loop of numerics/odeint.py:411-445 around
  * RungeKutta4.step / Euler.step / Midpoint.step (numerics/solvers/ode.py:61-104) -- in ONE launch: every CTA walks

@@ -303,6 +303,17 @@ class CudaKernels:
         _lib.check(rc, "tdyn_mlp_tc_forward_save")
         _launches += 1
 
+    def mlp_tc_dgrad(self, desc_t, img_t: Tensor, out: Tensor, g: Tensor, scale: float, a2: Tensor, a1: Tensor, d2: Tensor,
+                     d1: Tensor, flops_per_row: float):
+        """Input-gradient chain of the 32-256-256-32 class in one launch (tdyn_mlp_tc_dgrad); d2 / d1 feed the wgrads."""
+        global _launches
+        rows = g.numel() // 32
+        with _Timed("mlp_tc_stage", flops_per_row * rows):
+            rc = self.lib.tdyn_mlp_tc_dgrad(C.byref(desc_t), img_t.data_ptr(), out.data_ptr(), g.data_ptr(), float(scale),
+                                            a2.data_ptr(), a1.data_ptr(), d2.data_ptr(), d1.data_ptr(), rows, self._stream())
+        _lib.check(rc, "tdyn_mlp_tc_dgrad")
+        _launches += 1
+
     def mlp_tc_solve_supported(self, desc, rows: int) -> bool:
         return bool(self.lib.tdyn_mlp_tc_solve_supported(C.byref(desc), int(rows)))
 

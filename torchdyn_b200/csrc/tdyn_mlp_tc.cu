@@ -87,6 +87,7 @@ struct Params {
     float* act_out[2];         // stage mode only: the hidden activations a1, a2 ([rows][256]) are also written here (the
                                // adjoint's input / parameter gradients need them), or NULL
     float out_scale;           // k_out = out_scale * f(y)  (1 except for the reversed-time field of an adjoint)
+    const float* dact_in[2];   // dgrad variant: saved forward activations whose act' multiplies epilogue 0 (a2) / 1 (a1)
     int64_t rows; int num_tiles; int act;
 };
 
@@ -274,9 +275,20 @@ __device__ __forceinline__ void prologue(const Params& P, const Item& it, bool f
     fence_proxy_async();
 }
 
-// SAVE: also write the hidden activations (and scale the output) -- the adjoint's forward half; a separate instantiation so
-// that the integration kernels carry none of it (registers are at the limit of 576 threads per SM)
-template <int ACT, bool SAVE>
+// VAR 1 (save): also write the hidden activations (and scale the output) -- the adjoint's forward half.
+// VAR 2 (dgrad): the INPUT-GRADIENT chain of the same MLP, which has the forward's shape with transposed weights:
+//   delta2 = (g W3) * act'(a2),  delta1 = (delta2 W2) * act'(a1),  out = scale * (delta1 W1)      (32 -> 256 -> 256 -> 32)
+// -- the "activation" of a hidden layer is the multiplication with act' of the saved forward activation (read from global
+// memory), no biases; delta2 / delta1 are written out for the parameter gradients.  Separate instantiations, so that the
+// integration kernels carry none of it (registers are at the limit of 576 threads per SM).
+constexpr int kVarPlain = 0, kVarSave = 1, kVarDgrad = 2;
+template <int ACT>
+__device__ __forceinline__ float dact_from_out(float a) {
+    if (ACT == TDYN_ACT_RELU) return a > 0.f ? 1.f : 0.f;
+    if (ACT == TDYN_ACT_SOFTPLUS) return -expm1f(-a);       // sigmoid(z) = 1 - exp(-softplus(z))
+    return fmaf(-a, a, 1.f);                                  // 1 - tanh^2
+}
+template <int ACT, int VAR>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_constant__ Params P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t tmem_base_slot;
@@ -430,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
         for (int t = 0; t < n_items; ++t) {
             const uint32_t tpar = t & 1;
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)tl * gridDim.x;
-            const int64_t grow_cur = SAVE ? tile * kTileM + w.row : 0;
+            const int64_t grow_cur = VAR != kVarPlain ? tile * kTileM + w.row : 0;
             const int npass = tl + 1 < my_tiles ? pass : pass + 1, ntl = tl + 1 < my_tiles ? tl + 1 : 0;   // the next item
             const int64_t ntile = (int64_t)blockIdx.x + (int64_t)ntl * gridDim.x;
             const Item nxt = (t + 1 < n_items && npass != pass) ? make_item(P, npass) : cur;
@@ -465,14 +477,27 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
                         }
                         tmem_ld8(src + (uint32_t)((j + 1) * kKB), nxt);     // prefetch next chunk
                     }
-                    const float4 b0 = *reinterpret_cast<const float4*>(bias + j * kKB);
-                    const float4 b1 = *reinterpret_cast<const float4*>(bias + j * kKB + 4);
                     float v[8];
-                    v[0] = activate_biased<ACT>(__uint_as_float(cur[0]), b0.x); v[1] = activate_biased<ACT>(__uint_as_float(cur[1]), b0.y);
-                    v[2] = activate_biased<ACT>(__uint_as_float(cur[2]), b0.z); v[3] = activate_biased<ACT>(__uint_as_float(cur[3]), b0.w);
-                    v[4] = activate_biased<ACT>(__uint_as_float(cur[4]), b1.x); v[5] = activate_biased<ACT>(__uint_as_float(cur[5]), b1.y);
-                    v[6] = activate_biased<ACT>(__uint_as_float(cur[6]), b1.z); v[7] = activate_biased<ACT>(__uint_as_float(cur[7]), b1.w);
-                    if (SAVE && grow_cur < P.rows) {
+                    if (VAR == kVarDgrad) {
+                        // delta = acc * act'(saved activation): epilogue 0 pairs with a2, epilogue 1 with a1
+                        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+                        if (grow_cur < P.rows) {
+                            const float4* sp = reinterpret_cast<const float4*>(P.dact_in[layer] + (size_t)grow_cur * kH + j * kKB + w.sub * 8);
+                            s0 = __ldg(sp); s1 = __ldg(sp + 1);
+                        }
+                        v[0] = __uint_as_float(cur[0]) * dact_from_out<ACT>(s0.x); v[1] = __uint_as_float(cur[1]) * dact_from_out<ACT>(s0.y);
+                        v[2] = __uint_as_float(cur[2]) * dact_from_out<ACT>(s0.z); v[3] = __uint_as_float(cur[3]) * dact_from_out<ACT>(s0.w);
+                        v[4] = __uint_as_float(cur[4]) * dact_from_out<ACT>(s1.x); v[5] = __uint_as_float(cur[5]) * dact_from_out<ACT>(s1.y);
+                        v[6] = __uint_as_float(cur[6]) * dact_from_out<ACT>(s1.z); v[7] = __uint_as_float(cur[7]) * dact_from_out<ACT>(s1.w);
+                    } else {
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias + j * kKB);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias + j * kKB + 4);
+                        v[0] = activate_biased<ACT>(__uint_as_float(cur[0]), b0.x); v[1] = activate_biased<ACT>(__uint_as_float(cur[1]), b0.y);
+                        v[2] = activate_biased<ACT>(__uint_as_float(cur[2]), b0.z); v[3] = activate_biased<ACT>(__uint_as_float(cur[3]), b0.w);
+                        v[4] = activate_biased<ACT>(__uint_as_float(cur[4]), b1.x); v[5] = activate_biased<ACT>(__uint_as_float(cur[5]), b1.y);
+                        v[6] = activate_biased<ACT>(__uint_as_float(cur[6]), b1.z); v[7] = activate_biased<ACT>(__uint_as_float(cur[7]), b1.w);
+                    }
+                    if (VAR != kVarPlain && grow_cur < P.rows) {
                         float4* dst = reinterpret_cast<float4*>(P.act_out[layer] + (size_t)grow_cur * kH + j * kKB + w.sub * 8);
                         dst[0] = make_float4(v[0], v[1], v[2], v[3]);
                         dst[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -507,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const float4 bq = *reinterpret_cast<const float4*>(smem + kSmemBias + (2 * kH + w.sub * 8 + 4 * i) * 4);
-                    const float sc = SAVE ? P.out_scale : 1.f;
+                    const float sc = VAR != kVarPlain ? P.out_scale : 1.f;
                     o[4 * i] = sc * (__uint_as_float(ro[4 * i]) + bq.x); o[4 * i + 1] = sc * (__uint_as_float(ro[4 * i + 1]) + bq.y);
                     o[4 * i + 2] = sc * (__uint_as_float(ro[4 * i + 2]) + bq.z); o[4 * i + 3] = sc * (__uint_as_float(ro[4 * i + 3]) + bq.w);
                     reinterpret_cast<float4*>(k_out + goff)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
@@ -599,24 +624,25 @@ __global__ void prepare_weights_kernel(const float* __restrict__ w1, const float
 
 using namespace tdyn;
 
-template <bool SAVE>
+template <int VAR>
 static int launch_tc_t(const tdyn_mlp_t* m, tc::Params& P, int grid, cudaStream_t st) {
     static thread_local unsigned long long seen = 0;
     if (first_use_on_device(seen)) {
-        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_TANH, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
-        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_SOFTPLUS, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
-        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_RELU, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
+        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_TANH, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
+        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_SOFTPLUS, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
+        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_RELU, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
     }
     switch (m->act) {
-        case TDYN_ACT_TANH: tc::mlp_tc_stage_kernel<TDYN_ACT_TANH, SAVE><<<grid, tc::kThreads, tc::kSmemTotal, st>>>(P); break;
-        case TDYN_ACT_SOFTPLUS: tc::mlp_tc_stage_kernel<TDYN_ACT_SOFTPLUS, SAVE><<<grid, tc::kThreads, tc::kSmemTotal, st>>>(P); break;
-        default: tc::mlp_tc_stage_kernel<TDYN_ACT_RELU, SAVE><<<grid, tc::kThreads, tc::kSmemTotal, st>>>(P); break;
+        case TDYN_ACT_TANH: tc::mlp_tc_stage_kernel<TDYN_ACT_TANH, VAR><<<grid, tc::kThreads, tc::kSmemTotal, st>>>(P); break;
+        case TDYN_ACT_SOFTPLUS: tc::mlp_tc_stage_kernel<TDYN_ACT_SOFTPLUS, VAR><<<grid, tc::kThreads, tc::kSmemTotal, st>>>(P); break;
+        default: tc::mlp_tc_stage_kernel<TDYN_ACT_RELU, VAR><<<grid, tc::kThreads, tc::kSmemTotal, st>>>(P); break;
     }
     TDYN_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 static int launch_tc(const tdyn_mlp_t* m, tc::Params& P, int grid, cudaStream_t st) {
-    return P.act_out[0] ? launch_tc_t<true>(m, P, grid, st) : launch_tc_t<false>(m, P, grid, st);
+    if (P.dact_in[0]) return launch_tc_t<tc::kVarDgrad>(m, P, grid, st);
+    return P.act_out[0] ? launch_tc_t<tc::kVarSave>(m, P, grid, st) : launch_tc_t<tc::kVarPlain>(m, P, grid, st);
 }
 
 extern "C" {
@@ -689,6 +715,28 @@ int tdyn_mlp_tc_forward_save(const tdyn_mlp_t* m, const void* wsplit, float* out
     P.act = m->act;
     const int grid = P.num_tiles < kNumSMs ? P.num_tiles : kNumSMs;
     return launch_tc(m, P, grid, (cudaStream_t)stream);
+}
+
+int tdyn_mlp_tc_dgrad(const tdyn_mlp_t* mt, const void* wsplit_t, float* out, const float* g, float scale, const float* a2,
+                      const float* a1, float* d2, float* d1, int64_t rows, void* stream) {
+    TDYN_REQUIRE(tdyn_mlp_tc_supported(mt), "tdyn_mlp_tc_dgrad: unsupported MLP shape (need 32-256-256-32)");
+    TDYN_REQUIRE(wsplit_t && out && g && a1 && a2 && d1 && d2, "tdyn_mlp_tc_dgrad: null argument");
+    TDYN_REQUIRE((((uintptr_t)g | (uintptr_t)out | (uintptr_t)a1 | (uintptr_t)a2 | (uintptr_t)d1 | (uintptr_t)d2) & 15) == 0,
+                 "tdyn_mlp_tc_dgrad: pointers must be 16-byte aligned");
+    if (rows <= 0) return 0;
+    tc::Params P{};
+    P.wimg = (const uint8_t*)wsplit_t;
+    P.b1 = mt->b[0]; P.b2 = mt->b[1]; P.b3 = mt->b[2];        // zero vectors (the chain has no biases)
+    P.k_out0 = out; P.x_in = g; P.dt0 = 0.f;
+    P.st[0].n_k = 0; P.st[0].mode = TDYN_MODE_CHAIN;
+    P.n_stage = 1; P.n_steps = 1; P.solve = 0; P.out_scale = scale;
+    P.act_out[0] = d2; P.act_out[1] = d1;
+    P.dact_in[0] = a2; P.dact_in[1] = a1;
+    P.rows = rows;
+    P.num_tiles = (int)((rows + tc::kTileM - 1) / tc::kTileM);
+    P.act = mt->act;
+    const int grid = P.num_tiles < kNumSMs ? P.num_tiles : kNumSMs;
+    return launch_tc(mt, P, grid, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------- whole fixed-step solve

@@ -178,6 +178,23 @@ class FusedMLP:
             self._wide_imgs = [(kern.lin_tc_prepare(m.weight, False), kern.lin_tc_prepare(m.weight, True)) for m in self.linears]
         return self._wide_imgs
 
+    def tc_transposed(self, kern):
+        """(descriptor, prepared image) of the TRANSPOSED 32-256-256-32 network: the input-gradient chain of the fused
+        stage kernel (``tdyn_mlp_tc_dgrad``); rebuilt after a parameter update."""
+        if self.__dict__.get("_tc_t") is None:
+            wts = [m.weight.detach().t().contiguous() for m in reversed(self.linears)]      # W3^T, W2^T, W1^T
+            zeros = [torch.zeros(w.shape[0], dtype=torch.float32, device=w.device) for w in wts]
+            d = _lib.MlpDesc()
+            d.n_layers = len(wts)
+            for i, v in enumerate(reversed(self.dims)):
+                d.dims[i] = v
+            d.act = self.act
+            for i, (w, b) in enumerate(zip(wts, zeros)):
+                d.w[i] = w.data_ptr()
+                d.b[i] = b.data_ptr()
+            self._tc_t = (d, kern.mlp_tc_prepare(d), wts, zeros)
+        return self._tc_t[0], self._tc_t[1]
+
     def scratch(self, key, make):
         """Per-network cache of solver scratch buffers (stage storage, ping-pong state, status, trace): they are
         consumed within the call, so they can be reused by the next one (stream-ordered)."""
@@ -224,7 +241,7 @@ class FusedMLP:
         for i, m in enumerate(self.linears):
             d.w[i] = m.weight.data_ptr()
             d.b[i] = m.bias.data_ptr()
-        self._key, self._desc, self._img, self._wide_imgs = key, d, None, None
+        self._key, self._desc, self._img, self._wide_imgs, self._tc_t = key, d, None, None, None
         self._tc_ok = kern.mlp_tc_supported(d)
         self._ffma_ok = kern.mlp_ffma_supported(d)
         self._wide_ok = not self._ffma_ok and all(kern.lin_tc_supported(o, i) and kern.lin_tc_supported(i, o)
@@ -348,6 +365,23 @@ class FusedWideAdjoint:
         for i, o in zip(dims[:-1], dims[1:]):
             offs.append(o_)
             o_ += o * i + o
+        if fm.ready(kern) and len(saved) == 2:
+            # the 32-256-256-32 class: the whole input-gradient chain in ONE launch of the fused stage kernel on the
+            # transposed network; its hidden cotangents d2, d1 and lam feed the three parameter-gradient contractions
+            a1, a2 = saved
+            d2, d1 = torch.empty_like(a2), torch.empty_like(a1)
+            dl = dlam_out if dlam_out.data_ptr() % 16 == 0 else torch.empty(rows, dims[0], dtype=torch.float32, device=a1.device)
+            desc_t, img_t = fm.tc_transposed(kern)
+            kern.mlp_tc_dgrad(desc_t, img_t, dl, lam_flat, -sign, a2, a1, d2, d1, fm.flops_per_row)
+            if dl is not dlam_out:
+                dlam_out.view(-1).copy_(dl.view(-1))
+            for l, (gl, inp) in enumerate(((d1, x_flat), (d2, a1), (lam_flat, a2))):
+                i, o = dims[l], dims[l + 1]
+                ws = fm.scratch(("wgrad", l, rows, x_flat.device.index), lambda: kern.wgrad_tc_workspace(o, i, rows))
+                kern.wgrad_tc(gl, o, inp, i, dmu_out[offs[l]:offs[l] + o * i], dmu_out[offs[l] + o * i:offs[l] + o * i + o], -sign, ws, rows)
+            for c in self.counters:
+                c.nfe += 1
+            return
         g = lam_flat
         for l in range(len(fm.linears) - 1, -1, -1):
             i, o = dims[l], dims[l + 1]
