@@ -45,7 +45,7 @@ ROWS_PER_GPU = 1 << 20
 CPU_SAMPLE_ROWS = 16384
 METRIC = "sample-NFE/sec"
 FLOPS_PER_SAMPLE_NFE = 2 * sum(a * b for a, b in zip(DIMS[:-1], DIMS[1:]))     # 163 840
-TENSOR_KERNELS = ("mlp_tc_stage", "mlp_tc_solve", "lin_tc", "wgrad_tc")
+TENSOR_KERNELS = ("mlp_tc_stage", "mlp_tc_solve", "mlp_tc_adaptive", "lin_tc", "wgrad_tc")
 FFMA_KERNELS = ("mlp_solve", "mlp_solve_interp", "mlp_ffma_forward", "mlp_ffma_adjoint", "cnf_ffma_forward", "cnf_ffma_adjoint")
 
 

@@ -35,7 +35,7 @@ extern "C" {
 #define TDYN_API
 #endif
 
-#define TDYN_ABI_VERSION 14
+#define TDYN_ABI_VERSION 15
 #define TDYN_MAX_STAGES 7
 #define TDYN_MAX_PEERS 8
 
@@ -223,6 +223,26 @@ TDYN_API int64_t tdyn_mlp_tc_solve_workspace_bytes(int n_steps, int n_stages);
 TDYN_API int tdyn_mlp_tc_solve_fixed(const tdyn_mlp_t* mlp, const void* wsplit, const tdyn_rk_plan_t* plan, const float* x_in,
                                      float* xw, float* k, float* out, const float* dts, const int* save_slot, int n_steps,
                                      int64_t rows, void* workspace, void* stream);
+
+/* K2 (persistent ADAPTIVE form).  A whole adaptive `odeint` call of the same MLP class -- numerics/odeint.py:29-91 + :326-408
+ * around DormandPrince45.step / Tsitouras45.step (numerics/solvers/ode.py:145-178) -- in ONE cooperative launch of the
+ * tensor-core stage kernel: k1 = f(x0) and init_step (numerics/utils.py:37-54; skipped when dt0 > 0: then k[0] must hold
+ * k1 = sign*f(x0) and dt0 is the first step size), then per attempted step the stages 2..7 on the tensor cores (stage
+ * combination in the prologue), x_new = x + dt*(sum bsol_j k_j), err = dt*(sum berr_j k_j), the scaled sum of squares
+ * (odeint.py:365-372) reduced across the grid by ONE grid barrier, and the fp32 step controller with the checkpoint
+ * handling of odeint.py:352-401 (accept / reject, FSAL by swapping the roles of two stage buffers, adapt_step of
+ * numerics/utils.py:57-63), computed identically by one thread of every CTA.  Rows are independent and every thread
+ * re-reads only what it wrote itself: the error norm is the only grid-wide exchange.
+ * `t_span`: HOST array of 2..1024 increasing times (already negated for a reversed span; `sign` = -1 then: every stage
+ * derivative is sign*f, except init_step's trial evaluation, as in the reference).  x0 [rows*32] holds the initial state
+ * on entry; x0 / x1 ping-pong, status[5] tells which one holds the final state.  `k`: 7 stage buffers of rows*32 floats.
+ * out [out_cap][rows*32], t_out [out_cap]: slot 0 = the initial state.  status (device, 6 ints), trace (device,
+ * optional): as for tdyn_mlp_solve.  workspace: tdyn_mlp_tc_adaptive_workspace_bytes() bytes of device memory. */
+TDYN_API int64_t tdyn_mlp_tc_adaptive_workspace_bytes(void);
+TDYN_API int tdyn_mlp_tc_solve_adaptive(const tdyn_mlp_t* mlp, const void* wsplit, const tdyn_rk_plan_t* plan, float sign,
+                                        float atol, float rtol, const float* t_span, int n_t, int return_all, float dt0,
+                                        float* x0, float* x1, float* k, float* out, float* t_out, int out_cap, void* workspace,
+                                        int* status, float* trace, int trace_cap, int64_t rows, int max_steps, void* stream);
 
 /* ---- Layer-wise tensor-core kernels for wide MLP vector fields (any widths that are multiples of 32; output widths
  * <= 128 or multiples of 128, <= 2048): BASELINE configs[2] (128-1024-128) and the adjoint of the 32-256-256-32 class.

@@ -248,6 +248,15 @@ def functional_cases():
                                  kw=dict(solver="tsit5", atol=1e-4, rtol=1e-4, return_all_eval=True))
     cases["act_dopri5_4th_fn"] = dict(dims=[4, 64, 4], act="tanh", seed=5, gain=4.0, x=xa, t_span=torch.linspace(0, 4, 9),
                                       kw=dict(solver="dopri5", atol=1e-4, rtol=1e-4, interpolator="4th"))
+    # ACTIVE controller on the persistent tensor-core integrator (tdyn_mlp_tc_solve_adaptive): the config-2 network class,
+    # gain 6 (ratios 0.1-0.7, rejections at 1.03-15), more than two 128-row tiles (ragged last tile), interior output times, all accepted steps returned
+    torch.manual_seed(18)
+    xw = torch.randn(300, 32)
+    cases["act_w256x2_tsit5_fn"] = dict(dims=[32, 256, 256, 32], act="tanh", seed=16, gain=6.0, x=xw,
+                                        t_span=torch.tensor([0.0, 1.0, 2.0]),
+                                        kw=dict(solver="tsit5", atol=1e-2, rtol=1e-2, return_all_eval=True))
+    cases["act_w256x2_dopri5_fn"] = dict(dims=[32, 256, 256, 32], act="tanh", seed=16, gain=6.0, x=torch.cat([xw, xw[:33] * 0.5]),
+                                         t_span=torch.linspace(0, 2, 4), kw=dict(solver="dopri5", atol=1e-3, rtol=1e-3))
     cases["fn_rk4_save_at"] = dict(dims=[3, 16, 3], act="tanh", seed=7, x=x, t_span=torch.linspace(0, 1, 21),
                                    kw=dict(solver="rk4"), save_last=True)
     # cfg 2 reduced: rk4 100 steps, MLP 32-256-256-32, B=64, forward only, save last

@@ -115,7 +115,7 @@ NEURALODE_CASES = ["c1_moons_dopri5_adjoint", "c1_moons_tsit5_interp", "mlp3_tsi
                    "ho_order2_dopri5_adjoint", "dc_depthcat_tsit5_autograd", "dc_depthcat_dopri5_interp"]
 FUNCTIONAL_CASES = ["fn_euler_tspan10", "fn_midpoint_tspan10", "fn_rk4_tspan10", "fn_dopri5_tspan10", "fn_tsit5_tspan10",
                     "fn_dopri5_4th_tspan10", "fn_dopri5_reversed", "fn_tsit5_all_eval", "fn_rk4_save_at", "c2r_rk4_100",
-                    "act_tsit5_fn", "act_dopri5_4th_fn"]
+                    "act_tsit5_fn", "act_dopri5_4th_fn", "act_w256x2_tsit5_fn", "act_w256x2_dopri5_fn"]
 # fixtures whose controller is ACTIVE (error ratios ~0.2-0.9, rejections): the GPU must reproduce the step sequence
 ACTIVE_CASES = ["act_dopri5_adjoint", "act_tsit5_interp", "act_tsit5_fn", "act_dopri5_4th_fn",
                 "act_w256x2_dopri5_adjoint", "act_w1024_tsit5_interp"]

@@ -814,6 +814,93 @@ def test_mlp_tc_solve_fixed_is_bit_identical_to_the_per_stage_kernel(solver, row
     assert torch.equal(res[("all", True)][1][-1], res[("last", True)][1][-1])
 
 
+@pytest.mark.parametrize("name", ["act_w256x2_tsit5_fn", "act_w256x2_dopri5_fn"])
+def test_adaptive_tc_integrator_reproduces_the_reference_step_sequence(name):
+    """The one-launch adaptive integrator of the 32-256-256-32 class (tdyn_mlp_tc_solve_adaptive: k1, init_step, stages on
+    the tensor cores, error norm by one grid barrier, controller in the kernel) against the EXECUTED REFERENCE on an
+    active controller (ratios 0.1-0.7, rejections at 1.03-7.4, interior output times, ragged last tile): the attempted-step
+    count, accept / reject pattern and step times must pass the STRICT comparison; the result must be bit-identical to
+    the host-driven loop over the same stage kernel.  These dynamics are chaotic on purpose (gain 6: a perturbation of
+    2e-5 after the first step grows to 0.1 at t = 2), so the STATES are held to (i) 1e-5 of the state scale where nothing
+    has been amplified yet and (ii) 10x the deviation that torch's own fp32 evaluation of f on this GPU has from the CPU
+    reference at the same output time (the split-precision tensor-core evaluation carries 2-4x the rounding error of an
+    fp32 FFMA evaluation)."""
+    from torchdyn_b200 import fused
+    from parity_helpers import LAST_STRICT_FLAGS, assert_traces
+    fx = load_golden(name)
+    net = build_mlp(fx["dims"], fx["act"], fx["params"], DEV)
+    ref = fx["ref"]
+    t_eval, sol, traces = run_functional_case(fx, DEV, f=fused.MLPField(net))
+    assert "tdyn_mlp_tc_solve_adaptive" in (fused.last_used() or ""), fused.last_used()
+    assert_traces(ref["traces"], traces)
+    assert all(LAST_STRICT_FLAGS) and len(LAST_STRICT_FLAGS) == 1, LAST_STRICT_FLAGS
+    r, g = ref["traces"][0], traces[0]
+    assert len(r["t"]) == len(g["t"]) and [x <= 1 for x in r["ratio"]] == g["accept"]
+    assert "dopri5" in name or not all(g["accept"]), "the tsit5 fixture contains rejected steps"
+    assert sol.shape == ref["sol"].shape
+    np.testing.assert_allclose(t_eval.cpu().numpy(), ref["t_eval"].numpy(), rtol=2e-4, atol=1e-7)
+    fused.ADAPTIVE_TC = False
+    try:
+        t_host, sol_host, _ = run_functional_case(fx, DEV, f=fused.MLPField(net))
+    finally:
+        fused.ADAPTIVE_TC = True
+    assert "tdyn_mlp_tc_stage" in fused.last_used()
+    assert torch.equal(t_eval, t_host) and torch.equal(sol, sol_host), "one launch vs host-driven loop: not bit-identical"
+    _, sol_eager, _ = run_functional_case(fx, DEV)                   # f = torch fp32 call, generic kernels
+    rs = ref["sol"].double()
+    for i in range(len(rs)):
+        scale = float(rs[i].abs().max())
+        err = float((sol[i].double().cpu() - rs[i]).abs().max())
+        err_eager = float((sol_eager[i].double().cpu() - rs[i]).abs().max())
+        assert err <= max(10.0 * err_eager, 1e-5 * scale), (name, i, err, err_eager, scale)
+
+
+@pytest.mark.parametrize("solver,rows,ts,kw", [
+    ("dopri5", 300, [0.0, 1.0], {}),
+    ("tsit5", 1000, [0.0, 0.3, 0.35, 1.2], {}),
+    ("dopri5", 40001, [0.0, 0.5, 1.5], dict(return_all_eval=True)),
+    ("tsit5", 777, [1.0, 0.4, 0.0], {}),
+])
+def test_adaptive_tc_integrator_matches_the_host_driven_loop(solver, rows, ts, kw):
+    """tdyn_mlp_tc_solve_adaptive against the host-driven loop over the same stage kernel (one launch per stage +
+    tdyn_rk_finish + host controller): the stage arithmetic is the same, so the step sequences are identical and the
+    states agree to the last bits (the fp64 error sums are added in a different order)."""
+    import sys
+    from torchdyn_b200 import fused
+    om = sys.modules["torchdyn_b200.numerics.odeint"]
+    torch.manual_seed(21)
+    net = build_mlp([32, 256, 256, 32], "tanh").to(DEV)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(5.0)
+    x = torch.randn(rows, 32, device=DEV)
+    fld = fused.MLPField(net)
+    res = {}
+    for flag in (True, False):
+        fused.ADAPTIVE_TC = flag
+        om.TRACE_SINK = tr = []
+        fld.nfe = 0
+        try:
+            with torch.no_grad():
+                t_eval, sol = odeint(fld, x, torch.tensor(ts), solver, atol=1e-3, rtol=1e-3, **kw)
+        finally:
+            fused.ADAPTIVE_TC = True
+            om.TRACE_SINK = None
+        assert ("tdyn_mlp_tc_solve_adaptive" in fused.last_used()) == flag, fused.last_used()
+        res[flag] = (t_eval, sol, tr[0], fld.nfe)
+    (ta, sa, tra, na), (tb, sb, trb, nb) = res[True], res[False]
+    assert na == nb, (na, nb)
+    assert len(tra["t"]) == len(trb["t"]) and tra["accept"] == trb["accept"], (tra, trb)
+    assert len(tra["t"]) >= 4
+    np.testing.assert_allclose(tra["dt0"], trb["dt0"], rtol=1e-6)
+    np.testing.assert_allclose(tra["t"], trb["t"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(tra["dt"], trb["dt"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(tra["ratio"], trb["ratio"], rtol=1e-5, atol=1e-7)
+    assert ta.shape == tb.shape and sa.shape == sb.shape
+    np.testing.assert_allclose(ta.cpu().numpy(), tb.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    assert_close(sa, sb, "one-launch adaptive integrator vs host loop", rtol=2e-5, atol_scale=2e-6)
+
+
 @pytest.mark.parametrize("name", ["il_dopri5_adjoint", "il_tsit5_interp"])
 def test_integral_loss_runs_on_the_fused_adjoint(name):
     """integral_loss with both adjoints (reference sensitivity.py:67-69, 141-143): f, its VJP and the parameter gradient stay

@@ -330,6 +330,25 @@ class CudaKernels:
         _lib.check(rc, "tdyn_mlp_tc_solve_fixed")
         _launches += 1
 
+    def mlp_tc_adaptive_workspace(self) -> Tensor:
+        return torch.empty(int(self.lib.tdyn_mlp_tc_adaptive_workspace_bytes()), dtype=torch.uint8, device=self.device)
+
+    def mlp_tc_solve_adaptive(self, desc, img: Tensor, plan, sign: float, atol: float, rtol: float, t_span, return_all: bool,
+                              dt0: float, x0: Tensor, x1: Tensor, k: Tensor, out: Tensor, t_out: Tensor, out_cap: int,
+                              ws: Tensor, status: Tensor, trace: Optional[Tensor], rows: int, max_steps: int):
+        """Whole adaptive solve of the 32-256-256-32 class in one cooperative launch of the tensor-core stage kernel
+        (tdyn_mlp_tc_solve_adaptive); results are read from `status` by the caller, who also books the work."""
+        global _launches
+        with _Timed("mlp_tc_adaptive", 0.0):
+            rc = self.lib.tdyn_mlp_tc_solve_adaptive(C.byref(desc), img.data_ptr(), C.byref(plan), float(sign), float(atol),
+                                                     float(rtol), t_span.ctypes.data, t_span.size, int(return_all), float(dt0),
+                                                     x0.data_ptr(), x1.data_ptr(), k.data_ptr(), out.data_ptr(), t_out.data_ptr(),
+                                                     int(out_cap), ws.data_ptr(), status.data_ptr(), _ptr(trace),
+                                                     0 if trace is None else trace.numel(), int(rows), int(max_steps),
+                                                     self._stream())
+        _lib.check(rc, "tdyn_mlp_tc_solve_adaptive")
+        _launches += 1
+
     # ---- layer-wise tensor-core kernels for wide MLPs (tdyn_lin_tc_*, tdyn_wgrad_tc)
     def lin_tc_supported(self, n_out: int, k_in: int) -> bool:
         return bool(self.lib.tdyn_lin_tc_supported(int(n_out), int(k_in)))

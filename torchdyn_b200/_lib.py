@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdyn_b200.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 MAX_STAGES = 7
 MAX_LAYERS = 4
 MODE_CHAIN, MODE_INNER = 0, 1
@@ -95,6 +95,11 @@ SIGNATURES = {
     "tdyn_mlp_tc_solve_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "tdyn_mlp_tc_solve_fixed": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.POINTER(RkPlan), C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tdyn_mlp_tc_adaptive_workspace_bytes": (C.c_int64, []),
+    "tdyn_mlp_tc_solve_adaptive": (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.POINTER(RkPlan), C.c_float, C.c_float, C.c_float,
+                                             C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                             C.c_int64, C.c_int, C.c_void_p]),
     "tdyn_lin_tc_supported": (C.c_int, [C.c_int, C.c_int]),
     "tdyn_lin_tc_image_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "tdyn_lin_tc_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

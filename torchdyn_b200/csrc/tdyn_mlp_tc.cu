@@ -88,6 +88,16 @@ struct Params {
                                // adjoint's input / parameter gradients need them), or NULL
     float out_scale;           // k_out = out_scale * f(y)  (1 except for the reversed-time field of an adjoint)
     const float* dact_in[2];   // dgrad variant: saved forward activations whose act' multiplies epilogue 0 (a2) / 1 (a1)
+    // ---- adaptive variant (tdyn_mlp_tc_solve_adaptive): a whole dopri5 / tsit5 solve in one cooperative launch
+    float* xbuf[2];            // state ping-pong (xbuf[0] holds x0 on entry)
+    Coefs berr; int n_err;     // embedded error weights (st[kUpd] holds bsol, literal: no term dropped)
+    const float* t_span;       // device copy of the (already negated, if reversed) output times, n_t of them
+    int n_t, return_all, out_cap, max_steps, order, trace_cap;
+    float t_dt0;               // > 0: first step size given and kp[0] = k1 given; <= 0: k1 and init_step run in the kernel
+    float atol, rtol, safety, min_factor, max_factor;
+    float* t_out; int* status; float* trace;
+    unsigned int* gbar;        // grid barrier counter (zero on entry)
+    double* partials;          // [2 parities][2 sums][gridDim.x] per-CTA partial sums of squares
     int64_t rows; int num_tiles; int act;
 };
 
@@ -186,17 +196,28 @@ __device__ __forceinline__ float4 ld_f4(const float* p) { return __ldcg(reinterp
 
 // y = combine(x, k, coef) for 8 elements of this thread's row, in the reference's rounding order.  The k's are fetched in
 // groups of four with every load of a group issued before the first use (one exposed L2 round trip per group).
-__device__ __forceinline__ void combine_row8(const Params& P, int si, const float* x, float dt, size_t goff, bool valid,
-                                             float (&y)[8]) {
+// A flag that is the same in every thread, handed to the compiler as a warp-uniform value (a vote result): what is indexed
+// with it stays a constant-bank operand.  (__activemask: also called where a ragged last tile has switched lanes off.)
+__device__ __forceinline__ bool uniform_flag(bool p) { return __all_sync(__activemask(), p); }
+
+// `swapped` (adaptive variant only): FSAL without a copy -- after an accepted step the first and the last stage buffer swap
+// roles (k1 <- k_last).  Always handed over as a warp-UNIFORM value (a vote result), so that the pointer stays an indexed
+// constant-bank operand.
+__device__ __forceinline__ const float* kbuf(const Params& P, bool swapped, int j) {
+    const int last = P.n_stage - 1;
+    return P.kp[swapped ? (j == 0 ? last : (j == last ? 0 : j)) : j];
+}
+
+__device__ __forceinline__ void combine_row8(const Params& P, const StagePlan& sp, const float* x, float dt, size_t goff, bool valid,
+                                             float (&y)[8], bool kmap = false) {
     float xv[8];
-    const StagePlan& sp = P.st[si];
     const int n_k = valid ? sp.n_k : 0;
     float4 q[4][2];
     if (valid) {
         const float4 a = ld_f4(x + goff), b = ld_f4(x + goff + 4);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj)
-            if (jj < n_k) { const float* kp = P.kp[sp.kidx[jj]] + goff; q[jj][0] = ld_f4(kp); q[jj][1] = ld_f4(kp + 4); }
+            if (jj < n_k) { const float* kp = kbuf(P, kmap, sp.kidx[jj]) + goff; q[jj][0] = ld_f4(kp); q[jj][1] = ld_f4(kp + 4); }
         xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
     } else {
 #pragma unroll
@@ -215,7 +236,7 @@ __device__ __forceinline__ void combine_row8(const Params& P, int si, const floa
         if (j0 > 0) {
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
-                if (j0 + jj < n_k) { const float* kp = P.kp[sp.kidx[j0 + jj]] + goff; q[jj][0] = ld_f4(kp); q[jj][1] = ld_f4(kp + 4); }
+                if (j0 + jj < n_k) { const float* kp = kbuf(P, kmap, sp.kidx[j0 + jj]) + goff; q[jj][0] = ld_f4(kp); q[jj][1] = ld_f4(kp + 4); }
         }
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
@@ -257,22 +278,269 @@ __device__ __forceinline__ Item make_item(const Params& P, int pass) {
 __device__ __forceinline__ int plan_index(const Params& P, const Item& it, bool first_pass) {
     return !P.solve ? 0 : (it.g > 0 ? it.g : (first_pass ? kUpd + 1 : kUpd));
 }
+// Adaptive variant.  A batch is one of three PHASES: 0 = k1 = f(x0) (the empty plan st[kUpd + 1]); 1 = init_step's trial
+// evaluation f(x0 + h0*k1) (plan st[0], written to the last stage buffer); 2 = one attempted step, stages 2..s (pass p
+// evaluates stage p + 1 from plan st[p + 1]).  `slot` carries the plan index here.
+__device__ __forceinline__ Item make_item_adapt(const Params& P, int phase, int pass, float dt) {
+    Item it;
+    it.dt = dt;
+    if (phase == 2) { it.g = pass + 1; it.slot = pass + 1; }
+    else if (phase == 0) { it.g = 0; it.slot = kUpd + 1; }
+    else { it.g = P.n_stage - 1; it.slot = 0; }
+    return it;
+}
 
 // stage input of one tile -> A1 (hi/lo, swizzled); solve mode also stores it as the new state / an output
 __device__ __forceinline__ void prologue(const Params& P, const Item& it, bool first_pass, uint8_t* smem, const WorkerCtx& w,
-                                         int64_t tile) {
+                                         int64_t tile, const float* x_adaptive = nullptr, bool kmap = false) {
     const int64_t grow = tile * kTileM + w.row;
     const bool valid = grow < P.rows;
     const size_t goff = (size_t)grow * kD + w.sub * 8;
     float y[8];
     // (the very first pass of a solve copies the caller's state: no stage derivatives exist yet)
-    combine_row8(P, plan_index(P, it, first_pass), (first_pass || !P.solve) ? P.x_in : P.xw, it.dt, goff, valid, y);
-    if (valid && P.solve && it.g == 0) {
+    const float* xsrc = x_adaptive ? x_adaptive : ((first_pass || !P.solve) ? P.x_in : P.xw);
+    combine_row8(P, P.st[x_adaptive ? it.slot : plan_index(P, it, first_pass)], xsrc, it.dt, goff, valid, y, kmap);
+    if (valid && P.solve && !x_adaptive && it.g == 0) {
         store_row8(P.xw, goff, y);
         if (it.slot >= 0) store_row8(P.out + (size_t)it.slot * P.n_state, goff, y);
     }
     store_split8(smem + kSmemA1, w.row, w.sub, y);
     fence_proxy_async();
+}
+
+// adaptive variant, end of an attempted step for 8 elements of one row: x_new = x + dt*(sum bsol_j k_j), err = dt*(sum
+// berr_j k_j) in the reference's rounding (ode.py:154-155), returns the sum of the squared scaled errors
+__device__ __forceinline__ double finish_row8(const Params& P, bool kmap, const float* x, float* x_new, float dt, size_t goff) {
+    const StagePlan& sol = P.st[kUpd];               // bsol (no zero-dropping here: literal expression)
+    float xv[8], ss[8], se[8];
+    const float4 a = ld_f4(x + goff), b = ld_f4(x + goff + 4);
+    xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
+    for (int j0 = 0; j0 < P.n_err; j0 += 4) {
+        float4 q[4][2];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+            if (j0 + jj < P.n_err) { const float* kp = kbuf(P, kmap, j0 + jj) + goff; q[jj][0] = ld_f4(kp); q[jj][1] = ld_f4(kp + 4); }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = j0 + jj;
+            if (j < P.n_err) {
+                const float kv[8] = {q[jj][0].x, q[jj][0].y, q[jj][0].z, q[jj][0].w, q[jj][1].x, q[jj][1].y, q[jj][1].z, q[jj][1].w};
+                const float be = P.berr.c[j];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float m = mul_rn(be, kv[i]);
+                    se[i] = j == 0 ? m : add_rn(se[i], m);
+                }
+                if (j < sol.n_k) {
+                    const float bs = sol.coef[j];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float m = mul_rn(bs, kv[i]);
+                        ss[i] = j == 0 ? m : add_rn(ss[i], m);
+                    }
+                }
+            }
+        }
+    }
+    double acc = 0.0;
+    float xn[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        xn[i] = add_rn(xv[i], mul_rn(dt, ss[i]));
+        const float er = mul_rn(dt, se[i]);
+        const float den = add_rn(P.atol, mul_rn(P.rtol, fmaxf(fabsf(xv[i]), fabsf(xn[i]))));
+        const float r = div_rn(er, den);
+        acc += (double)mul_rn(r, r);
+    }
+    store_row8(x_new, goff, xn);
+    return acc;
+}
+
+// adaptive variant, init_step (numerics/utils.py:37-54) for 8 elements of one row.  phase 0: sums of (x0/scale)^2 and
+// (f0/scale)^2; phase 1: sum of ((f1 - f0)/scale)^2 with f1 = f(x0 + h0*f0) in the last stage buffer
+__device__ __forceinline__ void init_row8(const Params& P, int phase, const float* x, size_t goff, double& a0, double& a1) {
+    const float4 xa = ld_f4(x + goff), xb = ld_f4(x + goff + 4);
+    const float4 fa = ld_f4(P.kp[0] + goff), fb = ld_f4(P.kp[0] + goff + 4);
+    const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    const float f0[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+    if (phase == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float scale = add_rn(P.atol, mul_rn(fabsf(xv[i]), P.rtol));
+            const float q0 = div_rn(xv[i], scale), q1 = div_rn(f0[i], scale);
+            a0 += (double)mul_rn(q0, q0); a1 += (double)mul_rn(q1, q1);
+        }
+    } else {
+        const float* k1p = P.kp[P.n_stage - 1];
+        const float4 ga = ld_f4(k1p + goff), gb = ld_f4(k1p + goff + 4);
+        const float f1[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float scale = add_rn(P.atol, mul_rn(fabsf(xv[i]), P.rtol));
+            const float q = div_rn(sub_rn(f1[i], f0[i]), scale);
+            a0 += (double)mul_rn(q, q);
+        }
+    }
+}
+
+// adaptive variant: the step controller.  One worker thread per CTA runs it; every CTA computes the same values from the
+// same grid-wide sums, so no decision is ever communicated between CTAs.
+struct Ctrl {
+    float t, dt, dt_keep, T, h0, d1;
+    int ck, ck_flag, nout, attempt, accept, err, nfe;
+    unsigned int nbar;
+    // what the CTA's threads read at the start of the next batch / after the decision
+    int phase; float dt_attempt; int xcur; int swapped; int save_slot;
+};
+// start of an attempt (odeint.py:352-361): clamp to T, clamp to the next output time
+__device__ __forceinline__ void ctrl_begin_attempt(const Params& P, Ctrl& c) {
+    c.ck_flag = 0;
+    if (add_rn(c.t, c.dt) > c.T) c.dt = sub_rn(c.T, c.t);
+    if (c.ck < P.n_t - 1 && add_rn(c.t, c.dt) > __ldg(P.t_span + 1 + c.ck)) {
+        c.dt_keep = c.dt; c.ck_flag = 1;
+        c.dt = sub_rn(__ldg(P.t_span + 1 + c.ck), c.t);
+    }
+    c.dt_attempt = c.dt;
+}
+// after the grid-wide sums of a batch: returns the number of work items of the next batch (0: the solve is over)
+__device__ __noinline__ int ctrl_end_batch(const Params& P, Ctrl& c, double tot0, double tot1, int my_tiles, bool lead) {
+    const double count = (double)P.rows * kD;
+    c.save_slot = -1;
+    bool go = true;
+    if (c.phase == 0) {
+        // init_step, first half (utils.py:40-47)
+        const float d0 = sqrtf((float)(tot0 / count)), d1 = sqrtf((float)(tot1 / count));
+        c.h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : div_rn(mul_rn(0.01f, d0), d1);
+        c.d1 = d1;
+        c.nfe = 1;
+        c.phase = 1;
+        c.dt_attempt = c.h0;
+        return my_tiles;
+    }
+    if (c.phase == 1) {
+        // init_step, second half (utils.py:48-54)
+        const float d2 = div_rn(sqrtf((float)(tot0 / count)), c.h0);
+        float h1;
+        if (c.d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, mul_rn(c.h0, 1e-3f));
+        else {
+            const float base = mul_rn(div_rn(1.f, fmaxf(c.d1, d2)), 0.01f);
+            h1 = (float)pow((double)base, 1.0 / (double)(P.order + 1));
+        }
+        c.dt = fminf(mul_rn(100.f, c.h0), h1);
+        c.nfe = 2;
+        c.phase = 2;
+        if (lead && P.trace_cap > 0) P.trace[0] = c.dt;
+        go = c.t < c.T;
+    } else {
+        // error ratio, accept / reject, output bookkeeping (odeint.py:365-401), adapt_step (utils.py:57-63)
+        const float ratio = sqrtf((float)(tot0 / count));
+        const float dt = c.dt;
+        ++c.attempt;
+        c.nfe += P.n_stage - 1;
+        if (lead && 3 * c.attempt < P.trace_cap) {
+            P.trace[3 * c.attempt - 2] = c.t; P.trace[3 * c.attempt - 1] = dt; P.trace[3 * c.attempt] = ratio;
+        }
+        if (ratio <= 1.f) {
+            ++c.accept;
+            const float tn = add_rn(c.t, dt);
+            const bool hit = c.ck < P.n_t - 1 && tn == __ldg(P.t_span + 1 + c.ck);
+            if (hit || P.return_all) {
+                if (c.nout < P.out_cap) {
+                    c.save_slot = c.nout;
+                    if (lead) P.t_out[c.nout] = tn;
+                } else {
+                    c.err = 2;
+                }
+                ++c.nout;
+                if (hit) ++c.ck;
+            }
+            c.t = tn;
+            c.xcur ^= 1;
+            // FSAL: k1 <- k_last by swapping the two buffers' roles
+            c.swapped ^= 1;
+        }
+        if (c.ck_flag) c.dt = sub_rn(c.dt_keep, dt);             // the remainder of the intended step (:399-401)
+        if (ratio == 0.f) c.dt = mul_rn(c.dt, P.max_factor);
+        else {
+            const float lo = ratio < 1.f ? 1.f : P.min_factor;
+            const float pw = (float)pow((double)ratio, (double)div_rn(1.f, (float)P.order));
+            const float cand = div_rn(P.safety, pw);
+            const float fac = (cand != cand) ? cand : fminf(P.max_factor, fmaxf(cand, lo));
+            c.dt = mul_rn(c.dt, fac);
+        }
+        go = c.t < c.T && c.err == 0;
+        if (go && (c.attempt >= P.max_steps || c.dt != c.dt)) { c.err = 1; go = false; }
+    }
+    if (go) {
+        ctrl_begin_attempt(P, c);
+        return my_tiles * (P.n_stage - 1);
+    }
+    if (lead) {
+        P.status[0] = c.nout; P.status[1] = c.attempt; P.status[2] = c.accept;
+        P.status[3] = c.nfe; P.status[4] = c.err; P.status[5] = c.xcur;
+    }
+    return 0;
+}
+
+// adaptive variant, end of a batch (all worker threads): phase 2: x_new, err and the sum of squared scaled errors
+// (odeint.py:365-372); phases 0 / 1: init_step's norms; then ONE grid barrier carries the global sums, the controller
+// decides, and an accepted output step is copied out.  A separate (not inlined) function: nothing of it may cost the
+// item loop a register.
+__device__ __noinline__ void adaptive_batch_end(const Params& P, Ctrl& ctrl, int& batch_n, double* red_sm, int my_tiles) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = (warp - 2) >> 2, row = (warp & 3) * 32 + lane;
+    const int phase = ctrl.phase, xcur = ctrl.xcur;
+    const bool kmap = uniform_flag(ctrl.swapped != 0);
+    const float dt_att = ctrl.dt_attempt;
+    const bool second = uniform_flag(xcur != 0);
+    const float* xc = second ? P.xbuf[1] : P.xbuf[0];
+    float* xn = second ? P.xbuf[0] : P.xbuf[1];
+    double a0 = 0.0, a1 = 0.0;
+    for (int i = 0; i < my_tiles; ++i) {
+        const int64_t grow = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTileM + row;
+        if (grow < P.rows) {
+            const size_t goff = (size_t)grow * kD + sub * 8;
+            if (phase == 2) a0 += finish_row8(P, kmap, xc, xn, dt_att, goff);
+            else init_row8(P, phase, xc, goff, a0, a1);
+        }
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1);
+    if (lane == 0) { red_sm[2 * (warp - 2)] = a0; red_sm[2 * (warp - 2) + 1] = a1; }
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (threadIdx.x == 64) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int q = 0; q < kWorkers / 32; ++q) { s0 += red_sm[2 * q]; s1 += red_sm[2 * q + 1]; }
+        // all CTAs are co-resident (cooperative launch)
+        double* part = P.partials + (size_t)(ctrl.nbar & 1u) * 2 * gridDim.x;
+        part[blockIdx.x] = s0; part[gridDim.x + blockIdx.x] = s1;
+        __threadfence();
+        atomicAdd(P.gbar, 1u);
+        const unsigned int target = (++ctrl.nbar) * gridDim.x;
+        for (;;) {
+            unsigned int v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.gbar) : "memory");
+            if (v >= target) break;
+            __nanosleep(32);
+        }
+        double t0 = 0.0, t1 = 0.0;
+        for (unsigned int bq = 0; bq < gridDim.x; ++bq) { t0 += __ldcg(part + bq); t1 += __ldcg(part + gridDim.x + bq); }
+        // the controller: every CTA computes the same decision from the same totals
+        batch_n = ctrl_end_batch(P, ctrl, t0, t1, my_tiles, blockIdx.x == 0);
+    }
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    const int save_slot = ctrl.save_slot;
+    if (save_slot >= 0) {
+        // an accepted step that is an output: this thread copies what it wrote itself
+        float* dst = P.out + (size_t)save_slot * P.n_state;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int64_t grow = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTileM + row;
+            if (grow < P.rows) {
+                const size_t goff = (size_t)grow * kD + sub * 8;
+                reinterpret_cast<float4*>(dst + goff)[0] = ld_f4(xn + goff);
+                reinterpret_cast<float4*>(dst + goff)[1] = ld_f4(xn + goff + 4);
+            }
+        }
+    }
 }
 
 // VAR 1 (save): also write the hidden activations (and scale the output) -- the adjoint's forward half.
@@ -281,7 +549,7 @@ __device__ __forceinline__ void prologue(const Params& P, const Item& it, bool f
 // -- the "activation" of a hidden layer is the multiplication with act' of the saved forward activation (read from global
 // memory), no biases; delta2 / delta1 are written out for the parameter gradients.  Separate instantiations, so that the
 // integration kernels carry none of it (registers are at the limit of 576 threads per SM).
-constexpr int kVarPlain = 0, kVarSave = 1, kVarDgrad = 2;
+constexpr int kVarPlain = 0, kVarSave = 1, kVarDgrad = 2, kVarAdaptive = 3;
 template <int ACT>
 __device__ __forceinline__ float dact_from_out(float a) {
     if (ACT == TDYN_ACT_RELU) return a > 0.f ? 1.f : 0.f;
@@ -324,258 +592,325 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
     const int my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    // work items of this CTA: pass-major, its tiles within a pass (the launcher guarantees my_tiles >= 2 when n_pass > 1:
-    // the stage input of item i + 1 is built while item i is still in flight, so the two must be different tiles)
-    const int n_items = my_tiles * P.n_stage * P.n_steps;
+    constexpr bool ADAPT = VAR == kVarAdaptive;
+    // Work items of this CTA: pass-major, its tiles within a pass (the launchers guarantee my_tiles >= 2 when there is more
+    // than one pass: the stage input of item i + 1 is built while item i is still in flight, so the two must be different
+    // tiles).  Items come in BATCHES: one batch = everything whose inputs are known up front -- the whole launch for a
+    // stage / a fixed-step solve; ONE ATTEMPTED STEP (stages 2..s) for the adaptive variant, where the next batch exists only
+    // after the grid-wide error norm and the step controller have run.  The three roles leave and re-enter the software
+    // pipeline at batch boundaries; every mbarrier completes once per item, so their parities follow the global item count.
+    __shared__ int batch_n;              // items of the next batch (0: stop); written by the controller thread
+    __shared__ double red_sm[2 * kWorkers / 32];
+    __shared__ Ctrl ctrl;
+    if (ADAPT && threadIdx.x == 0) {
+        ctrl.t = __ldg(P.t_span); ctrl.T = __ldg(P.t_span + P.n_t - 1);
+        ctrl.ck = 0; ctrl.ck_flag = 0; ctrl.nout = 1; ctrl.attempt = 0; ctrl.accept = 0; ctrl.err = 0; ctrl.nfe = 0;
+        ctrl.nbar = 0; ctrl.xcur = 0; ctrl.swapped = 0; ctrl.save_slot = -1; ctrl.dt_attempt = 0.f;
+        if (P.t_dt0 > 0.f) {             // k1 and the first step size come from the caller
+            ctrl.dt = P.t_dt0; ctrl.phase = 2;
+            if (blockIdx.x == 0 && P.trace_cap > 0) P.trace[0] = P.t_dt0;
+            ctrl_begin_attempt(P, ctrl);
+            batch_n = my_tiles * (P.n_stage - 1);
+        } else {
+            ctrl.phase = 0;
+            batch_n = my_tiles;
+        }
+    }
     // TMEM map: X = cols [0,256): D1, converted in place to layer 2's A_hi; Y = cols [256,512): D2 -> layer 3's A_hi;
     // D3 = cols [224,256) (layer 2's A_hi is dead once layer 2 has been issued: the tensor pipe executes in order).
     // The NEXT tile's layer 1 is split: columns [0,224) are issued right after this tile's layer 2 (they run under the
     // layer-2 -> 3 epilogue), columns [224,256) once this tile's D3 has been read out.
     constexpr uint32_t kColD1 = 0, kColD2 = 256, kColD3 = kNSplit;
 
-    if (warp == 0) {
-        // ================= weight producer: W1(0) | per tile: W2[0..7], W1 + W1B(next tile), W3 =================
-        if (lane == 0) {
-            uint32_t it = 0;
-            auto load = [&](int s) {
-                const uint32_t slot = it & 1, use = it >> 1;
-                mbar_wait(bar(W_EMPTY0 + slot), (use & 1) ^ 1);
-                mbar_expect_tx(bar(W_FULL0 + slot), kWStage);
-                const uint32_t dst = sbase + kSmemWRing + slot * kWStage;
-                const uint8_t* src = P.wimg + (size_t)s * kWStage;
-                bulk_g2s(dst, src, kWStage / 2, bar(W_FULL0 + slot));
-                bulk_g2s(dst + kWStage / 2, src + kWStage / 2, kWStage / 2, bar(W_FULL0 + slot));
-                ++it;
-            };
-            auto load_w1b = [&](int t) {
-                mbar_wait(bar(W1B_EMPTY), (t & 1) ^ 1);
-                mbar_expect_tx(bar(W1B_FULL), kW1BBytes);
-                bulk_g2s(sbase + kSmemW1B, P.wimg + (size_t)kWStagesPerTile * kWStage, kW1BBytes, bar(W1B_FULL));
-            };
-            if (n_items > 0) { load(0); load_w1b(0); }
-            for (int t = 0; t < n_items; ++t) {
-                for (int s = 1; s <= 8; ++s) load(s);
-                if (t + 1 < n_items) { load(0); load_w1b(t + 1); }
-                load(9);
-            }
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            uint32_t wit = 0, ait = 0;
-            const uint32_t a1 = sbase + kSmemA1;
-            auto layer1a = [&](int t) {         // [128 x 32] x [224 x 32]^T -> D1 cols [0,224)
-                mbar_wait(bar(A1_FULL), t & 1);
-                const uint32_t slot = wit & 1, use = wit >> 1;
-                mbar_wait(bar(W_FULL0 + slot), use & 1);
-                tc_fence_after();
-                const uint32_t w = sbase + kSmemWRing + slot * kWStage;
-                issue_kblock(tmem + kColD1, a1, a1 + kATile, w, w + kWStage / 2, kNSplit, true);
-                tc_commit(bar(W_EMPTY0 + slot));
-                tc_commit(bar(D1_FULL));
-                ++wit;
-            };
-            auto layer1b = [&](int t) {         // remaining 32 output columns (W1 rows 224..255 from their own buffer)
-                mbar_wait(bar(W1B_FULL), t & 1);
-                tc_fence_after();
-                const uint32_t w = sbase + kSmemW1B;
-                issue_kblock(tmem + kColD1 + kNSplit, a1, a1 + kATile, w, w + 4096u, kH - kNSplit, true);
-                tc_commit(bar(W1B_EMPTY));
-                tc_commit(bar(D1B_FULL));
-            };
-            if (n_items > 0) { layer1a(0); layer1b(0); }
-            for (int t = 0; t < n_items; ++t) {
-                // ---- layer 2: 8 K-blocks, A_hi = X (in TMEM), A_lo ring -> D2 = Y
-                for (int j = 0; j < kH / kKB; ++j, ++wit, ++ait) {
-                    const uint32_t ws = wit & 1, wu = wit >> 1, as = ait % kLoStages, au = ait / kLoStages;
-                    mbar_wait(bar(A_FULL0 + as), au & 1);
-                    mbar_wait(bar(W_FULL0 + ws), wu & 1);
-                    tc_fence_after();
-                    const uint32_t w = sbase + kSmemWRing + ws * kWStage;
-                    issue_kblock_ts(tmem + kColD2, tmem + kColD1 + (uint32_t)(j * kKB), sbase + kSmemLoRing + as * kATile,
-                                    w, w + kWStage / 2, kH, j == 0);
-                    tc_commit(bar(W_EMPTY0 + ws));
-                    tc_commit(bar(A_EMPTY0 + as));
-                }
-                tc_commit(bar(D2_FULL));
-                // ---- first 224 columns of the next tile's layer 1: tensor work for the layer-2 -> 3 epilogue phase
-                if (t + 1 < n_items) layer1a(t + 1);
-                // ---- layer 3: 8 K-blocks, N = 32, A_hi = Y -> D3 = X[224,256); W3 stage = 8 x [hi 4 KB | lo 4 KB]
-                {
-                    const uint32_t ws = wit & 1, wu = wit >> 1;
-                    mbar_wait(bar(W_FULL0 + ws), wu & 1);
-                    const uint32_t w = sbase + kSmemWRing + ws * kWStage;
-                    for (int j = 0; j < kH / kKB; ++j, ++ait) {
-                        const uint32_t as = ait % kLoStages, au = ait / kLoStages;
-                        mbar_wait(bar(A_FULL0 + as), au & 1);
-                        tc_fence_after();
-                        const uint32_t wj = w + (uint32_t)j * 8192u;
-                        issue_kblock_ts(tmem + kColD3, tmem + kColD2 + (uint32_t)(j * kKB), sbase + kSmemLoRing + as * kATile,
-                                        wj, wj + 4096u, kD, j == 0);
-                        tc_commit(bar(A_EMPTY0 + as));
-                    }
-                    tc_commit(bar(W_EMPTY0 + ws));
-                    tc_commit(bar(D3_FULL));
-                    ++wit;
-                }
-                // ---- the last 32 columns of the next tile's layer 1 overwrite D3: wait until it has been read out
-                if (t + 1 < n_items) {
-                    mbar_wait(bar(D_FREE), t & 1);
-                    layer1b(t + 1);
-                }
-            }
-        }
-    } else {
-        // ================= workers: prologue / activation epilogues / output =================
-        WorkerCtx w;
+    // ring counters of the producer / MMA / worker roles: functions of the number of items done so far (10 weight stages
+    // and 16 operand tiles per item), so that only `gbase` lives across a batch boundary
+    WorkerCtx w;
+    {
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
         w.sub = (warp - 2) >> 2;                       // which 8 of every 32 columns (0..3)
         w.row = quarter * 32 + lane;                   // row inside the tile == TMEM lane
         w.lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-        uint32_t ait = 0;
-        int pass = 0, tl = 0;                          // (pass, local tile index) of the current item
-        Item cur = make_item(P, 0);
-        if (n_items > 0) {
-            prologue(P, cur, true, smem, w, (int64_t)blockIdx.x);
-            mbar_arrive(bar(A1_FULL));
+    }
+    // adaptive variant: what the threads need of the controller state (phase, attempted dt, current state buffer, stage
+    // buffer map) is re-read from shared memory at every use -- it is constant during a batch, and the kernel has no
+    // registers to spare
+    const volatile Ctrl* cv = &ctrl;
+    auto item_at = [&](int pss, const Item& fixed) -> Item {
+        if constexpr (ADAPT) {
+            // the phase decides which plan (Params::st entry, constant bank) the stage input uses: hand it to the compiler
+            // as a warp-UNIFORM value (vote results are), so that the plan stays an indexed constant-bank operand -- with
+            // a per-thread index the parameter array would be copied to local memory
+            const int ph = cv->phase;
+            const bool p2 = uniform_flag(ph == 2), p1 = uniform_flag(ph == 1);
+            return make_item_adapt(P, p2 ? 2 : (p1 ? 1 : 0), pss, cv->dt_attempt);
         }
-        for (int t = 0; t < n_items; ++t) {
-            const uint32_t tpar = t & 1;
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)tl * gridDim.x;
-            const int64_t grow_cur = VAR != kVarPlain ? tile * kTileM + w.row : 0;
-            const int npass = tl + 1 < my_tiles ? pass : pass + 1, ntl = tl + 1 < my_tiles ? tl + 1 : 0;   // the next item
-            const int64_t ntile = (int64_t)blockIdx.x + (int64_t)ntl * gridDim.x;
-            const Item nxt = (t + 1 < n_items && npass != pass) ? make_item(P, npass) : cur;
-            if (t + 1 < n_items && w.sub == 0) {
-                // the next item's stage-input rows (x and the k's, 128 B each) are consumed by prologue() half an item
-                // from now: pull them into L2 so that those loads do not pay the DRAM latency
-                const int64_t nrow = ntile * kTileM + w.row;
-                if (nrow < P.rows) {
-                    const StagePlan& np = P.st[plan_index(P, nxt, npass == 0)];
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(((npass == 0 || !P.solve) ? P.x_in : P.xw) + (size_t)nrow * kD));
-                    for (int j = 0; j < np.n_k; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.kp[np.kidx[j]] + (size_t)nrow * kD));
+        else return fixed;
+    };
+    auto x_adapt = [&]() -> const float* { return ADAPT ? (uniform_flag(cv->xcur != 0) ? P.xbuf[1] : P.xbuf[0]) : nullptr; };
+    auto kmap_now = [&]() -> bool { return ADAPT ? uniform_flag(cv->swapped != 0) : false; };
+    int gbase = 0;
+    for (;;) {
+        int n_items;
+        if constexpr (ADAPT) {
+            __syncthreads();
+            n_items = batch_n;
+            if (n_items == 0) break;
+        } else {
+            n_items = my_tiles * P.n_stage * P.n_steps;          // one batch: no back edge in these variants
+        }
+        if (warp == 0) {
+            // ================= weight producer: W1(0) | per item: W2[0..7], W1 + W1B(next item), W3 =================
+            if (lane == 0) {
+                uint32_t p_it = 10u * (uint32_t)gbase;
+                auto load = [&](int s) {
+                    const uint32_t slot = p_it & 1, use = p_it >> 1;
+                    mbar_wait(bar(W_EMPTY0 + slot), (use & 1) ^ 1);
+                    mbar_expect_tx(bar(W_FULL0 + slot), kWStage);
+                    const uint32_t dst = sbase + kSmemWRing + slot * kWStage;
+                    const uint8_t* src = P.wimg + (size_t)s * kWStage;
+                    bulk_g2s(dst, src, kWStage / 2, bar(W_FULL0 + slot));
+                    bulk_g2s(dst + kWStage / 2, src + kWStage / 2, kWStage / 2, bar(W_FULL0 + slot));
+                    ++p_it;
+                };
+                auto load_w1b = [&](int gt) {
+                    mbar_wait(bar(W1B_EMPTY), (gt & 1) ^ 1);
+                    mbar_expect_tx(bar(W1B_FULL), kW1BBytes);
+                    bulk_g2s(sbase + kSmemW1B, P.wimg + (size_t)kWStagesPerTile * kWStage, kW1BBytes, bar(W1B_FULL));
+                };
+                load(0); load_w1b(gbase);
+                for (int t = 0; t < n_items; ++t) {
+                    for (int s = 1; s <= 8; ++s) load(s);
+                    if (t + 1 < n_items) { load(0); load_w1b(gbase + t + 1); }
+                    load(9);
                 }
             }
-            // ---- two activation epilogues: D1 -> layer-2 operand, D2 -> layer-3 operand
-#pragma unroll 1
-            for (int layer = 0; layer < 2; ++layer) {
-                mbar_wait(bar(layer == 0 ? D1_FULL : D2_FULL), tpar);
-                tc_fence_after();
-                const float* bias = reinterpret_cast<const float*>(smem + kSmemBias) + layer * kH + w.sub * 8;
-                const uint32_t src = w.lane_addr + (layer == 0 ? kColD1 : kColD2) + (uint32_t)(w.sub * 8);
-                uint32_t ra[8], rb[8];
-                tmem_ld8(src, ra);
-                tmem_wait8(ra);
-#pragma unroll
-                for (int j = 0; j < kH / kKB; ++j, ++ait) {
-                    uint32_t (&cur)[8] = (j & 1) ? rb : ra;
-                    uint32_t (&nxt)[8] = (j & 1) ? ra : rb;
-                    if (j + 1 < kH / kKB) {
-                        if (layer == 0 && (j + 1) * kKB == kNSplit) {       // last chunk of D1 is produced by layer1b
-                            mbar_wait(bar(D1B_FULL), tpar);
+        } else if (warp == 1) {
+            // ================= MMA issuer =================
+            if (lane == 0) {
+                uint32_t m_wit = 10u * (uint32_t)gbase, m_ait = 16u * (uint32_t)gbase;
+                const uint32_t a1 = sbase + kSmemA1;
+                auto layer1a = [&](int gt) {        // [128 x 32] x [224 x 32]^T -> D1 cols [0,224)
+                    mbar_wait(bar(A1_FULL), gt & 1);
+                    const uint32_t slot = m_wit & 1, use = m_wit >> 1;
+                    mbar_wait(bar(W_FULL0 + slot), use & 1);
+                    tc_fence_after();
+                    const uint32_t wb = sbase + kSmemWRing + slot * kWStage;
+                    issue_kblock(tmem + kColD1, a1, a1 + kATile, wb, wb + kWStage / 2, kNSplit, true);
+                    tc_commit(bar(W_EMPTY0 + slot));
+                    tc_commit(bar(D1_FULL));
+                    ++m_wit;
+                };
+                auto layer1b = [&](int gt) {        // remaining 32 output columns (W1 rows 224..255 from their own buffer)
+                    mbar_wait(bar(W1B_FULL), gt & 1);
+                    tc_fence_after();
+                    const uint32_t wb = sbase + kSmemW1B;
+                    issue_kblock(tmem + kColD1 + kNSplit, a1, a1 + kATile, wb, wb + 4096u, kH - kNSplit, true);
+                    tc_commit(bar(W1B_EMPTY));
+                    tc_commit(bar(D1B_FULL));
+                };
+                layer1a(gbase); layer1b(gbase);
+                for (int t = 0; t < n_items; ++t) {
+                    // ---- layer 2: 8 K-blocks, A_hi = X (in TMEM), A_lo ring -> D2 = Y
+                    for (int j = 0; j < kH / kKB; ++j, ++m_wit, ++m_ait) {
+                        const uint32_t ws = m_wit & 1, wu = m_wit >> 1, as = m_ait % kLoStages, au = m_ait / kLoStages;
+                        mbar_wait(bar(A_FULL0 + as), au & 1);
+                        mbar_wait(bar(W_FULL0 + ws), wu & 1);
+                        tc_fence_after();
+                        const uint32_t wb = sbase + kSmemWRing + ws * kWStage;
+                        issue_kblock_ts(tmem + kColD2, tmem + kColD1 + (uint32_t)(j * kKB), sbase + kSmemLoRing + as * kATile,
+                                        wb, wb + kWStage / 2, kH, j == 0);
+                        tc_commit(bar(W_EMPTY0 + ws));
+                        tc_commit(bar(A_EMPTY0 + as));
+                    }
+                    tc_commit(bar(D2_FULL));
+                    // ---- first 224 columns of the next item's layer 1: tensor work for the layer-2 -> 3 epilogue phase
+                    if (t + 1 < n_items) layer1a(gbase + t + 1);
+                    // ---- layer 3: 8 K-blocks, N = 32, A_hi = Y -> D3 = X[224,256); W3 stage = 8 x [hi 4 KB | lo 4 KB]
+                    {
+                        const uint32_t ws = m_wit & 1, wu = m_wit >> 1;
+                        mbar_wait(bar(W_FULL0 + ws), wu & 1);
+                        const uint32_t wb = sbase + kSmemWRing + ws * kWStage;
+                        for (int j = 0; j < kH / kKB; ++j, ++m_ait) {
+                            const uint32_t as = m_ait % kLoStages, au = m_ait / kLoStages;
+                            mbar_wait(bar(A_FULL0 + as), au & 1);
                             tc_fence_after();
+                            const uint32_t wj = wb + (uint32_t)j * 8192u;
+                            issue_kblock_ts(tmem + kColD3, tmem + kColD2 + (uint32_t)(j * kKB), sbase + kSmemLoRing + as * kATile,
+                                            wj, wj + 4096u, kD, j == 0);
+                            tc_commit(bar(A_EMPTY0 + as));
                         }
-                        tmem_ld8(src + (uint32_t)((j + 1) * kKB), nxt);     // prefetch next chunk
+                        tc_commit(bar(W_EMPTY0 + ws));
+                        tc_commit(bar(D3_FULL));
+                        ++m_wit;
                     }
-                    float v[8];
-                    if (VAR == kVarDgrad) {
-                        // delta = acc * act'(saved activation): epilogue 0 pairs with a2, epilogue 1 with a1
-                        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-                        if (grow_cur < P.rows) {
-                            const float4* sp = reinterpret_cast<const float4*>(P.dact_in[layer] + (size_t)grow_cur * kH + j * kKB + w.sub * 8);
-                            s0 = __ldg(sp); s1 = __ldg(sp + 1);
-                        }
-                        v[0] = __uint_as_float(cur[0]) * dact_from_out<ACT>(s0.x); v[1] = __uint_as_float(cur[1]) * dact_from_out<ACT>(s0.y);
-                        v[2] = __uint_as_float(cur[2]) * dact_from_out<ACT>(s0.z); v[3] = __uint_as_float(cur[3]) * dact_from_out<ACT>(s0.w);
-                        v[4] = __uint_as_float(cur[4]) * dact_from_out<ACT>(s1.x); v[5] = __uint_as_float(cur[5]) * dact_from_out<ACT>(s1.y);
-                        v[6] = __uint_as_float(cur[6]) * dact_from_out<ACT>(s1.z); v[7] = __uint_as_float(cur[7]) * dact_from_out<ACT>(s1.w);
-                    } else {
-                        const float4 b0 = *reinterpret_cast<const float4*>(bias + j * kKB);
-                        const float4 b1 = *reinterpret_cast<const float4*>(bias + j * kKB + 4);
-                        v[0] = activate_biased<ACT>(__uint_as_float(cur[0]), b0.x); v[1] = activate_biased<ACT>(__uint_as_float(cur[1]), b0.y);
-                        v[2] = activate_biased<ACT>(__uint_as_float(cur[2]), b0.z); v[3] = activate_biased<ACT>(__uint_as_float(cur[3]), b0.w);
-                        v[4] = activate_biased<ACT>(__uint_as_float(cur[4]), b1.x); v[5] = activate_biased<ACT>(__uint_as_float(cur[5]), b1.y);
-                        v[6] = activate_biased<ACT>(__uint_as_float(cur[6]), b1.z); v[7] = activate_biased<ACT>(__uint_as_float(cur[7]), b1.w);
-                    }
-                    if (VAR != kVarPlain && grow_cur < P.rows) {
-                        float4* dst = reinterpret_cast<float4*>(P.act_out[layer] + (size_t)grow_cur * kH + j * kKB + w.sub * 8);
-                        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-                    }
-                    const uint32_t as = ait % kLoStages, au = ait / kLoStages;
-                    mbar_wait(bar(A_EMPTY0 + as), (au & 1) ^ 1);
-                    store_split8_tmem(src + (uint32_t)(j * kKB), smem + kSmemLoRing + as * kATile, w.row, w.sub, v);
-                    fence_proxy_async();
-                    tc_fence_before();
-                    mbar_arrive(bar(A_FULL0 + as));
-                    if (j + 1 < kH / kKB) tmem_wait8(nxt);
-                }
-                if (layer == 0 && t + 1 < n_items) {
-                    // next item's stage input (A1 is free: this item's layer 1 has completed)
-                    prologue(P, nxt, npass == 0, smem, w, ntile);
-                    mbar_arrive(bar(A1_FULL));
-                }
-            }
-            // ---- output: k_out = D3 + b3 (and x_new for the last stage of a fixed-step method)
-            mbar_wait(bar(D3_FULL), tpar);
-            tc_fence_after();
-            uint32_t ro[8];
-            tmem_ld8(w.lane_addr + kColD3 + (uint32_t)(w.sub * 8), ro);
-            tmem_wait8(ro);
-            tc_fence_before();
-            mbar_arrive(bar(D_FREE));
-            const int64_t grow = tile * kTileM + w.row;
-            if (grow < P.rows) {
-                const size_t goff = (size_t)grow * kD + w.sub * 8;
-                float o[8];
-                float* k_out = P.solve ? const_cast<float*>(P.kp[cur.g]) : P.k_out0;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const float4 bq = *reinterpret_cast<const float4*>(smem + kSmemBias + (2 * kH + w.sub * 8 + 4 * i) * 4);
-                    const float sc = VAR != kVarPlain ? P.out_scale : 1.f;
-                    o[4 * i] = sc * (__uint_as_float(ro[4 * i]) + bq.x); o[4 * i + 1] = sc * (__uint_as_float(ro[4 * i + 1]) + bq.y);
-                    o[4 * i + 2] = sc * (__uint_as_float(ro[4 * i + 2]) + bq.z); o[4 * i + 3] = sc * (__uint_as_float(ro[4 * i + 3]) + bq.w);
-                    reinterpret_cast<float4*>(k_out + goff)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-                }
-                if (P.x_new) {
-                    // x + dt*(b0*k0 + ... + b_last*k_out)
-                    float s[8];
-                    for (int j = 0; j < P.n_sol; ++j) {
-                        const float b = P.bsol.c[j];
-                        const bool last = j == P.n_sol - 1;
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            float4 q;
-                            if (last) q = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-                            else q = __ldg(reinterpret_cast<const float4*>(P.kp[j] + goff) + i);
-                            const float m0 = mul_rn(b, q.x), m1 = mul_rn(b, q.y), m2 = mul_rn(b, q.z), m3 = mul_rn(b, q.w);
-                            s[4 * i] = j == 0 ? m0 : add_rn(s[4 * i], m0);
-                            s[4 * i + 1] = j == 0 ? m1 : add_rn(s[4 * i + 1], m1);
-                            s[4 * i + 2] = j == 0 ? m2 : add_rn(s[4 * i + 2], m2);
-                            s[4 * i + 3] = j == 0 ? m3 : add_rn(s[4 * i + 3], m3);
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const float4 xq = __ldg(reinterpret_cast<const float4*>(P.x_in + goff) + i);
-                        reinterpret_cast<float4*>(P.x_new + goff)[i] =
-                            make_float4(add_rn(xq.x, mul_rn(P.dt0, s[4 * i])), add_rn(xq.y, mul_rn(P.dt0, s[4 * i + 1])),
-                                        add_rn(xq.z, mul_rn(P.dt0, s[4 * i + 2])), add_rn(xq.w, mul_rn(P.dt0, s[4 * i + 3])));
+                    // ---- the last 32 columns of the next item's layer 1 overwrite D3: wait until it has been read out
+                    if (t + 1 < n_items) {
+                        mbar_wait(bar(D_FREE), (gbase + t) & 1);
+                        layer1b(gbase + t + 1);
                     }
                 }
             }
-            pass = npass; tl = ntl; cur = nxt;
-        }
-        if (P.solve) {
-            // solve mode: the closing combination x_final = x + dt*(sum_j bsol_j k_j) of the last step (no evaluation)
-            for (int i = 0; i < my_tiles; ++i) {
-                const int64_t grow = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTileM + w.row;
+        } else {
+            // ================= workers: prologue / activation epilogues / output =================
+            uint32_t ait = 16u * (uint32_t)gbase;
+            int pass = 0, tl = 0;                          // (pass, local tile index) of the current item within the batch
+            Item cur = ADAPT ? Item{} : make_item(P, 0);
+            prologue(P, item_at(0, cur), !ADAPT && gbase == 0, smem, w, (int64_t)blockIdx.x, x_adapt(), kmap_now());
+            mbar_arrive(bar(A1_FULL));
+            for (int t = 0; t < n_items; ++t) {
+                const uint32_t tpar = (uint32_t)(gbase + t) & 1u;
+                const int64_t tile = (int64_t)blockIdx.x + (int64_t)tl * gridDim.x;
+                const int64_t grow_cur = (VAR == kVarSave || VAR == kVarDgrad) ? tile * kTileM + w.row : 0;
+                const int npass = tl + 1 < my_tiles ? pass : pass + 1, ntl = tl + 1 < my_tiles ? tl + 1 : 0;   // the next item
+                const int64_t ntile = (int64_t)blockIdx.x + (int64_t)ntl * gridDim.x;
+                const Item nxt = (!ADAPT && t + 1 < n_items && npass != pass) ? make_item(P, npass) : cur;
+                if (t + 1 < n_items && w.sub == 0) {
+                    // the next item's stage-input rows (x and the k's, 128 B each) are consumed by prologue() half an item
+                    // from now: pull them into L2 so that those loads do not pay the DRAM latency
+                    const int64_t nrow = ntile * kTileM + w.row;
+                    if (nrow < P.rows) {
+                        const bool first = !ADAPT && gbase == 0 && npass == 0;
+                        const Item ni = item_at(npass, nxt);
+                        const StagePlan& np = P.st[ADAPT ? ni.slot : plan_index(P, ni, first)];
+                        const float* xs = ADAPT ? x_adapt() : ((first || !P.solve) ? P.x_in : P.xw);
+                        const bool kmap = kmap_now();
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(xs + (size_t)nrow * kD));
+                        for (int j = 0; j < np.n_k; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(kbuf(P, kmap, np.kidx[j]) + (size_t)nrow * kD));
+                    }
+                }
+                // ---- two activation epilogues: D1 -> layer-2 operand, D2 -> layer-3 operand
+#pragma unroll 1
+                for (int layer = 0; layer < 2; ++layer) {
+                    mbar_wait(bar(layer == 0 ? D1_FULL : D2_FULL), tpar);
+                    tc_fence_after();
+                    const float* bias = reinterpret_cast<const float*>(smem + kSmemBias) + layer * kH + w.sub * 8;
+                    const uint32_t src = w.lane_addr + (layer == 0 ? kColD1 : kColD2) + (uint32_t)(w.sub * 8);
+                    // (the adaptive variant has no registers for the second buffer: it loads each chunk when it needs it)
+                    constexpr bool kPrefetch = !ADAPT;
+                    uint32_t ra[8], rb[kPrefetch ? 8 : 1];
+                    if (kPrefetch) {
+                        tmem_ld8(src, ra);
+                        tmem_wait8(ra);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kH / kKB; ++j, ++ait) {
+                        uint32_t (&cur)[8] = (kPrefetch && (j & 1)) ? reinterpret_cast<uint32_t (&)[8]>(rb) : ra;
+                        uint32_t (&nxt)[8] = (kPrefetch && !(j & 1)) ? reinterpret_cast<uint32_t (&)[8]>(rb) : ra;
+                        if (kPrefetch ? j + 1 < kH / kKB : true) {
+                            const int jl = kPrefetch ? j + 1 : j;                // the chunk loaded now
+                            if (layer == 0 && jl * kKB == kNSplit) {             // last chunk of D1 is produced by layer1b
+                                mbar_wait(bar(D1B_FULL), tpar);
+                                tc_fence_after();
+                            }
+                            tmem_ld8(src + (uint32_t)(jl * kKB), nxt);           // prefetch next chunk / load this one
+                            if (!kPrefetch) tmem_wait8(nxt);
+                        }
+                        float v[8];
+                        if (VAR == kVarDgrad) {
+                            // delta = acc * act'(saved activation): epilogue 0 pairs with a2, epilogue 1 with a1
+                            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+                            if (grow_cur < P.rows) {
+                                const float4* sp = reinterpret_cast<const float4*>(P.dact_in[layer] + (size_t)grow_cur * kH + j * kKB + w.sub * 8);
+                                s0 = __ldg(sp); s1 = __ldg(sp + 1);
+                            }
+                            v[0] = __uint_as_float(cur[0]) * dact_from_out<ACT>(s0.x); v[1] = __uint_as_float(cur[1]) * dact_from_out<ACT>(s0.y);
+                            v[2] = __uint_as_float(cur[2]) * dact_from_out<ACT>(s0.z); v[3] = __uint_as_float(cur[3]) * dact_from_out<ACT>(s0.w);
+                            v[4] = __uint_as_float(cur[4]) * dact_from_out<ACT>(s1.x); v[5] = __uint_as_float(cur[5]) * dact_from_out<ACT>(s1.y);
+                            v[6] = __uint_as_float(cur[6]) * dact_from_out<ACT>(s1.z); v[7] = __uint_as_float(cur[7]) * dact_from_out<ACT>(s1.w);
+                        } else {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bias + j * kKB);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bias + j * kKB + 4);
+                            v[0] = activate_biased<ACT>(__uint_as_float(cur[0]), b0.x); v[1] = activate_biased<ACT>(__uint_as_float(cur[1]), b0.y);
+                            v[2] = activate_biased<ACT>(__uint_as_float(cur[2]), b0.z); v[3] = activate_biased<ACT>(__uint_as_float(cur[3]), b0.w);
+                            v[4] = activate_biased<ACT>(__uint_as_float(cur[4]), b1.x); v[5] = activate_biased<ACT>(__uint_as_float(cur[5]), b1.y);
+                            v[6] = activate_biased<ACT>(__uint_as_float(cur[6]), b1.z); v[7] = activate_biased<ACT>(__uint_as_float(cur[7]), b1.w);
+                        }
+                        if ((VAR == kVarSave || VAR == kVarDgrad) && grow_cur < P.rows) {
+                            float4* dst = reinterpret_cast<float4*>(P.act_out[layer] + (size_t)grow_cur * kH + j * kKB + w.sub * 8);
+                            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                        }
+                        const uint32_t as = ait % kLoStages, au = ait / kLoStages;
+                        mbar_wait(bar(A_EMPTY0 + as), (au & 1) ^ 1);
+                        store_split8_tmem(src + (uint32_t)(j * kKB), smem + kSmemLoRing + as * kATile, w.row, w.sub, v);
+                        fence_proxy_async();
+                        tc_fence_before();
+                        mbar_arrive(bar(A_FULL0 + as));
+                        if (kPrefetch && j + 1 < kH / kKB) tmem_wait8(nxt);
+                    }
+                    if (layer == 0 && t + 1 < n_items) {
+                        // next item's stage input (A1 is free: this item's layer 1 has completed)
+                        prologue(P, item_at(npass, nxt), !ADAPT && gbase == 0 && npass == 0, smem, w, ntile, x_adapt(), kmap_now());
+                        mbar_arrive(bar(A1_FULL));
+                    }
+                }
+                // ---- output: k_out = D3 + b3 (and x_new for the last stage of a fixed-step method)
+                mbar_wait(bar(D3_FULL), tpar);
+                tc_fence_after();
+                uint32_t ro[8];
+                tmem_ld8(w.lane_addr + kColD3 + (uint32_t)(w.sub * 8), ro);
+                tmem_wait8(ro);
+                tc_fence_before();
+                mbar_arrive(bar(D_FREE));
+                const int64_t grow = tile * kTileM + w.row;
                 if (grow < P.rows) {
                     const size_t goff = (size_t)grow * kD + w.sub * 8;
-                    float y[8];
-                    combine_row8(P, kUpd, P.xw, __ldg(P.dts + P.n_steps - 1), goff, true, y);
-                    store_row8(P.out + (size_t)__ldg(P.slots + P.n_steps) * P.n_state, goff, y);
+                    float o[8];
+                    float* k_out = ADAPT ? const_cast<float*>(kbuf(P, kmap_now(), item_at(pass, cur).g))
+                                         : (P.solve ? const_cast<float*>(P.kp[cur.g]) : P.k_out0);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float4 bq = *reinterpret_cast<const float4*>(smem + kSmemBias + (2 * kH + w.sub * 8 + 4 * i) * 4);
+                        // (init_step's trial evaluation is the UN-negated field also on reversed spans: odeint.py:66 hands f, not f_)
+                        const float sc = VAR == kVarPlain ? 1.f : ((ADAPT && cv->phase == 1) ? 1.f : P.out_scale);
+                        o[4 * i] = sc * (__uint_as_float(ro[4 * i]) + bq.x); o[4 * i + 1] = sc * (__uint_as_float(ro[4 * i + 1]) + bq.y);
+                        o[4 * i + 2] = sc * (__uint_as_float(ro[4 * i + 2]) + bq.z); o[4 * i + 3] = sc * (__uint_as_float(ro[4 * i + 3]) + bq.w);
+                        reinterpret_cast<float4*>(k_out + goff)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    }
+                    if (P.x_new) {
+                        // x + dt*(b0*k0 + ... + b_last*k_out)
+                        float s[8];
+                        for (int j = 0; j < P.n_sol; ++j) {
+                            const float b = P.bsol.c[j];
+                            const bool last = j == P.n_sol - 1;
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                float4 q;
+                                if (last) q = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                                else q = __ldg(reinterpret_cast<const float4*>(P.kp[j] + goff) + i);
+                                const float m0 = mul_rn(b, q.x), m1 = mul_rn(b, q.y), m2 = mul_rn(b, q.z), m3 = mul_rn(b, q.w);
+                                s[4 * i] = j == 0 ? m0 : add_rn(s[4 * i], m0);
+                                s[4 * i + 1] = j == 0 ? m1 : add_rn(s[4 * i + 1], m1);
+                                s[4 * i + 2] = j == 0 ? m2 : add_rn(s[4 * i + 2], m2);
+                                s[4 * i + 3] = j == 0 ? m3 : add_rn(s[4 * i + 3], m3);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const float4 xq = __ldg(reinterpret_cast<const float4*>(P.x_in + goff) + i);
+                            reinterpret_cast<float4*>(P.x_new + goff)[i] =
+                                make_float4(add_rn(xq.x, mul_rn(P.dt0, s[4 * i])), add_rn(xq.y, mul_rn(P.dt0, s[4 * i + 1])),
+                                            add_rn(xq.z, mul_rn(P.dt0, s[4 * i + 2])), add_rn(xq.w, mul_rn(P.dt0, s[4 * i + 3])));
+                        }
+                    }
                 }
+                pass = npass; tl = ntl; cur = nxt;
+            }
+            // ================= end of the batch
+            if constexpr (ADAPT) adaptive_batch_end(P, ctrl, batch_n, red_sm, my_tiles);
+        }
+        if constexpr (!ADAPT) break;
+        gbase += n_items;
+    }
+    if (warp >= 2 && !ADAPT && P.solve) {
+        // solve mode: the closing combination x_final = x + dt*(sum_j bsol_j k_j) of the last step (no evaluation)
+        for (int i = 0; i < my_tiles; ++i) {
+            const int64_t grow = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTileM + w.row;
+            if (grow < P.rows) {
+                const size_t goff = (size_t)grow * kD + w.sub * 8;
+                float y[8];
+                combine_row8(P, P.st[kUpd], P.xw, __ldg(P.dts + P.n_steps - 1), goff, true, y);
+                store_row8(P.out + (size_t)__ldg(P.slots + P.n_steps) * P.n_state, goff, y);
             }
         }
     }
@@ -795,6 +1130,80 @@ int tdyn_mlp_tc_solve_fixed(const tdyn_mlp_t* m, const void* wsplit, const tdyn_
     int grid = P.num_tiles / 2;
     if (grid > kNumSMs) grid = kNumSMs;
     return launch_tc(m, P, grid, st);
+}
+
+// ------------------------------------------------------------------------------------------- whole adaptive solve
+int64_t tdyn_mlp_tc_adaptive_workspace_bytes(void) {
+    return 4096 /* t_span */ + 256 /* grid barrier */ + (int64_t)sizeof(double) * 2 * 2 * kNumSMs;
+}
+
+int tdyn_mlp_tc_solve_adaptive(const tdyn_mlp_t* m, const void* wsplit, const tdyn_rk_plan_t* plan, float sign, float atol,
+                               float rtol, const float* t_span, int n_t, int return_all, float dt0, float* x0, float* x1,
+                               float* k, float* out, float* t_out, int out_cap, void* workspace, int* status, float* trace,
+                               int trace_cap, int64_t rows, int max_steps, void* stream) {
+    TDYN_REQUIRE(m && plan && wsplit && t_span && x0 && x1 && k && out && t_out && workspace && status,
+                 "tdyn_mlp_tc_solve_adaptive: null argument");
+    TDYN_REQUIRE(tdyn_mlp_tc_solve_supported(m, rows), "tdyn_mlp_tc_solve_adaptive: unsupported MLP shape or too few rows");
+    TDYN_REQUIRE(plan->n_extra >= 1 && plan->n_extra <= TDYN_MAX_STAGES - 1 && plan->n_err == plan->n_extra + 1 &&
+                     plan->n_sol >= 1 && plan->n_sol <= plan->n_extra + 1,
+                 "tdyn_mlp_tc_solve_adaptive: need an embedded FSAL pair (dopri5 / tsit5)");
+    TDYN_REQUIRE(n_t >= 2 && n_t <= 1024 && t_span[n_t - 1] > t_span[0], "tdyn_mlp_tc_solve_adaptive: need 2..1024 increasing times");
+    TDYN_REQUIRE(out_cap >= 1 && max_steps >= 1, "tdyn_mlp_tc_solve_adaptive: out_cap and max_steps must be positive");
+    TDYN_REQUIRE((((uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)k | (uintptr_t)out | (uintptr_t)workspace) & 15) == 0,
+                 "tdyn_mlp_tc_solve_adaptive: pointers must be 16-byte aligned");
+    const int n_stage = plan->n_extra + 1;
+    const size_t n_state = (size_t)rows * tc::kD;
+    tc::Params P{};
+    auto fill = [&](tc::StagePlan& sp, int mode, int n, const float* c, bool drop_zeros) {
+        sp.n_k = 0; sp.mode = mode;
+        for (int j = 0; j < n; ++j)
+            if (!drop_zeros || c[j] != 0.f) { sp.kidx[sp.n_k] = j; sp.coef[sp.n_k] = c[j]; ++sp.n_k; }
+    };
+    for (int g = 1; g < n_stage; ++g) {
+        TDYN_REQUIRE(plan->nk[g - 1] >= 0 && plan->nk[g - 1] <= g, "tdyn_mlp_tc_solve_adaptive: stage %d combines later stages", g);
+        fill(P.st[g], plan->mode[g - 1], plan->nk[g - 1], plan->a[g - 1], true);
+    }
+    const float one = 1.f;
+    fill(P.st[0], TDYN_MODE_CHAIN, 1, &one, false);                       // init_step's trial point x0 + h0*k1
+    fill(P.st[tc::kUpd], TDYN_MODE_INNER, plan->n_sol, plan->bsol, false);
+    for (int g = 0; g < n_stage; ++g) P.kp[g] = k + (size_t)g * n_state;
+    P.n_err = plan->n_err;
+    for (int j = 0; j < plan->n_err; ++j) P.berr.c[j] = plan->berr[j];
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)workspace;
+    TDYN_CHECK_CUDA(cudaMemcpyAsync(ws, t_span, sizeof(float) * (size_t)n_t, cudaMemcpyHostToDevice, st));
+    TDYN_CHECK_CUDA(cudaMemsetAsync(ws + 4096, 0, 256, st));
+    TDYN_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 6, st));
+    // the first output is the initial state at t_span[0]
+    TDYN_CHECK_CUDA(cudaMemcpyAsync(out, x0, sizeof(float) * n_state, cudaMemcpyDeviceToDevice, st));
+    TDYN_CHECK_CUDA(cudaMemcpyAsync(t_out, ws, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    P.wimg = (const uint8_t*)wsplit;
+    P.b1 = m->b[0]; P.b2 = m->b[1]; P.b3 = m->b[2];
+    P.xbuf[0] = x0; P.xbuf[1] = x1; P.out = out; P.t_out = t_out; P.status = status; P.trace = trace;
+    P.trace_cap = trace ? trace_cap : 0;
+    P.t_span = (const float*)ws; P.n_t = n_t; P.return_all = return_all; P.out_cap = out_cap; P.max_steps = max_steps;
+    P.order = plan->order; P.t_dt0 = dt0; P.atol = atol; P.rtol = rtol;
+    P.safety = plan->safety; P.min_factor = plan->min_factor; P.max_factor = plan->max_factor;
+    P.gbar = (unsigned int*)(ws + 4096); P.partials = (double*)(ws + 4096 + 256);
+    P.n_state = n_state; P.n_stage = n_stage; P.n_steps = 1; P.solve = 1; P.out_scale = sign;
+    P.rows = rows;
+    P.num_tiles = (int)((rows + tc::kTileM - 1) / tc::kTileM);
+    P.act = m->act;
+    int grid = P.num_tiles / 2;
+    if (grid > kNumSMs) grid = kNumSMs;
+    static thread_local unsigned long long seen = 0;
+    if (first_use_on_device(seen)) {
+        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_TANH, tc::kVarAdaptive>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
+        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_SOFTPLUS, tc::kVarAdaptive>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
+        TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_RELU, tc::kVarAdaptive>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));
+    }
+    const void* fn = m->act == TDYN_ACT_TANH ? (const void*)tc::mlp_tc_stage_kernel<TDYN_ACT_TANH, tc::kVarAdaptive>
+                   : m->act == TDYN_ACT_SOFTPLUS ? (const void*)tc::mlp_tc_stage_kernel<TDYN_ACT_SOFTPLUS, tc::kVarAdaptive>
+                                                 : (const void*)tc::mlp_tc_stage_kernel<TDYN_ACT_RELU, tc::kVarAdaptive>;
+    void* args[] = {(void*)&P};
+    // cooperative: the in-kernel grid barrier needs every CTA resident (one per SM)
+    TDYN_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(tc::kThreads), args, tc::kSmemTotal, st));
+    return 0;
 }
 
 }  // extern "C"

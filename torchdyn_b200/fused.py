@@ -613,7 +613,11 @@ def try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, s
     if not isinstance(inner, FusedField):
         return None
     fm, kern = inner.fm, inner.kern
-    if not (x.dim() == 2 and x.is_contiguous() and x.shape[1] == fm.dims[0] and kern.mlp_solve_supported(fm._desc, False)):
+    if not (x.dim() == 2 and x.is_contiguous() and x.shape[1] == fm.dims[0]):
+        return None
+    if fm.ready(kern):
+        return _try_adaptive_tc(inner, sign, x, ts, solver, atol, rtol, return_all_eval)
+    if not kern.mlp_solve_supported(fm._desc, False):
         return None
     comm = None
     if _dist.is_enabled():
@@ -647,6 +651,44 @@ def try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, s
     _kernels.credit_work("mlp_solve", fm.flops_per_row * rows * nfe)
     _emit_trace(trace, n_attempt)
     _last = "persistent fused MLP integrator (tdyn_mlp_solve)" + (", error norm exchanged by NVLink peer stores" if comm else "")
+    return t_out[:n_out], out[:n_out]
+
+
+ADAPTIVE_TC = True        # adaptive solves of the 32-256-256-32 class: one cooperative launch (False: host-driven loop)
+
+
+def _try_adaptive_tc(inner, sign, x, ts, solver, atol, rtol, return_all_eval):
+    """Adaptive solve of the 32-256-256-32 class in ONE launch of the tensor-core stage kernel
+    (``tdyn_mlp_tc_solve_adaptive``: k1, init_step, every attempted step with its error norm and the controller)."""
+    global _last
+    from . import distributed as _dist
+    fm, kern = inner.fm, inner.kern
+    rows, D = x.shape
+    n_t = len(ts)
+    if not ADAPTIVE_TC or _dist.is_enabled() or n_t > MAX_T_SPAN or not (ts[-1] > ts[0]) or x.data_ptr() % 16 \
+            or not kern.mlp_tc_solve_supported(fm._desc, rows):
+        return None
+    cap = n_t + (512 if return_all_eval else 0)
+    dev = x.device
+    x0 = x.clone()
+    x1, k, status, trace, ws = fm.scratch(("adaptive_tc", rows, dev.index), lambda: (
+        torch.empty_like(x), torch.empty(7 * rows * D, dtype=torch.float32, device=dev),
+        torch.zeros(8, dtype=torch.int32, device=dev), torch.empty(TRACE_CAP, dtype=torch.float32, device=dev),
+        kern.mlp_tc_adaptive_workspace()))
+    out = torch.empty(cap, rows, D, dtype=torch.float32, device=dev)       # returned to the caller: always fresh
+    t_out = torch.empty(cap, dtype=torch.float32, device=dev)
+    t_host = np.ascontiguousarray(ts, dtype=np.float32)
+    kern.mlp_tc_solve_adaptive(fm._desc, fm._img, _rk_plan(solver), sign, atol, rtol, t_host, return_all_eval, 0.0, x0, x1, k,
+                               out, t_out, cap, ws, status, trace, rows, MAX_STEPS)
+    st = status.cpu().tolist()
+    n_out, n_attempt, nfe, err = st[0], st[1], st[3], st[4]
+    if err != 0 or n_out == 0:
+        return None                          # output buffer full / more than MAX_STEPS attempts / NaN: the host loop redoes it
+    for c in inner.counters:
+        c.nfe += nfe
+    _kernels.credit_work("mlp_tc_adaptive", fm.flops_per_row * rows * nfe)
+    _emit_trace(trace, n_attempt)
+    _last = "persistent fused tcgen05 adaptive integrator (tdyn_mlp_tc_solve_adaptive)"
     return t_out[:n_out], out[:n_out]
 
 
