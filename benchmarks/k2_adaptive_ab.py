@@ -37,6 +37,7 @@ def main():
             p.mul_(a.gain)
     x = torch.randn(a.rows, 32, device=dev)
     fld = fused.MLPField(net)
+    fused.ADAPTIVE_TC_MAX_ROWS = None        # A/B at every size
     ts = torch.tensor([0.0, a.t1])
     res = {True: [], False: []}
     nfe = {}

@@ -877,14 +877,15 @@ def test_adaptive_tc_integrator_matches_the_host_driven_loop(solver, rows, ts, k
     fld = fused.MLPField(net)
     res = {}
     for flag in (True, False):
-        fused.ADAPTIVE_TC = flag
+        fused.ADAPTIVE_TC, keep = flag, fused.ADAPTIVE_TC_MAX_ROWS
+        fused.ADAPTIVE_TC_MAX_ROWS = None                  # (the size heuristic is not under test)
         om.TRACE_SINK = tr = []
         fld.nfe = 0
         try:
             with torch.no_grad():
                 t_eval, sol = odeint(fld, x, torch.tensor(ts), solver, atol=1e-3, rtol=1e-3, **kw)
         finally:
-            fused.ADAPTIVE_TC = True
+            fused.ADAPTIVE_TC, fused.ADAPTIVE_TC_MAX_ROWS = True, keep
             om.TRACE_SINK = None
         assert ("tdyn_mlp_tc_solve_adaptive" in fused.last_used()) == flag, fused.last_used()
         res[flag] = (t_eval, sol, tr[0], fld.nfe)

@@ -785,26 +785,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
                     tc_fence_after();
                     const float* bias = reinterpret_cast<const float*>(smem + kSmemBias) + layer * kH + w.sub * 8;
                     const uint32_t src = w.lane_addr + (layer == 0 ? kColD1 : kColD2) + (uint32_t)(w.sub * 8);
-                    // (the adaptive variant has no registers for the second buffer: it loads each chunk when it needs it)
+                    // (the adaptive variant has no registers for a second buffer: it re-issues the load of the next chunk into
+                    // the SAME registers as soon as the activation has consumed them, so that the TMEM read overlaps the
+                    // split / store half of the chunk)
                     constexpr bool kPrefetch = !ADAPT;
                     uint32_t ra[8], rb[kPrefetch ? 8 : 1];
-                    if (kPrefetch) {
-                        tmem_ld8(src, ra);
-                        tmem_wait8(ra);
-                    }
+                    tmem_ld8(src, ra);
+                    if (kPrefetch) tmem_wait8(ra);
 #pragma unroll
                     for (int j = 0; j < kH / kKB; ++j, ++ait) {
                         uint32_t (&cur)[8] = (kPrefetch && (j & 1)) ? reinterpret_cast<uint32_t (&)[8]>(rb) : ra;
                         uint32_t (&nxt)[8] = (kPrefetch && !(j & 1)) ? reinterpret_cast<uint32_t (&)[8]>(rb) : ra;
-                        if (kPrefetch ? j + 1 < kH / kKB : true) {
-                            const int jl = kPrefetch ? j + 1 : j;                // the chunk loaded now
-                            if (layer == 0 && jl * kKB == kNSplit) {             // last chunk of D1 is produced by layer1b
+                        if (kPrefetch && j + 1 < kH / kKB) {
+                            if (layer == 0 && (j + 1) * kKB == kNSplit) {       // last chunk of D1 is produced by layer1b
                                 mbar_wait(bar(D1B_FULL), tpar);
                                 tc_fence_after();
                             }
-                            tmem_ld8(src + (uint32_t)(jl * kKB), nxt);           // prefetch next chunk / load this one
-                            if (!kPrefetch) tmem_wait8(nxt);
+                            tmem_ld8(src + (uint32_t)((j + 1) * kKB), nxt);     // prefetch next chunk
                         }
+                        if (!kPrefetch) tmem_wait8(ra);
                         float v[8];
                         if (VAR == kVarDgrad) {
                             // delta = acc * act'(saved activation): epilogue 0 pairs with a2, epilogue 1 with a1
@@ -824,6 +823,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
                             v[2] = activate_biased<ACT>(__uint_as_float(cur[2]), b0.z); v[3] = activate_biased<ACT>(__uint_as_float(cur[3]), b0.w);
                             v[4] = activate_biased<ACT>(__uint_as_float(cur[4]), b1.x); v[5] = activate_biased<ACT>(__uint_as_float(cur[5]), b1.y);
                             v[6] = activate_biased<ACT>(__uint_as_float(cur[6]), b1.z); v[7] = activate_biased<ACT>(__uint_as_float(cur[7]), b1.w);
+                        }
+                        if (!kPrefetch && j + 1 < kH / kKB) {
+                            if (layer == 0 && (j + 1) * kKB == kNSplit) {
+                                mbar_wait(bar(D1B_FULL), tpar);
+                                tc_fence_after();
+                            }
+                            tmem_ld8(src + (uint32_t)((j + 1) * kKB), ra);      // the activation has consumed ra
                         }
                         if ((VAR == kVarSave || VAR == kVarDgrad) && grow_cur < P.rows) {
                             float4* dst = reinterpret_cast<float4*>(P.act_out[layer] + (size_t)grow_cur * kH + j * kKB + w.sub * 8);
