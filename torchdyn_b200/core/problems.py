@@ -9,6 +9,7 @@ MultipleShootingProblem / SDEProblem are outside this implementation.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Callable, Generator, Iterable, Union
 
 import torch
@@ -21,6 +22,9 @@ from ..numerics.solvers.ode import str_to_solver
 from .utils import standardize_vf_call_signature
 
 _SENSITIVITIES = ("autograd", "adjoint", "interpolated_adjoint")
+# ODEProblem -> (configuration key, autograd Function class): building the class costs ~0.1 ms per forward otherwise; kept
+# off the module so that it stays picklable
+_FN_CACHE = weakref.WeakKeyDictionary()
 
 
 class ODEProblem(nn.Module):
@@ -68,9 +72,16 @@ class ODEProblem(nn.Module):
             gather = _gather_odefunc_interp_adjoint
         else:
             return None
-        return gather(self.vf, self.vf_params, self.solver, self.atol, self.rtol, self.interpolator,
-                      self.solver_adjoint, self.atol_adjoint, self.rtol_adjoint, self.integral_loss,
-                      problem_type="standard").apply
+        # (the Function closes over the configuration, not over vf_params: re-used until an attribute is re-assigned)
+        key = (gather, id(self.vf), id(self.solver), self.atol, self.rtol, id(self.interpolator) if not isinstance(self.interpolator, str) else self.interpolator,
+               id(self.solver_adjoint), self.atol_adjoint, self.rtol_adjoint, id(self.integral_loss))
+        hit = _FN_CACHE.get(self)
+        if hit is None or hit[0] != key:
+            hit = (key, gather(self.vf, self.vf_params, self.solver, self.atol, self.rtol, self.interpolator,
+                               self.solver_adjoint, self.atol_adjoint, self.rtol_adjoint, self.integral_loss,
+                               problem_type="standard"))
+            _FN_CACHE[self] = hit
+        return hit[1].apply
 
     def odeint(self, x: Tensor, t_span: Tensor, save_at: Tensor = (), args={}):
         "Returns Tuple(`t_eval`, `solution`)"

@@ -242,10 +242,13 @@ class FusedMLP:
             d.w[i] = m.weight.data_ptr()
             d.b[i] = m.bias.data_ptr()
         self._key, self._desc, self._img, self._wide_imgs, self._tc_t = key, d, None, None, None
-        self._tc_ok = kern.mlp_tc_supported(d)
-        self._ffma_ok = kern.mlp_ffma_supported(d)
-        self._wide_ok = not self._ffma_ok and all(kern.lin_tc_supported(o, i) and kern.lin_tc_supported(i, o)
-                                                  for i, o in zip(self.dims[:-1], self.dims[1:]))
+        if self.__dict__.get("_shape_flags") is None:
+            # which kernel family takes this net depends on its layer widths and activation only
+            ffma = kern.mlp_ffma_supported(d)
+            self._shape_flags = (kern.mlp_tc_supported(d), ffma,
+                                 not ffma and all(kern.lin_tc_supported(o, i) and kern.lin_tc_supported(i, o)
+                                                  for i, o in zip(self.dims[:-1], self.dims[1:])))
+        self._tc_ok, self._ffma_ok, self._wide_ok = self._shape_flags
         if self._tc_ok:
             self._img = kern.mlp_tc_prepare(d)
         return True

@@ -161,7 +161,7 @@ def _gather_odefunc_adjoint(vf, vf_params, solver, atol, rtol, interpolator, sol
             sol, t_sol = ctx.saved_tensors
             th = ctx.t_host
             g_t, g_sol = grad_output[0], grad_output[-1]
-            P = _flat(vf).numel()
+            P = sum(p.numel() for p in vf.parameters())
             xT, lamT = sol[-1], g_sol[-1]
             n = xT.numel()
             from .. import fused
@@ -170,7 +170,7 @@ def _gather_odefunc_adjoint(vf, vf_params, solver, atol, rtol, interpolator, sol
             A = torch.cat([xT.flatten(), lam_flat, torch.zeros(P, dtype=xT.dtype, device=xT.device), lam_t[None]])
             dyn = BacksolveDynamics(vf, xT.shape, lamT.shape, P, integral_loss, device=xT.device)
 
-            dLdt = torch.zeros(len(th)).to(xT)
+            dLdt = torch.zeros(len(th), dtype=xT.dtype, device=xT.device)
             dLdt[-1] = lam_t
             for i in range(len(th) - 1, 0, -1):
                 last = fused.try_adjoint_interval(dyn, A, th[i], th[i - 1], solver_adjoint, atol_adjoint, rtol_adjoint)
@@ -209,7 +209,7 @@ def _gather_odefunc_interp_adjoint(vf, vf_params, solver, atol, rtol, interpolat
             sol, t_sol = ctx.saved_tensors
             span = ctx.span_host
             g_sol = grad_output[-1]
-            P = _flat(vf).numel()
+            P = sum(p.numel() for p in vf.parameters())
             lamT = g_sol[-1]
             n = lamT.numel()
             A = torch.cat([lamT.flatten(), torch.zeros(P, dtype=lamT.dtype, device=lamT.device)])
