@@ -46,6 +46,11 @@ extern "C" {
 TDYN_API int tdyn_version(void);
 TDYN_API const char* tdyn_last_error(void);
 
+/* Measurement aid (bench.py): runs `iters` x 64 dependent-chain FP32 FMAs per thread with register operands on a full grid
+ * and reports the FLOPs issued; timed by the caller with CUDA events, it gives the FP32 FMA rate this GPU sustains -- the
+ * denominator of the FFMA kernels' roofline.  `out`: one device float (never written). */
+TDYN_API int tdyn_probe_ffma(float* out, int iters, double* flops_out, void* stream);
+
 /* bytes of zero-initialised device scratch every reducing entry point needs (partials + ticket). */
 TDYN_API int64_t tdyn_reduce_workspace_bytes(void);
 

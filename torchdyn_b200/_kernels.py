@@ -330,6 +330,22 @@ class CudaKernels:
         _lib.check(rc, "tdyn_mlp_tc_solve_fixed")
         _launches += 1
 
+    def probe_ffma_tflops(self, iters: int = 4096, reps: int = 5) -> float:
+        """Sustained FP32 FMA rate of this GPU in TFLOP/s (register-operand FFMA chains on a full grid, CUDA events, best
+        of `reps`): the measured denominator of the FFMA kernels' roofline."""
+        out = torch.zeros(1, dtype=torch.float32, device=self.device)
+        flops = C.c_double(0.0)
+        best = 0.0
+        for rep in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(self.lib.tdyn_probe_ffma(out.data_ptr(), int(iters), C.byref(flops), self._stream()), "tdyn_probe_ffma")
+            e1.record()
+            e1.synchronize()
+            if rep > 0:
+                best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        return best
+
     def mlp_tc_adaptive_workspace(self) -> Tensor:
         return torch.empty(int(self.lib.tdyn_mlp_tc_adaptive_workspace_bytes()), dtype=torch.uint8, device=self.device)
 

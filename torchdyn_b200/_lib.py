@@ -47,6 +47,7 @@ class Comm(C.Structure):
 # name -> (restype, argtypes); every symbol include/tdyn_b200.h declares
 SIGNATURES = {
     "tdyn_version": (C.c_int, []),
+    "tdyn_probe_ffma": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
     "tdyn_last_error": (C.c_char_p, []),
     "tdyn_reduce_workspace_bytes": (C.c_int64, []),
     "tdyn_rk_combine": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp, c_float_p, C.c_int, C.c_int, C.c_float,

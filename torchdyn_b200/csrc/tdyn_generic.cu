@@ -373,9 +373,37 @@ __global__ void __launch_bounds__(kThreads) spline_eval_kernel(float* __restrict
 
 using namespace tdyn;
 
+// Measurement aid: the FP32 FMA issue rate this GPU sustains with register operands (16 independent chains per thread,
+// 8 blocks of 256 threads per SM), the denominator of the FFMA kernels' roofline (no driver-written peak exists for it).
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float* out, int iters, float b, float c) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
+    const float bb = b + (float)(threadIdx.x & 1) * 1e-6f, cc = c + (float)(blockIdx.x & 1) * 1e-6f;     // registers, not immediates
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], bb, cc);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456f) out[0] = s;             // never true: keeps the chains alive
+}
+
 extern "C" {
 
 int tdyn_version(void) { return TDYN_ABI_VERSION; }
+
+int tdyn_probe_ffma(float* out, int iters, double* flops_out, void* stream) {
+    TDYN_REQUIRE(out && iters > 0, "tdyn_probe_ffma: bad argument");
+    const int grid = kNumSMs * 8;
+    ffma_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 1e-4f);
+    TDYN_CHECK_CUDA(cudaGetLastError());
+    if (flops_out) *flops_out = 2.0 * 64.0 * (double)iters * 256.0 * (double)grid;
+    return 0;
+}
 const char* tdyn_last_error(void) { return g_err; }
 int64_t tdyn_reduce_workspace_bytes(void) { return (int64_t)sizeof(ReduceWs); }
 
