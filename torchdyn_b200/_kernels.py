@@ -97,6 +97,9 @@ def _ptr(t: Optional[Tensor]):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or (lambda idx: torch.cuda.current_stream(idx).cuda_stream)
+
+
 def _on_own_device(fn):
     """The C entry points launch on the calling thread's CURRENT device; a state on cuda:1 while cuda:0 is current is
     ordinary PyTorch usage, so every launching method switches to the instance's device for the duration of the call."""
@@ -136,7 +139,8 @@ class CudaKernels:
 
     # -- helpers ------------------------------------------------------------------------------
     def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        # (the raw handle of PyTorch's current stream on this device: ~0.3 us, against ~8 us for the Stream object)
+        return _raw_stream(self.device.index)
 
     @staticmethod
     def _chk(t: Tensor, name: str):
