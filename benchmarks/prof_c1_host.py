@@ -20,4 +20,4 @@ print("ms/iter", 1e3*(time.perf_counter()-t0)/200)
 pr = cProfile.Profile(); pr.enable()
 for _ in range(200): it()
 torch.cuda.synchronize(); pr.disable()
-s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(45); print(s.getvalue()[:9000])
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(40); print(s.getvalue()[:9000])

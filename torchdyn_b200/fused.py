@@ -34,6 +34,18 @@ def reset_last():
     _last = None
 
 
+
+def _bump(counters, n):
+    """``c.nfe += n`` for every wrapper in ``counters``.  ``nfe`` is a plain float attribute; writing it through
+    ``nn.Module.__setattr__`` costs ~6 us per wrapper and call, so it goes straight into the instance dict."""
+    for c in counters:
+        d = c.__dict__
+        if "nfe" in d:
+            d["nfe"] += n
+        else:
+            c.nfe += n
+
+
 class MLPField(nn.Module):
     """Functional-API helper: ``odeint(MLPField(net), x, t_span, ...)`` == ``odeint(lambda t, x: net(x), ...)`` but
     lets the library see (and fuse) the network."""
@@ -303,8 +315,7 @@ class FusedField:
             kern.mlp_ffma_forward(fm._desc, y, out, sign, fm.flops_per_row)
         else:
             wide_forward(fm, kern, y, out, sign)
-        for c in self.counters:
-            c.nfe += 1
+        _bump(self.counters, 1)
         return out
 
 
@@ -382,8 +393,7 @@ class FusedWideAdjoint:
                 i, o = dims[l], dims[l + 1]
                 ws = fm.scratch(("wgrad", l, rows, x_flat.device.index), lambda: kern.wgrad_tc_workspace(o, i, rows))
                 kern.wgrad_tc(gl, o, inp, i, dmu_out[offs[l]:offs[l] + o * i], dmu_out[offs[l] + o * i:offs[l] + o * i + o], -sign, ws, rows)
-            for c in self.counters:
-                c.nfe += 1
+            _bump(self.counters, 1)
             return
         g = lam_flat
         for l in range(len(fm.linears) - 1, -1, -1):
@@ -400,8 +410,7 @@ class FusedWideAdjoint:
                 kern.lin_tc_apply(imgs[0][1], i, o, g, None, None, dl, fm.act, LIN_MODE_LINEAR, -sign, rows)
                 if dl is not dlam_out:
                     dlam_out.view(-1).copy_(dl.view(-1))
-        for c in self.counters:
-            c.nfe += 1
+        _bump(self.counters, 1)
 
 
 class FusedCNFField:
@@ -426,8 +435,7 @@ class FusedCNFField:
             out = self.f(kern.time_tensor(t_host, s), s)
             return out if sign == 1.0 else -out
         out = kern.cnf_ffma_forward(fm._desc, s, eps, torch.empty_like(s), sign, fm.flops_per_row)
-        for c in self.counters:
-            c.nfe += 1
+        _bump(self.counters, 1)
         return out
 
 
@@ -442,8 +450,7 @@ class FusedCNFAdjoint:
         fm = self.fm
         self.kern.cnf_ffma_adjoint(fm._desc, s_flat, lam_flat, self.cnf.noise, ds_out, dlam_out, dmu_out, fm.workspace(self.kern),
                                    rows, sign, fm.flops_per_row)
-        for c in self.counters:
-            c.nfe += 1
+        _bump(self.counters, 1)
 
 
 def _get_fused_cnf(f):
@@ -500,8 +507,7 @@ def eval_field(vf, t, x):
                     kern.mlp_ffma_forward(fm._desc, x, out, 1.0, fm.flops_per_row)
                 else:
                     wide_forward(fm, kern, x, out, 1.0)
-                for c in counters:
-                    c.nfe += 1
+                _bump(counters, 1)
                 return out
     return vf(t, x)
 
@@ -517,8 +523,7 @@ class FusedAdjoint:
         fm = self.fm
         self.kern.mlp_ffma_adjoint(fm._desc, x_flat, lam_flat, dx_out, dlam_out, dmu_out, fm.workspace(self.kern), rows,
                                    sign, fm.flops_per_row)
-        for c in self.counters:
-            c.nfe += 1
+        _bump(self.counters, 1)
 
 
 def adjoint_for(vf, x_shape, device) -> Optional[FusedAdjoint]:
@@ -649,8 +654,7 @@ def try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, s
         # solve, or a NaN error estimate).  Either way the host loop redoes the solve from x: it has the reference's
         # limits and raises on a NaN step size.
         return None
-    for c in inner.counters:
-        c.nfe += nfe
+    _bump(inner.counters, nfe)
     _kernels.credit_work("mlp_solve", fm.flops_per_row * rows * nfe)
     _emit_trace(trace, n_attempt)
     _last = "persistent fused MLP integrator (tdyn_mlp_solve)" + (", error norm exchanged by NVLink peer stores" if comm else "")
@@ -693,8 +697,7 @@ def _try_adaptive_tc(inner, sign, x, ts, solver, atol, rtol, return_all_eval):
     n_out, n_attempt, nfe, err = st[0], st[1], st[3], st[4]
     if err != 0 or n_out == 0:
         return None                          # output buffer full / more than MAX_STEPS attempts / NaN: the host loop redoes it
-    for c in inner.counters:
-        c.nfe += nfe
+    _bump(inner.counters, nfe)
     _kernels.credit_work("mlp_tc_adaptive", fm.flops_per_row * rows * nfe)
     _emit_trace(trace, n_attempt)
     _last = "persistent fused tcgen05 adaptive integrator (tdyn_mlp_tc_solve_adaptive)"
@@ -733,8 +736,7 @@ def try_adjoint_interval(dyn, A, t_from, t_to, solver, atol, rtol):
     st = status.cpu().tolist()
     if st[4] != 0:
         return None                          # more than MAX_STEPS attempts: the host loop redoes the interval from A
-    for c in fa.counters:
-        c.nfe += st[3]
+    _bump(fa.counters, st[3])
     _kernels.credit_work("mlp_solve", 3.0 * fm.flops_per_row * rows * st[3])
     _emit_trace(trace, st[1])
     return y0 if st[5] == 0 else y1
@@ -766,8 +768,7 @@ def try_interp_interval(dyn, A, t_from, t_to, solver, atol, rtol):
     st = status.cpu().tolist()
     if st[4] != 0:
         return None                          # more than MAX_STEPS attempts: the host loop redoes the interval from A
-    for c in fa.counters:
-        c.nfe += st[3]
+    _bump(fa.counters, st[3])
     _kernels.credit_work("mlp_solve_interp", 3.0 * fm.flops_per_row * rows * st[3])
     _emit_trace(trace, st[1])
     return y0 if st[5] == 0 else y1
@@ -817,8 +818,7 @@ def try_fixed(f, x, ts, sv, solver) -> Optional[List[torch.Tensor]]:
             xw, kbuf = fm.scratch(("solve_fixed", x.shape[0], n_stage, x.device.index), lambda: (
                 torch.empty_like(x), torch.empty(n_stage, *x.shape, dtype=torch.float32, device=x.device)))
             kern.mlp_tc_solve_fixed(fm._desc, fm._img, _rk_plan(solver), x, xw, kbuf, out, dts, slot, n_stage, fm.flops_per_row)
-            for c in counters:
-                c.nfe += n_stage * n_steps
+            _bump(counters, n_stage * n_steps)
             _last = "persistent fused tcgen05 split-precision (TF32 + bf16 corrections) fixed-step integrator (tdyn_mlp_tc_solve_fixed)"
             return ([x] if first else []) + list(out.unbind(0))
     ks = [torch.empty_like(x) for _ in range(n_stage)]
@@ -842,7 +842,6 @@ def try_fixed(f, x, ts, sv, solver) -> Optional[List[torch.Tensor]]:
             x, keep_x = x_new, saved
             if step < len(ts) - 1:
                 dt = f32(ts[step + 1] - t)
-    for c in counters:
-        c.nfe += n_stage * (len(ts) - 1)
+    _bump(counters, n_stage * (len(ts) - 1))
     _last = "fused tcgen05 split-precision (TF32 + bf16 corrections) MLP stage kernel (tdyn_mlp_tc_stage)"
     return sol
