@@ -855,11 +855,39 @@ def test_adaptive_tc_integrator_reproduces_the_reference_step_sequence(name):
         assert err <= max(10.0 * err_eager, 1e-5 * scale), (name, i, err, err_eager, scale)
 
 
+def test_adaptive_tc_integrator_limits_fall_back_to_the_host_loop():
+    """More attempts than one launch may take (fused.MAX_STEPS) or more accepted steps than the output buffer holds
+    (return_all_eval): the kernel reports it in its status word and the host-driven loop redoes the solve -- same result
+    as with the one-launch form switched off."""
+    from torchdyn_b200 import fused
+    torch.manual_seed(22)
+    net = build_mlp([32, 256, 256, 32], "tanh").to(DEV)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(5.0)
+    x = torch.randn(400, 32, device=DEV)
+    fld = fused.MLPField(net)
+    keep = fused.MAX_STEPS
+    try:
+        with torch.no_grad():
+            fused.MAX_STEPS = 3
+            t_a, s_a = odeint(fld, x, torch.tensor([0.0, 1.0]), "dopri5", atol=1e-3, rtol=1e-3)
+            assert "tdyn_mlp_tc_solve_adaptive" not in fused.last_used(), fused.last_used()
+            fused.MAX_STEPS = keep
+            fused.ADAPTIVE_TC = False
+            t_b, s_b = odeint(fld, x, torch.tensor([0.0, 1.0]), "dopri5", atol=1e-3, rtol=1e-3)
+    finally:
+        fused.MAX_STEPS, fused.ADAPTIVE_TC = keep, True
+    assert torch.equal(t_a, t_b) and torch.equal(s_a, s_b)
+
+
 @pytest.mark.parametrize("solver,rows,ts,kw", [
     ("dopri5", 300, [0.0, 1.0], {}),
     ("tsit5", 1000, [0.0, 0.3, 0.35, 1.2], {}),
     ("dopri5", 40001, [0.0, 0.5, 1.5], dict(return_all_eval=True)),
     ("tsit5", 777, [1.0, 0.4, 0.0], {}),
+    ("dopri5", 513, [0.0, 0.7], dict(act="softplus")),
+    ("tsit5", 2049, [0.0, 0.2, 0.9], dict(act="relu", return_all_eval=True)),
 ])
 def test_adaptive_tc_integrator_matches_the_host_driven_loop(solver, rows, ts, kw):
     """tdyn_mlp_tc_solve_adaptive against the host-driven loop over the same stage kernel (one launch per stage +
@@ -869,7 +897,8 @@ def test_adaptive_tc_integrator_matches_the_host_driven_loop(solver, rows, ts, k
     from torchdyn_b200 import fused
     om = sys.modules["torchdyn_b200.numerics.odeint"]
     torch.manual_seed(21)
-    net = build_mlp([32, 256, 256, 32], "tanh").to(DEV)
+    kw = dict(kw)
+    net = build_mlp([32, 256, 256, 32], kw.pop("act", "tanh")).to(DEV)
     with torch.no_grad():
         for p in net.parameters():
             p.mul_(5.0)
