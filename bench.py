@@ -14,7 +14,7 @@ ONE JSON line (rank 0): value (inputs resident in HBM), e2e (pinned host buffers
 timed region), roofline (dominant kernel, CUDA-event timed inside the timed region), cpu_baseline (the CPU oracle port on
 a bounded sub-batch), gpu_eager_baseline (the oracle's op sequence with CUDA tensors: "same box, no custom kernel"),
 clocks, gpu_launches -- and `configs`: the metric's own workloads measured in the same run,
-  N = 1:  c1 / c2a / c3 / c4 = dopri5 (tsit5) forward + adjoint training iterations (BASELINE.json configs[0], the
+  N = 1:  c1 / c2a / c2s (= c2a at 16 384 rows: the one-launch adaptive tensor-core integrator) / c3 / c4 = dopri5 (tsit5) forward + adjoint training iterations (BASELINE.json configs[0], the
           config-2 network with dopri5 + backsolve adjoint, configs[2], configs[3]), each with ms_per_iter,
           sample_nfe_per_s, nfe, roofline, cpu_baseline and gpu_eager_baseline;
   N > 1:  the SHARDED adaptive solves whose step controller couples the ranks: config 3 strong and weak (per-stage
@@ -207,7 +207,10 @@ def roofline_from(agg, step_ms, pk, traffic=None):
 # ----------------------------------------------------------------------------------------------------------------------
 # configs block, one GPU: the metric's own workloads (forward + adjoint training iterations)
 # ----------------------------------------------------------------------------------------------------------------------
-CONFIG_IDS = {"1": 1, "2a": 2, "3": 3, "4": 4, "5": 5}
+CONFIG_IDS = {"1": 1, "2a": 2, "2s": 2, "3": 3, "4": 4, "5": 5}
+# "2s": config 2a at 1/16 of the batch (16 384 rows) -- the size class of the ONE-LAUNCH adaptive tensor-core integrator
+# (tdyn_mlp_tc_solve_adaptive; above 32 768 rows the host-driven loop is faster and is what "2a" measures)
+CONFIG_SCALE = {"2s": 1.0 / 16}
 CPU_SCALE = {1: 1.0, 2: 1 / 32, 3: 1 / 32, 4: 1 / 8, 5: 1 / 32}       # sub-batch of the CPU leg (throughput is batch-linear)
 
 
@@ -215,8 +218,8 @@ def measure_config(key, dev, pk, iters=5, cpu=True, eager=True):
     import torchdyn_b200
     from benchmarks import run_configs as rc
     from torchdyn_b200 import _kernels, fused
-    cfg = CONFIG_IDS[key]
-    net, X, t_span, kw, loss_fn, name = rc.build(cfg, dev)
+    cfg, scale = CONFIG_IDS[key], CONFIG_SCALE.get(key, 1.0)
+    net, X, t_span, kw, loss_fn, name = rc.build(cfg, dev, scale)
     net = net.to(dev)
     model = torchdyn_b200.NeuralODE(net, **kw)
     x = X.to(dev)
@@ -266,10 +269,10 @@ def measure_config(key, dev, pk, iters=5, cpu=True, eager=True):
            "gpu_launches_per_iter": launches, "path": path, "roofline": roofline_from(agg, e0.elapsed_time(e1), pk)}
     del model
     if eager:
-        out["gpu_eager_baseline"] = eager_config(cfg, dev, B, nfe, out["sample_nfe_per_s"])
+        out["gpu_eager_baseline"] = eager_config(cfg, dev, B, nfe, out["sample_nfe_per_s"], scale)
     if cpu:
         try:
-            r = rc.run_cpu(cfg, 1, CPU_SCALE[cfg])
+            r = rc.run_cpu(cfg, 1, min(CPU_SCALE[cfg], scale))
             out["cpu_baseline"] = {"value": r["sample_nfe_per_s"], "unit": "sample-NFE/s", "cores": r["cores"], "kind": "port",
                                    "sample": f"{r['batch']} of {B} rows, one training iteration ({r['ms_per_iter'] / 1e3:.1f} s, "
                                              f"{r['nfe_per_iter']:.0f} NFE)"}
@@ -279,12 +282,12 @@ def measure_config(key, dev, pk, iters=5, cpu=True, eager=True):
     return out
 
 
-def eager_config(cfg, dev, B, nfe_b200, value_b200):
+def eager_config(cfg, dev, B, nfe_b200, value_b200, scale=1.0):
     """The oracle's op sequence (= the reference's: ~78 ATen launches per dopri5 step, autograd VJPs) with CUDA tensors."""
     from benchmarks import run_configs as rc
     from oracle import erk_oracle as eo
     try:
-        net, X, t_span, kw, loss_fn, _ = rc.build(cfg, dev)
+        net, X, t_span, kw, loss_fn, _ = rc.build(cfg, dev, scale)
         net = net.to(dev)
         x = X.to(dev)
         ts = t_span.to(dev)
@@ -434,7 +437,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help=argparse.SUPPRESS)
-    ap.add_argument("--configs", default="1,2a,3,4,5", help="configs block: comma-separated of 1,2a,3,4,5 or 'none'")
+    ap.add_argument("--configs", default="1,2a,2s,3,4,5", help="configs block: comma-separated of 1,2a,2s,3,4,5 or 'none'")
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-eager-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--force-generic", action="store_true", help="keep f a torch call (generic kernels only)")
