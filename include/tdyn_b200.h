@@ -237,7 +237,8 @@ TDYN_API int tdyn_mlp_tc_solve_fixed(const tdyn_mlp_t* mlp, const void* wsplit, 
  * (odeint.py:365-372) reduced across the grid by ONE grid barrier, and the fp32 step controller with the checkpoint
  * handling of odeint.py:352-401 (accept / reject, FSAL by swapping the roles of two stage buffers, adapt_step of
  * numerics/utils.py:57-63), computed identically by one thread of every CTA.  Rows are independent and every thread
- * re-reads only what it wrote itself: the error norm is the only grid-wide exchange.
+ * re-reads only what it wrote itself: the error norm is the only grid-wide exchange.  Any number of rows >= 1: one CTA per
+ * 128-row tile up to the SM count; a CTA that owns a single tile chains its stages serially.
  * `t_span`: HOST array of 2..1024 increasing times (already negated for a reversed span; `sign` = -1 then: every stage
  * derivative is sign*f, except init_step's trial evaluation, as in the reference).  x0 [rows*32] holds the initial state
  * on entry; x0 / x1 ping-pong, status[5] tells which one holds the final state.  `k`: 7 stage buffers of rows*32 floats.

@@ -887,6 +887,11 @@ def test_adaptive_tc_integrator_limits_fall_back_to_the_host_loop():
     ("dopri5", 40001, [0.0, 0.5, 1.5], dict(return_all_eval=True)),
     ("tsit5", 777, [1.0, 0.4, 0.0], {}),
     ("dopri5", 513, [0.0, 0.7], dict(act="softplus")),
+    ("dopri5", 1, [0.0, 1.0], {}),
+    ("tsit5", 100, [0.0, 0.4, 1.0], dict(return_all_eval=True)),
+    ("dopri5", 129, [1.0, 0.0], {}),
+    ("tsit5", 148 * 128 + 5, [0.0, 1.0], {}),
+    ("dopri5", 200 * 128, [0.0, 1.0], {}),
     ("tsit5", 2049, [0.0, 0.2, 0.9], dict(act="relu", return_all_eval=True)),
 ])
 def test_adaptive_tc_integrator_matches_the_host_driven_loop(solver, rows, ts, kw):

@@ -648,6 +648,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
     };
     auto x_adapt = [&]() -> const float* { return ADAPT ? (uniform_flag(cv->xcur != 0) ? P.xbuf[1] : P.xbuf[0]) : nullptr; };
     auto kmap_now = [&]() -> bool { return ADAPT ? uniform_flag(cv->swapped != 0) : false; };
+    // SERIAL mode (adaptive variant, a CTA that owns ONE row tile): consecutive work items are the same tile, so the stage input
+    // of item t + 1 needs the output of item t -- it is built after the output instead of under the first epilogue, the next
+    // item's layer 1 is issued after this item's layer 3, and the weight stages are streamed in that order (W2, W3, W1).
+    // Small batches then run one tile per SM instead of two tiles on half as many SMs.
+    const bool serial = ADAPT && my_tiles == 1;
     int gbase = 0;
     for (;;) {
         int n_items;
@@ -680,8 +685,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
                 load(0); load_w1b(gbase);
                 for (int t = 0; t < n_items; ++t) {
                     for (int s = 1; s <= 8; ++s) load(s);
-                    if (t + 1 < n_items) { load(0); load_w1b(gbase + t + 1); }
+                    if (!serial && t + 1 < n_items) { load(0); load_w1b(gbase + t + 1); }
                     load(9);
+                    if (serial && t + 1 < n_items) { load(0); load_w1b(gbase + t + 1); }
                 }
             }
         } else if (warp == 1) {
@@ -724,7 +730,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
                     }
                     tc_commit(bar(D2_FULL));
                     // ---- first 224 columns of the next item's layer 1: tensor work for the layer-2 -> 3 epilogue phase
-                    if (t + 1 < n_items) layer1a(gbase + t + 1);
+                    if (!serial && t + 1 < n_items) layer1a(gbase + t + 1);
                     // ---- layer 3: 8 K-blocks, N = 32, A_hi = Y -> D3 = X[224,256); W3 stage = 8 x [hi 4 KB | lo 4 KB]
                     {
                         const uint32_t ws = m_wit & 1, wu = m_wit >> 1;
@@ -746,6 +752,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
                     // ---- the last 32 columns of the next item's layer 1 overwrite D3: wait until it has been read out
                     if (t + 1 < n_items) {
                         mbar_wait(bar(D_FREE), (gbase + t) & 1);
+                        if (serial) layer1a(gbase + t + 1);          // (its stage input exists only after this item's output)
                         layer1b(gbase + t + 1);
                     }
                 }
@@ -844,7 +851,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
                         mbar_arrive(bar(A_FULL0 + as));
                         if (kPrefetch && j + 1 < kH / kKB) tmem_wait8(nxt);
                     }
-                    if (layer == 0 && t + 1 < n_items) {
+                    if (layer == 0 && t + 1 < n_items && !serial) {
                         // next item's stage input (A1 is free: this item's layer 1 has completed)
                         prologue(P, item_at(npass, nxt), !ADAPT && gbase == 0 && npass == 0, smem, w, ntile, x_adapt(), kmap_now());
                         mbar_arrive(bar(A1_FULL));
@@ -899,6 +906,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_stage_kernel(const __grid_
                                             add_rn(xq.z, mul_rn(P.dt0, s[4 * i + 2])), add_rn(xq.w, mul_rn(P.dt0, s[4 * i + 3])));
                         }
                     }
+                }
+                if (serial && t + 1 < n_items) {
+                    // serial mode: the next item is the next stage of the SAME tile -- its input needs the k just written
+                    prologue(P, item_at(npass, nxt), false, smem, w, ntile, x_adapt(), kmap_now());
+                    mbar_arrive(bar(A1_FULL));
                 }
                 pass = npass; tl = ntl; cur = nxt;
             }
@@ -1149,7 +1161,7 @@ int tdyn_mlp_tc_solve_adaptive(const tdyn_mlp_t* m, const void* wsplit, const td
                                int trace_cap, int64_t rows, int max_steps, void* stream) {
     TDYN_REQUIRE(m && plan && wsplit && t_span && x0 && x1 && k && out && t_out && workspace && status,
                  "tdyn_mlp_tc_solve_adaptive: null argument");
-    TDYN_REQUIRE(tdyn_mlp_tc_solve_supported(m, rows), "tdyn_mlp_tc_solve_adaptive: unsupported MLP shape or too few rows");
+    TDYN_REQUIRE(tdyn_mlp_tc_supported(m) && rows >= 1, "tdyn_mlp_tc_solve_adaptive: unsupported MLP shape or no rows");
     TDYN_REQUIRE(plan->n_extra >= 1 && plan->n_extra <= TDYN_MAX_STAGES - 1 && plan->n_err == plan->n_extra + 1 &&
                      plan->n_sol >= 1 && plan->n_sol <= plan->n_extra + 1,
                  "tdyn_mlp_tc_solve_adaptive: need an embedded FSAL pair (dopri5 / tsit5)");
@@ -1195,8 +1207,8 @@ int tdyn_mlp_tc_solve_adaptive(const tdyn_mlp_t* m, const void* wsplit, const td
     P.rows = rows;
     P.num_tiles = (int)((rows + tc::kTileM - 1) / tc::kTileM);
     P.act = m->act;
-    int grid = P.num_tiles / 2;
-    if (grid > kNumSMs) grid = kNumSMs;
+    // one CTA per row tile up to the SM count (a CTA with a single tile runs in serial mode, see the kernel)
+    int grid = P.num_tiles < kNumSMs ? P.num_tiles : kNumSMs;
     static thread_local unsigned long long seen = 0;
     if (first_use_on_device(seen)) {
         TDYN_CHECK_CUDA(cudaFuncSetAttribute(tc::mlp_tc_stage_kernel<TDYN_ACT_TANH, tc::kVarAdaptive>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal));

@@ -664,9 +664,10 @@ def try_adaptive(f_, x, ts, solver, atol, rtol, interpolator, return_all_eval, s
 ADAPTIVE_TC = True        # adaptive solves of the 32-256-256-32 class: one cooperative launch (False: host-driven loop)
 # The one-launch integrator builds every stage input in the prologue of its tile (x and up to 6 stage derivatives per row:
 # exposed L2 / DRAM latency, ~20 % of the worker warps' time in the ncu capture), the host-driven loop runs the stage
-# combination as its own HBM-bound launch.  Measured on B200 (benchmarks/k2_adaptive_ab.py, dopri5, 14 NFE): 4 096 rows 1.23
-# vs 1.47 ms, 16 384 rows 1.25 vs 1.46 ms, 65 536 rows 1.91 vs 1.77 ms, 2^20 rows 17.7 vs 12.6 ms -- so the one-launch form
-# takes the launch- / sync-bound sizes and the host loop the bandwidth-bound ones.  None: no limit (tests, A/B runs).
+# combination as its own HBM-bound launch.  Measured on B200 (benchmarks/k2_adaptive_ab.py, dopri5, 14 NFE): 4 096 rows 0.97
+# vs 1.30 ms, 16 384 rows 1.02 vs 1.29 ms, 32 768 rows 1.28 vs 1.34 ms, 65 536 rows 1.87 vs 1.71 ms, 2^20 rows 17.7 vs 12.6 ms
+# -- so the one-launch form takes the launch- / sync-bound sizes and the host loop the bandwidth-bound ones.  None: no limit
+# (tests, A/B runs).
 ADAPTIVE_TC_MAX_ROWS = 32768
 
 
@@ -679,7 +680,7 @@ def _try_adaptive_tc(inner, sign, x, ts, solver, atol, rtol, return_all_eval):
     rows, D = x.shape
     n_t = len(ts)
     if not ADAPTIVE_TC or _dist.is_enabled() or n_t > MAX_T_SPAN or not (ts[-1] > ts[0]) or x.data_ptr() % 16 \
-            or not kern.mlp_tc_solve_supported(fm._desc, rows) or (ADAPTIVE_TC_MAX_ROWS is not None and rows > ADAPTIVE_TC_MAX_ROWS):
+            or rows < 1 or (ADAPTIVE_TC_MAX_ROWS is not None and rows > ADAPTIVE_TC_MAX_ROWS):
         return None
     cap = n_t + (512 if return_all_eval else 0)
     dev = x.device
