@@ -855,6 +855,46 @@ def test_adaptive_tc_integrator_reproduces_the_reference_step_sequence(name):
         assert err <= max(10.0 * err_eager, 1e-5 * scale), (name, i, err, err_eager, scale)
 
 
+def test_adaptive_tc_entry_point_with_a_given_first_step():
+    """tdyn_mlp_tc_solve_adaptive with dt0 > 0 (k1 and the first step size supplied by the caller, init_step skipped)
+    reproduces the self-starting call bit for bit: states, output times, attempted steps."""
+    import sys
+    from torchdyn_b200 import fused
+    from torchdyn_b200.numerics.solvers.ode import DormandPrince45
+    om = sys.modules["torchdyn_b200.numerics.odeint"]
+    torch.manual_seed(23)
+    net = build_mlp([32, 256, 256, 32], "tanh").to(DEV)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(4.0)
+    x = torch.randn(700, 32, device=DEV)
+    fld = fused.MLPField(net)
+    ts = np.array([0.0, 0.6, 1.0], dtype=np.float32)
+    om.TRACE_SINK = tr = []
+    try:
+        with torch.no_grad():
+            t_ref, s_ref = odeint(fld, x, torch.tensor(ts), "dopri5", atol=1e-3, rtol=1e-3)
+    finally:
+        om.TRACE_SINK = None
+    assert "tdyn_mlp_tc_solve_adaptive" in fused.last_used()
+    kern = _kernels.get(x)
+    fm = fused._fused_of(net)
+    fm.begin_solve()
+    assert fm.ready(kern)
+    rows = x.shape[0]
+    x0, x1 = x.clone(), torch.empty_like(x)
+    k = torch.empty(7 * rows * 32, device=DEV)
+    kern.mlp_tc_stage(fm._desc, fm._img, k[:rows * 32].view(rows, 32), x0, [], (), MODE_INNER, 0.0, None, (), fm.flops_per_row)   # k1 = f(x0)
+    out, t_out = torch.empty(len(ts), rows, 32, device=DEV), torch.empty(len(ts), device=DEV)
+    status, trace = torch.zeros(8, dtype=torch.int32, device=DEV), torch.empty(3 * 64 + 1, device=DEV)
+    kern.mlp_tc_solve_adaptive(fm._desc, fm._img, fused._rk_plan(DormandPrince45()), 1.0, 1e-3, 1e-3, ts, False, tr[0]["dt0"], x0, x1, k,
+                               out, t_out, len(ts), kern.mlp_tc_adaptive_workspace(), status, trace, rows, 4000)
+    st = status.cpu().tolist()
+    assert st[4] == 0 and st[0] == len(ts) and st[1] == len(tr[0]["t"]), (st, len(tr[0]["t"]))
+    assert st[3] == 6 * st[1], st                     # no k1 / init_step evaluations inside this call
+    assert torch.equal(t_out, t_ref) and torch.equal(out, s_ref)
+
+
 def test_adaptive_tc_integrator_limits_fall_back_to_the_host_loop():
     """More attempts than one launch may take (fused.MAX_STEPS) or more accepted steps than the output buffer holds
     (return_all_eval): the kernel reports it in its status word and the host-driven loop redoes the solve -- same result
