@@ -36,6 +36,7 @@ __device__ __forceinline__ void matvec_t(const Net& net, const float* w_s, int l
         const int g = i / K, k = i - g * K;
         const float* wc = w_s + net.w_off[l] + k;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
         for (int nn = 0; nn < N; ++nn) {
             const float w = wc[nn * ld];
             const float4 sv = *reinterpret_cast<const float4*>(src + nn * kLd + 4 * g);
@@ -61,6 +62,8 @@ __device__ __forceinline__ void matvec(const Net& net, const float* w_s, int l, 
         const int g = i / N, n = i - g * N;
         const float* wr = w_s + net.w_off[l] + n * ld;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // (unrolled: eight iterations' shared-memory loads are in flight before their FFMAs; the accumulation order is unchanged)
+#pragma unroll 8
         for (int k = 0; k < K; ++k) {
             const float w = wr[k];
             const float4 sv = *reinterpret_cast<const float4*>(src + k * kLd + 4 * g);

@@ -186,6 +186,8 @@ __device__ __forceinline__ void forward_tile(const Net& net, const float* w_s, f
                 const float* wr = w_s + net.w_off[l] + n * ld;
                 const float bias = w_s[net.b_off[l] + n];
                 float4 acc = make_float4(bias, bias, bias, bias);
+                // (unrolled: eight iterations' shared-memory loads are in flight before their FFMAs; the accumulation order is unchanged)
+#pragma unroll 8
                 for (int k = 0; k < K; ++k) {
                     const float w = wr[k];
                     const float4 hv = *reinterpret_cast<const float4*>(hin + k * kLd + 4 * g);
@@ -302,6 +304,7 @@ __device__ __forceinline__ float* backward_tile(const Net& net, const float* w_s
             const int g = i / K, k = i - g * K;
             const float* wc = w_s + net.w_off[l] + k;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
             for (int nn = 0; nn < N; ++nn) {
                 const float w = wc[nn * ld];
                 const float4 dv = *reinterpret_cast<const float4*>(dcur + nn * kLd + 4 * g);
