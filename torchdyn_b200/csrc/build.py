@@ -39,14 +39,19 @@ def up_to_date() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB
-    objs = []
-    for src in sources():
+    objs, procs = [], []
+    for src in sources():                   # the translation units are independent: compile them side by side
         obj = src[:-3] + ".o"
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
-        subprocess.run(cmd, check=True)
+            subprocess.run(cmd, check=True)     # (serial: ptxas -v output stays readable)
+        else:
+            procs.append((cmd, subprocess.Popen(cmd)))
         objs.append(obj)
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
     cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart_static", "-lcuda", "-lpthread", "-ldl", "-lrt"]
     if verbose:
         print(" ".join(cmd), flush=True)
