@@ -895,6 +895,26 @@ def test_adaptive_tc_entry_point_with_a_given_first_step():
     assert torch.equal(t_out, t_ref) and torch.equal(out, s_ref)
 
 
+def test_adaptive_tc_integrator_on_a_side_stream():
+    """The one-launch integrator launches on PyTorch's CURRENT stream (cooperative launch, memsets and copies included):
+    same result on a side stream as on the default stream."""
+    from torchdyn_b200 import fused
+    torch.manual_seed(24)
+    net = build_mlp([32, 256, 256, 32], "tanh").to(DEV)
+    x = torch.randn(900, 32, device=DEV)
+    fld = fused.MLPField(net)
+    ts = torch.tensor([0.0, 0.5, 1.0])
+    with torch.no_grad():
+        t_a, s_a = odeint(fld, x, ts, "tsit5", atol=1e-4, rtol=1e-4)
+        side = torch.cuda.Stream(device=DEV)
+        side.wait_stream(torch.cuda.current_stream(DEV))
+        with torch.cuda.stream(side):
+            t_b, s_b = odeint(fld, x, ts, "tsit5", atol=1e-4, rtol=1e-4)
+        side.synchronize()
+    assert "tdyn_mlp_tc_solve_adaptive" in fused.last_used()
+    assert torch.equal(t_a, t_b) and torch.equal(s_a, s_b)
+
+
 def test_adaptive_tc_integrator_limits_fall_back_to_the_host_loop():
     """More attempts than one launch may take (fused.MAX_STEPS) or more accepted steps than the output buffer holds
     (return_all_eval): the kernel reports it in its status word and the host-driven loop redoes the solve -- same result
@@ -927,6 +947,7 @@ def test_adaptive_tc_integrator_limits_fall_back_to_the_host_loop():
     ("dopri5", 40001, [0.0, 0.5, 1.5], dict(return_all_eval=True)),
     ("tsit5", 777, [1.0, 0.4, 0.0], {}),
     ("dopri5", 513, [0.0, 0.7], dict(act="softplus")),
+    ("dopri5", 300, [float(v) for v in np.linspace(0.0, 1.0, 61)], {}),
     ("dopri5", 1, [0.0, 1.0], {}),
     ("tsit5", 100, [0.0, 0.4, 1.0], dict(return_all_eval=True)),
     ("dopri5", 129, [1.0, 0.0], {}),
