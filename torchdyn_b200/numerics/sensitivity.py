@@ -170,8 +170,10 @@ def _gather_odefunc_adjoint(vf, vf_params, solver, atol, rtol, interpolator, sol
             A = torch.cat([xT.flatten(), lam_flat, torch.zeros(P, dtype=xT.dtype, device=xT.device), lam_t[None]])
             dyn = BacksolveDynamics(vf, xT.shape, lamT.shape, P, integral_loss, device=xT.device)
 
-            dLdt = torch.zeros(len(th), dtype=xT.dtype, device=xT.device)
-            dLdt[-1] = lam_t
+            # (the reference fills a dLdt vector over all of t_sol and hands back its two end points, sensitivity.py:78-98: only
+            # those two are kept here, and the last interval does not re-assemble a flat A that nobody integrates)
+            dLdt_last, dLdt_first = lam_t, lam_t
+            lam = mu = None
             for i in range(len(th) - 1, 0, -1):
                 last = fused.try_adjoint_interval(dyn, A, th[i], th[i - 1], solver_adjoint, atol_adjoint, rtol_adjoint)
                 if last is None:
@@ -179,12 +181,15 @@ def _gather_odefunc_adjoint(vf, vf_params, solver, atol, rtol, interpolator, sol
                                    atol=atol_adjoint, rtol=rtol_adjoint, seminorm=(True, 2 * n))
                     last = As[-1]
                 xt = last[:n].reshape(xT.shape)
-                dLdt[i - 1] = last[n:2 * n] @ fused.eval_field(vf, t_sol[i], xt.contiguous()).flatten()   # index i: reference quirk (:88)
-                lt = last[-1:] - g_t[i - 1]
-                A = torch.cat([last[:n], last[n:2 * n] + g_sol[i - 1].flatten(), last[-P - 1:-1], lt])
-            lam = A[n:2 * n].reshape(lamT.shape)
-            mu = A[-P - 1:-1]
-            return (mu, lam, torch.stack([dLdt[0], dLdt[-1]]), None, None, None)
+                # (evaluated at every interval like the reference does -- it is an NFE there too; index i: reference quirk, :88)
+                dLdt_first = last[n:2 * n] @ fused.eval_field(vf, t_sol[i], xt.contiguous()).flatten()
+                if i == 1:
+                    lam = (last[n:2 * n] + g_sol[0].flatten()).reshape(lamT.shape)
+                    mu = last[-P - 1:-1]
+                else:
+                    lt = last[-1:] - g_t[i - 1]
+                    A = torch.cat([last[:n], last[n:2 * n] + g_sol[i - 1].flatten(), last[-P - 1:-1], lt])
+            return (mu, lam, torch.stack([dLdt_first, dLdt_last]), None, None, None)
 
     return _ODEProblemFunc
 
