@@ -33,10 +33,6 @@ def generic_odeint(problem_type, vf, x, t_span, solver, atol, rtol, interpolator
     raise NotImplementedError(f"problem_type {problem_type!r} (multiple shooting) is outside torchdyn_b200's scope")
 
 
-def _flat(vf):
-    return torch.cat([p.contiguous().flatten() for p in vf.parameters()])
-
-
 def _time(t_host, like):
     return torch.full((), float(t_host), dtype=like.dtype, device=like.device)
 
