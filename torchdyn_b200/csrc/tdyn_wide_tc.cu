@@ -140,10 +140,17 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
-    const int my_tiles = (P.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int nchunks = P.N / P.Nc;
     const int nkb = P.K / kKB;
-    const int items = my_tiles * nchunks;           // item = (row tile, output chunk); chunk is the fast index
+    // Work items = (row tile, output chunk), chunk the fast index; a CTA takes a CONTIGUOUS range [g0, g1) of the global
+    // item list, so that the CTAs' loads differ by at most one item (whole tiles per CTA lose up to half of the machine
+    // when there are fewer than ~3 tiles per SM: 256 tiles on 148 SMs).  A tile whose chunks are split between two CTAs
+    // has its A operand produced by both.
+    const long long total_items = (long long)P.num_tiles * nchunks;
+    const int g0 = (int)(total_items * blockIdx.x / gridDim.x), g1 = (int)(total_items * (blockIdx.x + 1) / gridDim.x);
+    const int items = g1 - g0;
+    const int tile_first = g0 / nchunks;
+    const int my_tiles = items > 0 ? (g1 - 1) / nchunks - tile_first + 1 : 0;       // distinct row tiles in the range
     const bool resident = nkb <= kASlots;           // A of a row tile fits the TMEM ring: produced once per tile
     const uint32_t aring = resident ? (uint32_t)nkb : (uint32_t)kASlots;
     const uint32_t slab = (uint32_t)P.Nc * 256u;
@@ -153,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
         if (lane == 0) {
             uint32_t it = 0;
             for (int item = 0; item < items; ++item) {
-                const int c = item % nchunks;
+                const int c = (g0 + item) % nchunks;
                 const uint8_t* src = P.img + (size_t)c * nkb * slab;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t slot = it % kBStages, use = it / kBStages;
@@ -174,21 +181,22 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
                     tc_fence_after();
                     const uint32_t d = tmem + (buf ? kColAcc1 : kColAcc0);
                     const int kb1 = kb0 + kSegKB < nkb ? kb0 + kSegKB : nkb;
-                    const int c = item % nchunks;
+                    const int c = (g0 + item) % nchunks;
+                    const bool tile_begin = c == 0 || item == 0, tile_end = c == nchunks - 1 || item == items - 1;   // ... of MY share of the tile
                     for (int kb = kb0; kb < kb1; ++kb, ++bit) {
                         const uint32_t as = ait % aring, au = ait / aring, bs = bit % kBStages, bu = bit / kBStages;
-                        if (!resident || c == 0) mbar_wait(bar(LA_FULL0 + as), au & 1);
+                        if (!resident || tile_begin) mbar_wait(bar(LA_FULL0 + as), au & 1);
                         mbar_wait(bar(LB_FULL0 + bs), bu & 1);
                         tc_fence_after();
                         const uint32_t a_hi = tmem + kColA + as * 64u;
                         const uint32_t b_hi = sbase + kLSmemB + bs * kBStage;
                         issue_kblock_tt(d, a_hi, b_hi, b_hi + slab / 2, P.Nc, kb == kb0);
-                        if (!resident || c == nchunks - 1) tc_commit(bar(LA_EMPTY0 + as));
+                        if (!resident || tile_end) tc_commit(bar(LA_EMPTY0 + as));
                         tc_commit(bar(LB_EMPTY0 + bs));
                         // resident: the ring position runs over (tile, kb) only and is rewound for every further chunk
                         ++ait;
                     }
-                    if (resident && kb1 == nkb && c != nchunks - 1) ait -= (uint32_t)nkb;
+                    if (resident && kb1 == nkb && !tile_end) ait -= (uint32_t)nkb;
                     tc_commit(bar(LACC_FULL0 + buf));
                 }
             }
@@ -200,10 +208,9 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
         const int row = quarter * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + kColA;
         const int total = (resident ? my_tiles : items) * nkb;
-        const int per_tile = resident ? 1 : nchunks;
         auto load = [&](float4 (&r)[4], int n) {
-            const int item = n / nkb, kb = n - item * nkb;
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)(item / per_tile) * gridDim.x;
+            const int item = n / nkb, kb = n - item * nkb;        // resident: item = tile index inside my range
+            const int64_t tile = resident ? tile_first + item : (g0 + item) / nchunks;
             const int64_t grow = tile * kTileM + row;
             if (grow < P.rows) {
                 const float4* p = reinterpret_cast<const float4*>(P.in + (size_t)grow * P.K + kb * kKB + cg * 16);
@@ -263,9 +270,9 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
         uint32_t sc = 0;
         float4 sv[4];                                             // saved activations of the NEXT pass (MODE_DACT)
         auto fetch_saved = [&](int item, int pass) {
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)(item / nchunks) * gridDim.x;
+            const int64_t tile = (g0 + item) / nchunks;
             const int64_t row0 = tile * kTileM + quarter * 32;
-            const int n0 = (item % nchunks) * P.Nc + half * ncol + pass * 16;
+            const int n0 = ((g0 + item) % nchunks) * P.Nc + half * ncol + pass * 16;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int64_t r = row0 + i * 8 + lr;
@@ -275,8 +282,8 @@ __global__ void __launch_bounds__(kThreads, 1) lin_tc_kernel(const LinParams P) 
         };
         if (MODE == MODE_DACT && items > 0) fetch_saved(0, 0);
         for (int item = 0; item < items; ++item) {
-            const int c = item % nchunks;
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)(item / nchunks) * gridDim.x;
+            const int c = (g0 + item) % nchunks;
+            const int64_t tile = (g0 + item) / nchunks;
             const int64_t row0 = tile * kTileM + quarter * 32;    // first row of this warp
             const int n0 = c * P.Nc + half * ncol;
             for (int seg = 0; seg < nseg; ++seg, ++sc) {
@@ -730,7 +737,8 @@ int tdyn_lin_tc_apply(const void* img, int n_out, int k_in, const float* in, con
     P.img = (const uint8_t*)img; P.in = in; P.bias = bias; P.saved = saved; P.out = out;
     P.N = n_out; P.K = k_in; P.Nc = wtc::chunk_of(n_out); P.scale = scale; P.rows = rows;
     P.num_tiles = (int)((rows + tcx::kTileM - 1) / tcx::kTileM);
-    const int grid = P.num_tiles < kNumSMs ? P.num_tiles : kNumSMs;
+    const long long total_items = (long long)P.num_tiles * (n_out / P.Nc);       // (row tile, output chunk) items, spread evenly
+    const int grid = total_items < kNumSMs ? (int)total_items : kNumSMs;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == wtc::MODE_LIN) return launch_lin<TDYN_ACT_TANH, wtc::MODE_LIN>(P, grid, st);
     if (mode == wtc::MODE_ACT) {
